@@ -1,0 +1,315 @@
+// dmvae_common.cuh - shared device/host infrastructure of libdmvae (sm_100a only).
+//
+//   * Layout      : offsets of the 24 state_dict tensors (torch layout) and of the
+//                   kernel-layout ("packed") weight arena.
+//   * WeightRing  : weights are streamed L2 -> shared memory by a dedicated producer
+//                   warp with TMA bulk copies (cp.async.bulk, completion on an
+//                   mbarrier) through a ring of 32 KB stages; the eight consumer warps
+//                   wait on the "full" barrier of a stage, run FFMA over it and release
+//                   it through the "empty" barrier.
+//   * gemm_chunk  : the one FFMA primitive,  C[i][j] += sum_c P[c][i] * Q[c][j],
+//                   both operands contraction-major in shared memory, register-tiled
+//                   (4*GI) x (VJ*GJ) per thread with 128-bit shared loads.
+//   * gemm_nt4    : C[i][j] += sum_c P[i][c] * Q[j][c] (both operands vectorised
+//                   along the contraction), used by the weight-gradient GEMMs.
+//   * Philox4x32-10 + Box-Muller for in-kernel latent / reparameterisation noise.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dmvae.h"
+
+namespace dmvae {
+
+constexpr int H = 128;             // hidden width (every shipped checkpoint)
+constexpr int NUM_LAYERS = 11;     // cond0 cond1 enc0 enc1 enc2 enc3 heads dec0 dec1 dec2 dec3
+constexpr int CONSUMER_WARPS = 8;
+constexpr int CONSUMER_THREADS = CONSUMER_WARPS * 32;
+constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;  // + one producer warp
+constexpr int STAGE_FLOATS = 8192;                    // 32 KB ring stage
+constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+
+enum LayerId { L_COND0 = 0, L_COND1, L_ENC0, L_ENC1, L_ENC2, L_ENC3, L_HEADS, L_DEC0, L_DEC1, L_DEC2, L_DEC3 };
+
+__host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Offsets in floats.  Torch layout ("p_*") follows the state_dict order
+// (Training_VAE.py:132-167); the packed arena ("q_*") holds, per layer, the
+// transposed weight Wt[k][Np] (k-major, N padded with zeros to Np) followed by the
+// bias padded to Np.  The heads layer packs fc_mu and fc_logvar side by side
+// (columns [0,L) = mu, [L,2L) = logvar); rows [0,128) multiply h_traj, [128,256) h_c
+// (Training_VAE.py:193).  dec0 rows [0,L) multiply z, [L,L+128) h_c (:214).
+struct Layout {
+  int T, L, I;      // seq_len, latent_dim, 3*seq_len
+  int Ip;           // I padded: 32, 64 or 128
+  int L2p;          // 2L padded: 32, 64 or 128
+  int n_params;
+  int n_packed;
+  int p_w[NUM_LAYERS];   // heads: fc_mu.weight
+  int p_b[NUM_LAYERS];   // heads: fc_mu.bias
+  int p_wlv, p_blv;      // fc_logvar.weight / bias
+  int K[NUM_LAYERS];     // contraction length of the forward GEMM
+  int N[NUM_LAYERS];     // true output width
+  int Np[NUM_LAYERS];    // padded output width
+  int q_w[NUM_LAYERS];
+  int q_b[NUM_LAYERS];
+  // data-gradient operands: aligned copies W[n][k] (n-major = contraction-major for
+  // dX = dY * W).  r_w[l] < 0 for layers whose input needs no gradient (cond0, enc0).
+  // heads: [2L][256] (mu rows then logvar rows); dec0: the h_c part [128][128] with the
+  // z part [128][Lq] (Lq = L rounded up to 4, zero padded) at r_dec0z.
+  int r_w[NUM_LAYERS];
+  int r_dec0z, Lq;
+};
+
+__host__ __device__ inline int pad_width(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
+
+// Returns 0 on success, DMVAE_ERR_SHAPE when outside the envelope.
+inline int make_layout(const DmvaeCfg* c, Layout* lo) {
+  if (!c || c->dim != 3 || c->hidden_dim != H) return DMVAE_ERR_SHAPE;
+  if (c->latent_dim < 1 || c->latent_dim > 64) return DMVAE_ERR_SHAPE;
+  if (c->seq_len < 2 || c->seq_len * 3 > 128) return DMVAE_ERR_SHAPE;
+  Layout& l = *lo;
+  l.T = c->seq_len; l.L = c->latent_dim; l.I = 3 * l.T;
+  l.Ip = pad_width(l.I); l.L2p = pad_width(2 * l.L);
+  const int Ks[NUM_LAYERS] = {2, H, l.I, H, H, H, 2 * H, l.L + H, H, H, H};
+  const int Ns[NUM_LAYERS] = {H, H, H, H, H, H, 2 * l.L, H, H, H, l.I};
+  int p = 0, q = 0;
+  for (int i = 0; i < NUM_LAYERS; ++i) {
+    l.K[i] = Ks[i]; l.N[i] = Ns[i];
+    l.Np[i] = (i == L_HEADS) ? l.L2p : (i == L_DEC3 ? l.Ip : H);
+    if (i == L_HEADS) {
+      l.p_w[i] = p; p += l.L * 2 * H;
+      l.p_b[i] = p; p += l.L;
+      l.p_wlv = p; p += l.L * 2 * H;
+      l.p_blv = p; p += l.L;
+    } else {
+      l.p_w[i] = p; p += Ns[i] * Ks[i];
+      l.p_b[i] = p; p += Ns[i];
+    }
+    l.q_w[i] = q; q += round_up(Ks[i] * l.Np[i], 4);
+    l.q_b[i] = q; q += l.Np[i];
+  }
+  l.n_params = p;
+  q = round_up(q, 4);
+  l.Lq = round_up(l.L, 4);
+  for (int i = 0; i < NUM_LAYERS; ++i) {
+    if (i == L_COND0 || i == L_ENC0) { l.r_w[i] = -1; continue; }
+    l.r_w[i] = q;
+    if (i == L_HEADS) q += 2 * l.L * 2 * H;
+    else if (i == L_DEC3) q += l.I * H;
+    else q += H * H;
+    q = round_up(q, 4);
+  }
+  l.r_dec0z = q; q += H * l.Lq;
+  l.n_packed = round_up(q, 4);
+  return DMVAE_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// PTX helpers: mbarrier, TMA bulk copy, named barrier, cp.async
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni DONE_%=;\n\t"
+      "bra.uni WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(addr), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Barrier among the consumer warps only (the producer warp never joins it).
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_THREADS) : "memory"); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// --------------------------------------------------------------------------------------
+// Weight ring
+// --------------------------------------------------------------------------------------
+// One streamed operand: `rows` contraction rows of `width` floats each, contiguous
+// in global memory from `src`, cut into chunks of `rows_per_chunk` rows.
+struct StreamOp {
+  const float* src;
+  int rows;
+  int width;
+  __device__ __forceinline__ int rows_per_chunk() const { return STAGE_FLOATS / width; }
+};
+
+template <int STAGES>
+struct RingState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+  }
+};
+
+// Producer side (one elected lane of the producer warp).
+template <int STAGES>
+__device__ __forceinline__ void produce_op(const StreamOp& op, float* ring, uint64_t* full, uint64_t* empty,
+                                           RingState<STAGES>& rs) {
+  const int rpc = op.rows_per_chunk();
+  for (int r0 = 0; r0 < op.rows; r0 += rpc) {
+    const int rows = min(rpc, op.rows - r0);
+    const uint32_t bytes = (uint32_t)(rows * op.width * 4);
+    mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+    mbar_arrive_expect_tx(&full[rs.stage], bytes);
+    tma_load_1d(ring + rs.stage * STAGE_FLOATS, op.src + (size_t)r0 * op.width, bytes, &full[rs.stage]);
+    rs.advance();
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// FFMA GEMM primitives
+// --------------------------------------------------------------------------------------
+// Thread tile (4*GI) x (VJ*GJ); lanes are 8 (i) x 4 (j) with lane = tj*8 + ti so that
+// every quarter-warp of a 128-bit P load reads 128 contiguous bytes and every
+// quarter-warp of a Q load reads one address (broadcast).  i-groups are 32 apart,
+// j-groups 4*VJ apart.  Warps are WI x WJ.
+template <int GI_, int GJ_, int VJ_, int WI_, int WJ_>
+struct TileCfg {
+  static constexpr int GI = GI_, GJ = GJ_, VJ = VJ_, WI = WI_, WJ = WJ_;
+  static constexpr int TI = 4 * GI, TJ = VJ * GJ;
+  static constexpr int SI = 32, SJ = 4 * VJ;
+  static constexpr int I = WI * GI * 32, J = WJ * GJ * SJ;
+  static constexpr int ACTIVE_WARPS = WI * WJ;
+  static_assert(ACTIVE_WARPS <= CONSUMER_WARPS, "too many warps");
+  __device__ static __forceinline__ bool active(int warp) { return warp < ACTIVE_WARPS; }
+  __device__ static __forceinline__ int i0(int warp, int lane) { return (warp % WI) * (GI * 32) + (lane & 7) * 4; }
+  __device__ static __forceinline__ int j0(int warp, int lane) { return (warp / WI) * (GJ * SJ) + (lane >> 3) * VJ; }
+};
+
+// Forward / data-gradient tiles: I = rows of the batch tile, J = output features.
+template <int M, int N> struct FwdCfg;
+template <> struct FwdCfg<128, 128> : TileCfg<2, 2, 4, 2, 4> {};
+template <> struct FwdCfg<128, 64> : TileCfg<2, 1, 4, 2, 4> {};
+template <> struct FwdCfg<128, 32> : TileCfg<1, 2, 2, 4, 2> {};
+template <> struct FwdCfg<64, 128> : TileCfg<1, 2, 4, 2, 4> {};
+template <> struct FwdCfg<64, 64> : TileCfg<1, 1, 4, 2, 4> {};
+template <> struct FwdCfg<64, 32> : TileCfg<1, 1, 2, 2, 4> {};
+template <> struct FwdCfg<32, 128> : TileCfg<1, 1, 4, 1, 8> {};
+template <> struct FwdCfg<32, 64> : TileCfg<1, 1, 2, 1, 8> {};
+template <> struct FwdCfg<32, 32> : TileCfg<1, 1, 1, 1, 8> {};
+
+template <int V> struct VecLoad;
+template <> struct VecLoad<4> {
+  __device__ static __forceinline__ void ld(float* d, const float* s) {
+    const float4 v = *reinterpret_cast<const float4*>(s);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+};
+template <> struct VecLoad<2> {
+  __device__ static __forceinline__ void ld(float* d, const float* s) {
+    const float2 v = *reinterpret_cast<const float2*>(s);
+    d[0] = v.x; d[1] = v.y;
+  }
+};
+template <> struct VecLoad<1> {
+  __device__ static __forceinline__ void ld(float* d, const float* s) { d[0] = *s; }
+};
+
+// acc[i][j] += sum_{c<rows} P[c*ldp + i] * Q[c*ldq + j]   (P, Q already offset to the
+// thread's i0 / j0).
+template <class C>
+__device__ __forceinline__ void gemm_chunk(float (&acc)[C::TI][C::TJ], const float* __restrict__ P, int ldp,
+                                           const float* __restrict__ Q, int ldq, int rows) {
+#pragma unroll 4
+  for (int c = 0; c < rows; ++c) {
+    float a[C::TI], b[C::TJ];
+#pragma unroll
+    for (int g = 0; g < C::GI; ++g) VecLoad<4>::ld(&a[4 * g], P + c * ldp + g * C::SI);
+#pragma unroll
+    for (int g = 0; g < C::GJ; ++g) VecLoad<C::VJ>::ld(&b[C::VJ * g], Q + c * ldq + g * C::SJ);
+#pragma unroll
+    for (int i = 0; i < C::TI; ++i)
+#pragma unroll
+      for (int j = 0; j < C::TJ; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+
+template <class C>
+__device__ __forceinline__ void zero_acc(float (&acc)[C::TI][C::TJ]) {
+#pragma unroll
+  for (int i = 0; i < C::TI; ++i)
+#pragma unroll
+    for (int j = 0; j < C::TJ; ++j) acc[i][j] = 0.f;
+}
+
+// Consume one streamed operand: acc += P[rows][.]^T * ring chunks.  Every consumer
+// warp waits and releases every chunk, also warps that own no output of this tile
+// shape, so that the ring protocol is independent of the tile configuration.
+template <class C, int STAGES>
+__device__ __forceinline__ void consume_op(float (&acc)[C::TI][C::TJ], const float* __restrict__ P, int ldp,
+                                           int rows, int width, const float* ring, uint64_t* full,
+                                           uint64_t* empty, RingState<STAGES>& rs, int warp, int lane) {
+  const int rpc = STAGE_FLOATS / width;
+  const bool act = C::active(warp);
+  const int i0 = C::i0(warp, lane), j0 = C::j0(warp, lane);
+  for (int r0 = 0; r0 < rows; r0 += rpc) {
+    const int n = min(rpc, rows - r0);
+    mbar_wait(&full[rs.stage], rs.phase);
+    if (act) gemm_chunk<C>(acc, P + r0 * ldp + i0, ldp, ring + rs.stage * STAGE_FLOATS + j0, width, n);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[rs.stage]);
+    rs.advance();
+  }
+}
+
+// --------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) + Box-Muller
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) {  // (0, 1)
+  return (float)(x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);
+}
+// Four standard normals for (sample, block); stream distinguishes z / eps / step.
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample, uint32_t block, uint32_t stream) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)sample, (uint32_t)(sample >> 32), block, stream),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float r0 = sqrtf(-2.0f * logf(u01(r.x))), r1 = sqrtf(-2.0f * logf(u01(r.z)));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u01(r.y), &s0, &c0);
+  sincospif(2.0f * u01(r.w), &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+}  // namespace dmvae

@@ -1,0 +1,115 @@
+"""ctypes binding of libdmvae.so (the C ABI in include/dmvae.h).
+
+The library is built in-tree by ``defensive-model-vae_b200/csrc/build.sh``
+(``__graft_entry__.build()``).  There is no CPU implementation behind this
+module: if the shared object is missing, or the device is not a B200, every
+compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libdmvae.so")
+
+
+class DmvaeError(RuntimeError):
+    pass
+
+
+class DmvaeCfg(ctypes.Structure):
+    _fields_ = [("seq_len", c_int32), ("dim", c_int32), ("latent_dim", c_int32), ("hidden_dim", c_int32)]
+
+
+class DmvaeLossWeights(ctypes.Structure):
+    _fields_ = [("recon", c_float), ("kld", c_float), ("start", c_float), ("time", c_float)]
+
+
+class DmvaeAdam(ctypes.Structure):
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("step", c_int64)]
+
+
+# name -> (restype, argtypes); mirrors include/dmvae.h one to one
+_P = c_void_p
+_CFG = POINTER(DmvaeCfg)
+SIGNATURES = {
+    "dmvae_abi_version": (c_int, []),
+    "dmvae_last_error": (c_char_p, []),
+    "dmvae_device_sm_count": (c_int, []),
+    "dmvae_param_count": (c_int64, [_CFG]),
+    "dmvae_param_offset": (c_int64, [_CFG, c_int]),
+    "dmvae_packed_count": (c_int64, [_CFG]),
+    "dmvae_pack_weights": (c_int, [_CFG, _P, _P, _P]),
+    "dmvae_decode": (c_int, [_CFG, _P, _P, c_uint64, c_uint64, _P, c_int, _P, _P, c_int64, c_int, _P]),
+    "dmvae_grad_count": (c_int64, [_CFG]),
+    "dmvae_train_workspace_bytes": (c_int64, [_CFG, c_int64]),
+    "dmvae_train_fwd_bwd": (c_int, [_CFG, _P, _P, _P, _P, c_uint64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
+                                    c_float, c_int64, _P, _P, _P]),
+    "dmvae_adam_step": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P]),
+    "dmvae_stash_bytes": (c_int64, [_CFG, c_int64]),
+    "dmvae_forward": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "dmvae_backward": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "dmvae_loss": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeLossWeights), c_int64, _P, _P, _P, _P, _P]),
+    "dmvae_cond_encode": (c_int, [_CFG, _P, _P, _P, c_int64, _P]),
+    "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
+}
+
+_lib = None
+# TODO(round 1, in progress): entry points being brought up; emptied once they land
+_PENDING = {"dmvae_grad_count", "dmvae_train_workspace_bytes", "dmvae_train_fwd_bwd", "dmvae_adam_step",
+            "dmvae_stash_bytes", "dmvae_forward", "dmvae_backward", "dmvae_loss"}
+
+
+def lib() -> ctypes.CDLL:
+    """Load libdmvae.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DmvaeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or defensive-model-vae_b200/csrc/build.sh).  dmvae has no CPU or PyTorch fallback.")
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        if name in _PENDING and not hasattr(handle, name):
+            continue
+        fn = getattr(handle, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    got = handle.dmvae_abi_version()
+    if got != 1:
+        raise DmvaeError(f"libdmvae ABI version {got}, expected 1")
+    _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().dmvae_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> int:
+    if rc < 0:
+        raise DmvaeError(f"{what} failed ({rc}): {last_error()}")
+    return rc
+
+
+def cfg(seq_len: int, latent_dim: int, dim: int = 3, hidden_dim: int = 128) -> DmvaeCfg:
+    return DmvaeCfg(int(seq_len), int(dim), int(latent_dim), int(hidden_dim))
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+__all__ = ["lib", "check", "cfg", "ptr", "stream_ptr", "byref", "DmvaeCfg", "DmvaeLossWeights", "DmvaeAdam",
+           "DmvaeError", "SIGNATURES", "LIB_PATH", "last_error"]

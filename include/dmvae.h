@@ -1,0 +1,160 @@
+/*
+ * dmvae.h - C ABI of the B200-native trajectory-VAE hot path (libdmvae.so).
+ *
+ * The reference (yslf2035/Defensive-Model-VAE) has no FFI/plugin interface for
+ * this path: every call below replaces a chain of PyTorch-CPU ops that the
+ * reference issues from Python.  Each entry point cites the reference lines it
+ * stands in for (paths relative to the reference root).  The Python drop-in
+ * modules (Training_VAE.py, Tools.py at the repo root) bind these symbols with
+ * ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (in practice
+ *     torch-owned), fp32, contiguous, 16-byte aligned unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous with respect to the host and ordered on `stream`;
+ *   - return value 0 = success, negative = error (dmvae_last_error() describes
+ *     the last error of the calling thread); no exception crosses the ABI;
+ *   - the library allocates no persistent device memory: the caller sizes the
+ *     workspaces with the *_bytes()/ *_count() queries;
+ *   - sm_100 (B200) only.  On any other device every compute call returns
+ *     DMVAE_ERR_DEVICE.  There is no CPU path.
+ *
+ * Shape envelope: dim == 3, hidden_dim == 128,
+ * 1 <= latent_dim <= 64, 2 <= seq_len with 3*seq_len <= 128 in this ABI version.
+ */
+#ifndef DMVAE_H_
+#define DMVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMVAE_ABI_VERSION 1
+
+#define DMVAE_OK 0
+#define DMVAE_ERR_SHAPE (-1)   /* configuration outside the supported envelope */
+#define DMVAE_ERR_ARG (-2)     /* null / misaligned pointer, bad size */
+#define DMVAE_ERR_DEVICE (-3)  /* no sm_100 device / wrong device */
+#define DMVAE_ERR_CUDA (-4)    /* a CUDA runtime call failed */
+
+/* ConditionalTrajectoryVAE(seq_len, dim, latent_dim, hidden_dim=128)
+ * (Training_VAE.py:124-129). */
+typedef struct DmvaeCfg {
+  int32_t seq_len;
+  int32_t dim;
+  int32_t latent_dim;
+  int32_t hidden_dim;
+} DmvaeCfg;
+
+/* conditional_vae_loss weights (Training_VAE.py:229, :300-306). */
+typedef struct DmvaeLossWeights {
+  float recon;
+  float kld;
+  float start;
+  float time;
+} DmvaeLossWeights;
+
+/* torch.optim.Adam hyper-parameters (Training_VAE.py:332; torch optim/adam.py). */
+typedef struct DmvaeAdam {
+  float lr;
+  float beta1;
+  float beta2;
+  float eps;
+  int64_t step; /* 1-based index of the update being applied */
+} DmvaeAdam;
+
+int dmvae_abi_version(void);
+const char* dmvae_last_error(void);
+/* Number of SMs of the current device, or a negative error. */
+int dmvae_device_sm_count(void);
+
+/* ---- layouts ------------------------------------------------------------- */
+/* Number of fp32 parameters in state_dict order (Training_VAE.py:132-167):
+ * 128942 for seq_len 10, latent 8. */
+int64_t dmvae_param_count(const DmvaeCfg* cfg);
+/* Offset (in floats) of the i-th state_dict tensor (0..23) in the flat
+ * parameter arena; i == 24 returns the total.  Negative on error. */
+int64_t dmvae_param_offset(const DmvaeCfg* cfg, int index);
+/* Size in floats of the kernel-layout (transposed, padded) weight arena. */
+int64_t dmvae_packed_count(const DmvaeCfg* cfg);
+/* params (torch layout, dmvae_param_count floats) -> packed (dmvae_packed_count). */
+int dmvae_pack_weights(const DmvaeCfg* cfg, const float* params, float* packed, void* stream);
+
+/* ---- generation ------------------------------------------------------------
+ * Replaces Tools.py:44-63 (one trajectory) and Tools.py:898-912 (a batch):
+ * h = condition_encoder(start); rel = decode(z, h); out = rel with
+ * fp32(start) added to the x, y columns when add_start != 0.
+ *   packed          kernel-layout weights from dmvae_pack_weights
+ *   z               (B, L) latents, or NULL to draw them in-kernel with
+ *                   Philox4x32-10 keyed by `seed`, counter = sample_offset + row
+ *   start           (B, 2) start points, or (1, 2) when start_is_shared != 0
+ *   out             (B, T, 3) [t, x, y]
+ *   z_out           optional (B, L): receives the latents actually used */
+int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint64_t seed,
+                 uint64_t sample_offset, const float* start, int start_is_shared, float* out,
+                 float* z_out, int64_t B, int add_start, void* stream);
+
+/* model.condition_encoder(c) on its own (Training_VAE.py:132-137; called directly
+ * at Tools.py:55, :898): start (B,2) -> h_c (B,128). */
+int dmvae_cond_encode(const DmvaeCfg* cfg, const float* packed, const float* start, float* h_c, int64_t B,
+                      void* stream);
+/* model.decode(z, condition) on its own (Training_VAE.py:208-215; called directly
+ * at Tools.py:58, :904): z (B,L), h_c (B,128) -> relative trajectories (B,T,3). */
+int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const float* z, const float* h_c,
+                                float* out, int64_t B, void* stream);
+
+/* ---- training ---------------------------------------------------------------
+ * One fused pass over a batch: relative-offset transform (Training_VAE.py:345-348),
+ * forward (:217-226), five-term loss (:229-268) and the full backward (:362).
+ *   params/packed   torch-layout parameters and their packed copy
+ *   x               (B, T, 3) absolute trajectories
+ *   eps             (B, L) reparameterisation noise, or NULL for Philox
+ *                   (key seed, counter = sample_offset + row, stream id `step`)
+ *   inv_batch       1 / (global batch size): the loss is a mean over the
+ *                   GLOBAL batch, so data-parallel ranks pass the global size
+ *   workspace       dmvae_train_workspace_bytes(cfg, B) bytes
+ *   grads           out: dmvae_grad_count(cfg) floats = gradient of the total
+ *                   loss in state_dict order followed by the five loss terms
+ *                   [total, recon, kld, start, time] (sums already scaled by
+ *                   inv_batch, i.e. this rank's share of the global means) */
+int64_t dmvae_grad_count(const DmvaeCfg* cfg);
+int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
+int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* params, const float* packed,
+                        const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
+                        uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
+                        void* workspace, float* grads, void* stream);
+/* optimizer.step() of torch.optim.Adam (Training_VAE.py:363): updates params,
+ * m, v in place from grads (n = dmvae_param_count floats each) and refreshes
+ * `packed` (may be NULL). */
+int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v,
+                    const DmvaeAdam* h, float* packed, void* stream);
+
+/* ---- unfused pieces behind the nn.Module / autograd surface ---------------
+ * forward (Training_VAE.py:217-226) on already-relative trajectories:
+ *   x_rel (B,T,3), start (B,2), eps (B,L)  ->  recon (B,T,3), mu, logvar (B,L),
+ *   h_c (B,128); activations needed by dmvae_backward are kept in `stash`
+ *   (dmvae_stash_bytes(cfg, B) bytes). */
+int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B);
+int dmvae_forward(const DmvaeCfg* cfg, const float* packed, const float* x_rel, const float* start,
+                  const float* eps, float* recon, float* mu, float* logvar, float* h_c, void* stash,
+                  int64_t B, void* stream);
+/* backward of dmvae_forward for upstream gradients g_recon (B,T,3), g_mu,
+ * g_logvar (B,L), g_hc (B,128) (any may be NULL = zero): parameter gradients
+ * (dmvae_param_count floats, overwritten). */
+int dmvae_backward(const DmvaeCfg* cfg, const float* params, const float* g_recon, const float* g_mu,
+                   const float* g_logvar, const float* g_hc, const void* stash, void* workspace,
+                   float* grads, int64_t B, void* stream);
+/* conditional_vae_loss (Training_VAE.py:229-268): losses[5] = total, recon,
+ * kld, start, time; when g_recon/g_mu/g_logvar are non-NULL also the gradient
+ * of `total` scaled by *g_total (device scalar, or NULL for 1). */
+int dmvae_loss(const DmvaeCfg* cfg, const float* recon, const float* x, const float* mu,
+               const float* logvar, const DmvaeLossWeights* w, int64_t B, float* losses,
+               float* g_recon, float* g_mu, float* g_logvar, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMVAE_H_ */

@@ -196,7 +196,7 @@ def loss_and_grads(p: Params, batch: torch.Tensor, eps: torch.Tensor, weights=SC
     keep = {k: v.detach() for k, v in keep.items()}
     keep["x_rel"] = batch_rel
     keep["start"] = start_points
-    return [float(l) for l in losses], grads, keep
+    return [float(l.detach()) if torch.is_tensor(l) else float(l) for l in losses], grads, keep
 
 
 class AdamState:
