@@ -165,4 +165,193 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "decode_from_condition");
 }
 
+
+// ---------------------------------------------------------------------------- training
+namespace {
+struct Workspace {
+  float* slabs;
+  float* stash;
+};
+// workspace = [grid slabs][stash units], both 16-byte aligned
+Workspace carve(void* ws, const dmvae::TrainPlan& p) {
+  Workspace w;
+  w.slabs = static_cast<float*>(ws);
+  w.stash = w.slabs + (size_t)p.grid * p.slab_stride;
+  return w;
+}
+size_t workspace_floats(const dmvae::TrainPlan& p) {
+  return (size_t)p.grid * p.slab_stride + (size_t)p.stash_units * p.stash_stride;
+}
+}  // namespace
+
+int64_t dmvae_grad_count(const DmvaeCfg* cfg) {
+  dmvae::Layout lo;
+  const int rc = layout_or_fail(cfg, &lo);
+  return rc == DMVAE_OK ? lo.n_params + 5 : rc;
+}
+
+int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B < 0) return fail(DMVAE_ERR_ARG, "train_workspace_bytes: negative batch");
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const dmvae::TrainPlan p = dmvae::plan_train(lo, B > 0 ? B : 1, sms, false);
+  return (int64_t)(workspace_floats(p) * sizeof(float));
+}
+
+int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B < 0) return fail(DMVAE_ERR_ARG, "stash_bytes: negative batch");
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const dmvae::TrainPlan p = dmvae::plan_train(lo, B > 0 ? B : 1, sms, true);
+  return (int64_t)((size_t)p.stash_units * p.stash_stride * sizeof(float));
+}
+
+static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
+                        uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
+                        void* workspace, float* grads, const DmvaeAdam* adam, float* params, float* m, float* v,
+                        float* packed_rw, void* stream, const char* what) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B <= 0) return fail(DMVAE_ERR_ARG, "%s: batch must be positive", what);
+  if (!packed || !x || !w || !workspace || !grads || !aligned16(packed) || !aligned16(workspace) || !aligned16(grads) ||
+      !aligned16(x))
+    return fail(DMVAE_ERR_ARG, "%s: null or misaligned pointer", what);
+  if (adam && (!params || !m || !v || !aligned16(params) || !aligned16(m) || !aligned16(v)))
+    return fail(DMVAE_ERR_ARG, "%s: null or misaligned optimizer state", what);
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, false);
+  const Workspace ws = carve(workspace, plan);
+  dmvae::TrainIO io;
+  io.packed = packed; io.x = x; io.eps = eps; io.stash = ws.stash; io.slabs = ws.slabs;
+  io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.B = B;
+  io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
+  cudaError_t e = dmvae::launch_train(lo, plan, 0, io, st);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  const float wv[4] = {w->recon, w->kld, w->start, w->time};
+  e = dmvae::launch_reduce(lo, ws.slabs, plan.grid, plan.slab_stride, wv, grads, adam, params, m, v, st);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  if (adam && packed_rw) {
+    e = dmvae::launch_pack(lo, params, packed_rw, st);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+  }
+  return DMVAE_OK;
+}
+
+int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
+                        uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
+                        void* workspace, float* grads, void* stream) {
+  return train_common(cfg, packed, x, eps, seed, sample_offset, step, w, inv_batch, B, workspace, grads, nullptr,
+                      nullptr, nullptr, nullptr, nullptr, stream, "train_fwd_bwd");
+}
+
+int dmvae_train_step(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
+                     const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
+                     float inv_batch, int64_t B, const DmvaeAdam* adam, void* workspace, float* grads, void* stream) {
+  if (!adam) return fail(DMVAE_ERR_ARG, "train_step: adam is null");
+  return train_common(cfg, packed, x, eps, seed, sample_offset, (uint64_t)adam->step, w, inv_batch, B, workspace, grads,
+                      adam, params, m, v, packed, stream, "train_step");
+}
+
+int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v, const DmvaeAdam* adam,
+                    float* packed, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (!params || !grads || !m || !v || !adam || !aligned16(params) || !aligned16(grads) || !aligned16(m) || !aligned16(v))
+    return fail(DMVAE_ERR_ARG, "adam_step: null or misaligned pointer");
+  if (adam->step < 1) return fail(DMVAE_ERR_ARG, "adam_step: step must be >= 1");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = dmvae::launch_adam(lo, params, grads, m, v, *adam, st);
+  if (e != cudaSuccess) return cuda_fail(e, "adam_step");
+  if (packed) {
+    e = dmvae::launch_pack(lo, params, packed, st);
+    if (e != cudaSuccess) return cuda_fail(e, "adam_step(pack)");
+  }
+  return DMVAE_OK;
+}
+
+int dmvae_forward(const DmvaeCfg* cfg, const float* packed, const float* x_rel, const float* start, const float* eps,
+                  float* recon, float* mu, float* logvar, float* h_c, void* stash, int64_t B, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B < 0) return fail(DMVAE_ERR_ARG, "forward: negative batch");
+  if (B == 0) return DMVAE_OK;
+  if (!packed || !x_rel || !start || !eps || !recon || !mu || !logvar || !h_c || !stash || !aligned16(packed) ||
+      !aligned16(stash))
+    return fail(DMVAE_ERR_ARG, "forward: null or misaligned pointer");
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, true);
+  dmvae::TrainIO io;
+  io.packed = packed; io.x = x_rel; io.start = start; io.eps = eps; io.stash = static_cast<float*>(stash);
+  io.recon = recon; io.mu = mu; io.logvar = logvar; io.hc = h_c; io.B = B;
+  const cudaError_t e = dmvae::launch_train(lo, plan, 1, io, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "forward");
+}
+
+int dmvae_backward(const DmvaeCfg* cfg, const float* packed, const float* g_recon, const float* g_mu,
+                   const float* g_logvar, const float* g_hc, const void* stash, void* workspace, float* grads,
+                   int64_t B, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B <= 0) return fail(DMVAE_ERR_ARG, "backward: batch must be positive");
+  if (!packed || !stash || !workspace || !grads || !aligned16(packed) || !aligned16(stash) || !aligned16(workspace) ||
+      !aligned16(grads))
+    return fail(DMVAE_ERR_ARG, "backward: null or misaligned pointer");
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, true);
+  dmvae::TrainIO io;
+  io.packed = packed; io.stash = const_cast<float*>(static_cast<const float*>(stash));
+  io.slabs = static_cast<float*>(workspace);
+  io.g_recon = g_recon; io.g_mu = g_mu; io.g_logvar = g_logvar; io.g_hc = g_hc; io.B = B;
+  io.inv_batch = 0.f;  // the KLD / loss seeds arrive through the upstream gradients
+  cudaError_t e = dmvae::launch_train(lo, plan, 2, io, st);
+  if (e != cudaSuccess) return cuda_fail(e, "backward");
+  const float wv[4] = {0.f, 0.f, 0.f, 0.f};
+  e = dmvae::launch_reduce(lo, io.slabs, plan.grid, plan.slab_stride, wv, grads, nullptr, nullptr, nullptr, nullptr, st);
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "backward(reduce)");
+}
+
+int dmvae_loss(const DmvaeCfg* cfg, const float* recon, const float* x, const float* mu, const float* logvar,
+               const DmvaeLossWeights* w, int64_t B, float* losses, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B <= 0) return fail(DMVAE_ERR_ARG, "loss: batch must be positive");
+  if (!recon || !x || !mu || !logvar || !w || !losses) return fail(DMVAE_ERR_ARG, "loss: null pointer");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const float wv[4] = {w->recon, w->kld, w->start, w->time};
+  const cudaError_t e = dmvae::launch_loss(lo, B, recon, x, mu, logvar, wv, losses, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "loss");
+}
+
+int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x, const float* mu, const float* logvar,
+                        const DmvaeLossWeights* w, int64_t B, const float* g_out, float* g_recon, float* g_mu,
+                        float* g_logvar, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if (B <= 0) return fail(DMVAE_ERR_ARG, "loss_backward: batch must be positive");
+  if (!recon || !x || !mu || !logvar || !w) return fail(DMVAE_ERR_ARG, "loss_backward: null pointer");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const float wv[4] = {w->recon, w->kld, w->start, w->time};
+  const cudaError_t e = dmvae::launch_loss_grad(lo, B, recon, x, mu, logvar, wv, g_out, g_recon, g_mu, g_logvar,
+                                                static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "loss_backward");
+}
+
 }  // extern "C"

@@ -56,10 +56,13 @@ struct Layout {
   int q_b[NUM_LAYERS];
   // data-gradient operands: aligned copies W[n][k] (n-major = contraction-major for
   // dX = dY * W).  r_w[l] < 0 for layers whose input needs no gradient (cond0, enc0).
-  // heads: [2L][256] (mu rows then logvar rows); dec0: the h_c part [128][128] with the
-  // z part [128][Lq] (Lq = L rounded up to 4, zero padded) at r_dec0z.
+  // heads: rows are mu then logvar; r_w[heads] = columns [0,128) (the h_traj part,
+  // [2L][128]), r_heads_c = columns [128,256) (the h_c part).  dec0: r_w = the h_c part
+  // [128][128]; r_dec0z = the z part [128][Lzp], Lzp = L padded to 32/64 with zeros.
   int r_w[NUM_LAYERS];
-  int r_dec0z, Lq;
+  int r_heads_c;
+  int r_dec0z, Lzp;
+  int Lq;            // L rounded up to 4 (rows of the latent tiles in shared memory)
 };
 
 __host__ __device__ inline int pad_width(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
@@ -96,12 +99,19 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   for (int i = 0; i < NUM_LAYERS; ++i) {
     if (i == L_COND0 || i == L_ENC0) { l.r_w[i] = -1; continue; }
     l.r_w[i] = q;
-    if (i == L_HEADS) q += 2 * l.L * 2 * H;
-    else if (i == L_DEC3) q += l.I * H;
-    else q += H * H;
+    if (i == L_HEADS) {
+      q += 2 * l.L * H;
+      l.r_heads_c = q;
+      q += 2 * l.L * H;
+    } else if (i == L_DEC3) {
+      q += l.I * H;
+    } else {
+      q += H * H;
+    }
     q = round_up(q, 4);
   }
-  l.r_dec0z = q; q += H * l.Lq;
+  l.Lzp = l.L <= 32 ? 32 : 64;
+  l.r_dec0z = q; q += H * l.Lzp;
   l.n_packed = round_up(q, 4);
   return DMVAE_OK;
 }
@@ -155,35 +165,26 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // --------------------------------------------------------------------------------------
 // Weight ring
 // --------------------------------------------------------------------------------------
-// One streamed operand: `rows` contraction rows of `width` floats each, contiguous
-// in global memory from `src`, cut into chunks of `rows_per_chunk` rows.
-struct StreamOp {
-  const float* src;
-  int rows;
-  int width;
-  __device__ __forceinline__ int rows_per_chunk() const { return STAGE_FLOATS / width; }
-};
-
-template <int STAGES>
-struct RingState {
-  int stage = 0;
+// Ring position (stage index + phase parity); producer and every consumer warp keep
+// their own copy and advance it once per chunk.
+struct RingStateRt {
+  int stage = 0, stages;
   uint32_t phase = 0;
+  __device__ explicit RingStateRt(int s) : stages(s) {}
   __device__ __forceinline__ void advance() {
-    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    if (++stage == stages) { stage = 0; phase ^= 1u; }
   }
 };
 
-// Producer side (one elected lane of the producer warp).
-template <int STAGES>
-__device__ __forceinline__ void produce_op(const StreamOp& op, float* ring, uint64_t* full, uint64_t* empty,
-                                           RingState<STAGES>& rs) {
-  const int rpc = op.rows_per_chunk();
-  for (int r0 = 0; r0 < op.rows; r0 += rpc) {
-    const int rows = min(rpc, op.rows - r0);
-    const uint32_t bytes = (uint32_t)(rows * op.width * 4);
+__device__ __forceinline__ void produce(const float* src, int rows, int width, float* ring, uint64_t* full,
+                                        uint64_t* empty, RingStateRt& rs) {
+  const int rpc = STAGE_FLOATS / width;
+  for (int r0 = 0; r0 < rows; r0 += rpc) {
+    const int n = min(rpc, rows - r0);
+    const uint32_t bytes = (uint32_t)(n * width * 4);
     mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
     mbar_arrive_expect_tx(&full[rs.stage], bytes);
-    tma_load_1d(ring + rs.stage * STAGE_FLOATS, op.src + (size_t)r0 * op.width, bytes, &full[rs.stage]);
+    tma_load_1d(ring + rs.stage * STAGE_FLOATS, src + (size_t)r0 * width, bytes, &full[rs.stage]);
     rs.advance();
   }
 }
@@ -264,13 +265,14 @@ __device__ __forceinline__ void zero_acc(float (&acc)[C::TI][C::TJ]) {
     for (int j = 0; j < C::TJ; ++j) acc[i][j] = 0.f;
 }
 
-// Consume one streamed operand: acc += P[rows][.]^T * ring chunks.  Every consumer
-// warp waits and releases every chunk, also warps that own no output of this tile
-// shape, so that the ring protocol is independent of the tile configuration.
-template <class C, int STAGES>
-__device__ __forceinline__ void consume_op(float (&acc)[C::TI][C::TJ], const float* __restrict__ P, int ldp,
-                                           int rows, int width, const float* ring, uint64_t* full,
-                                           uint64_t* empty, RingState<STAGES>& rs, int warp, int lane) {
+// Consume one streamed operand (`rows` contraction rows of `width` floats, cut into
+// ring chunks): acc += P^T * Q.  Every consumer warp waits for and releases every chunk,
+// also warps that own no output of this tile shape, so the ring protocol does not
+// depend on the tile configuration.
+template <class C>
+__device__ __forceinline__ void consume(float (&acc)[C::TI][C::TJ], const float* __restrict__ P, int ldp, int rows,
+                                        int width, const float* ring, uint64_t* full, uint64_t* empty,
+                                        RingStateRt& rs, int warp, int lane) {
   const int rpc = STAGE_FLOATS / width;
   const bool act = C::active(warp);
   const int i0 = C::i0(warp, lane), j0 = C::j0(warp, lane);
@@ -283,6 +285,7 @@ __device__ __forceinline__ void consume_op(float (&acc)[C::TI][C::TJ], const flo
     rs.advance();
   }
 }
+
 
 // --------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) + Box-Muller

@@ -34,45 +34,6 @@ enum DecodeMode { MODE_FULL = 0, MODE_SHARED = 1, MODE_FROM_HC = 2, MODE_COND_ON
 constexpr int DEC_M = 128;
 constexpr int DEC_LD = DEC_M + 4;
 
-struct RingStateRt {
-  int stage = 0, stages;
-  uint32_t phase = 0;
-  __device__ explicit RingStateRt(int s) : stages(s) {}
-  __device__ __forceinline__ void advance() {
-    if (++stage == stages) { stage = 0; phase ^= 1u; }
-  }
-};
-
-__device__ __forceinline__ void produce(const float* src, int rows, int width, float* ring, uint64_t* full,
-                                        uint64_t* empty, RingStateRt& rs) {
-  const int rpc = STAGE_FLOATS / width;
-  for (int r0 = 0; r0 < rows; r0 += rpc) {
-    const int n = min(rpc, rows - r0);
-    const uint32_t bytes = (uint32_t)(n * width * 4);
-    mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
-    mbar_arrive_expect_tx(&full[rs.stage], bytes);
-    tma_load_1d(ring + rs.stage * STAGE_FLOATS, src + (size_t)r0 * width, bytes, &full[rs.stage]);
-    rs.advance();
-  }
-}
-
-template <class C>
-__device__ __forceinline__ void consume(float (&acc)[C::TI][C::TJ], const float* __restrict__ P, int ldp, int rows,
-                                        int width, const float* ring, uint64_t* full, uint64_t* empty,
-                                        RingStateRt& rs, int warp, int lane) {
-  const int rpc = STAGE_FLOATS / width;
-  const bool act = C::active(warp);
-  const int i0 = C::i0(warp, lane), j0 = C::j0(warp, lane);
-  for (int r0 = 0; r0 < rows; r0 += rpc) {
-    const int n = min(rpc, rows - r0);
-    mbar_wait(&full[rs.stage], rs.phase);
-    if (act) gemm_chunk<C>(acc, P + r0 * ldp + i0, ldp, ring + rs.stage * STAGE_FLOATS + j0, width, n);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[rs.stage]);
-    rs.advance();
-  }
-}
-
 // act[n][m] = relu(acc + bias[n]) for a 128-wide layer.
 template <class C>
 __device__ __forceinline__ void store_relu(const float (&acc)[C::TI][C::TJ], float* act, int ld,
@@ -98,7 +59,7 @@ __device__ __forceinline__ void store_relu(const float (&acc)[C::TI][C::TJ], flo
 }
 
 template <int NP3>
-__global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_constant__ DecodeArgs a) {
+__global__ void __maxnreg__(224) decode_kernel(const __grid_constant__ DecodeArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Layout& lo = a.lo;
   const int L = lo.L, Lq = lo.Lq, I = lo.I;

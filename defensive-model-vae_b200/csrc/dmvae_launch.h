@@ -14,4 +14,45 @@ cudaError_t launch_decode(const Layout& lo, int mode, const float* packed, const
                           uint64_t sample_offset, const float* start, const float* hc_in, float* hc_out, float* out,
                           float* z_out, long long B, int add_start, int sm_count, cudaStream_t stream);
 
+// Tiling of one training pass over B rows.
+struct TrainPlan {
+  int M;                   // rows per tile: 64 or 32
+  int stages;              // ring depth
+  int grid;                // CTAs = min(n_tiles, SMs) = number of gradient slabs written
+  long long n_tiles;
+  long long stash_stride;  // floats per stash unit
+  long long stash_units;   // grid (fused: per CTA, recycled per tile) or n_tiles (forward/backward pair)
+  int slab_stride;         // floats per gradient slab (n_params + loss tail, padded)
+  size_t smem;
+};
+TrainPlan plan_train(const Layout& lo, long long B, int sm_count, bool per_tile_stash);
+
+struct TrainIO {
+  const float* packed = nullptr;
+  const float* x = nullptr;
+  const float* start = nullptr;
+  const float* eps = nullptr;
+  float* stash = nullptr;
+  float* slabs = nullptr;
+  float* recon = nullptr; float* mu = nullptr; float* logvar = nullptr; float* hc = nullptr;
+  const float* g_recon = nullptr; const float* g_mu = nullptr; const float* g_logvar = nullptr; const float* g_hc = nullptr;
+  unsigned long long seed = 0, sample_offset = 0, step = 0;
+  long long B = 0;
+  float w_recon = 0.f, w_kld = 0.f, w_start = 0.f, w_time = 0.f, inv_batch = 0.f;
+};
+// mode: 0 fused forward+loss+backward, 1 forward only, 2 backward only
+cudaError_t launch_train(const Layout& lo, const TrainPlan& plan, int mode, const TrainIO& io, cudaStream_t stream);
+
+// grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
+cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],
+                          float* grads, const DmvaeAdam* adam, float* p, float* m, float* v, cudaStream_t stream);
+cudaError_t launch_adam(const Layout& lo, float* p, const float* g, float* m, float* v, const DmvaeAdam& a,
+                        cudaStream_t stream);
+
+cudaError_t launch_loss(const Layout& lo, long long B, const float* recon, const float* x, const float* mu,
+                        const float* logvar, const float w[4], float* losses, cudaStream_t stream);
+cudaError_t launch_loss_grad(const Layout& lo, long long B, const float* recon, const float* x, const float* mu,
+                             const float* logvar, const float w[4], const float* g_out, float* g_recon, float* g_mu,
+                             float* g_logvar, cudaStream_t stream);
+
 }  // namespace dmvae

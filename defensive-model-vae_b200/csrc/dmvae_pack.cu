@@ -32,13 +32,15 @@ __global__ void pack_kernel(const __grid_constant__ Layout lo, const float* __re
     if (l == L_HEADS) {
       for (int idx = tid; idx < 2 * lo.L * 2 * H; idx += nth) {
         const int n = idx / (2 * H), k = idx % (2 * H);
-        q[lo.r_w[l] + idx] = n < lo.L ? p[lo.p_w[l] + n * 2 * H + k] : p[lo.p_wlv + (n - lo.L) * 2 * H + k];
+        const float w = n < lo.L ? p[lo.p_w[l] + n * 2 * H + k] : p[lo.p_wlv + (n - lo.L) * 2 * H + k];
+        if (k < H) q[lo.r_w[l] + n * H + k] = w;
+        else q[lo.r_heads_c + n * H + (k - H)] = w;
       }
     } else if (l == L_DEC0) {
       const int Kd = lo.L + H;
       for (int idx = tid; idx < H * H; idx += nth) q[lo.r_w[l] + idx] = p[lo.p_w[l] + (idx / H) * Kd + lo.L + (idx % H)];
-      for (int idx = tid; idx < H * lo.Lq; idx += nth) {
-        const int n = idx / lo.Lq, j = idx % lo.Lq;
+      for (int idx = tid; idx < H * lo.Lzp; idx += nth) {
+        const int n = idx / lo.Lzp, j = idx % lo.Lzp;
         q[lo.r_dec0z + idx] = j < lo.L ? p[lo.p_w[l] + n * Kd + j] : 0.f;
       }
     } else {

@@ -45,22 +45,21 @@ SIGNATURES = {
     "dmvae_decode": (c_int, [_CFG, _P, _P, c_uint64, c_uint64, _P, c_int, _P, _P, c_int64, c_int, _P]),
     "dmvae_grad_count": (c_int64, [_CFG]),
     "dmvae_train_workspace_bytes": (c_int64, [_CFG, c_int64]),
-    "dmvae_train_fwd_bwd": (c_int, [_CFG, _P, _P, _P, _P, c_uint64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
+    "dmvae_train_fwd_bwd": (c_int, [_CFG, _P, _P, _P, c_uint64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                     c_float, c_int64, _P, _P, _P]),
+    "dmvae_train_step": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
+                                 c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P]),
     "dmvae_adam_step": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P]),
     "dmvae_stash_bytes": (c_int64, [_CFG, c_int64]),
     "dmvae_forward": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "dmvae_backward": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
-    "dmvae_loss": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeLossWeights), c_int64, _P, _P, _P, _P, _P]),
+    "dmvae_loss": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeLossWeights), c_int64, _P, _P]),
+    "dmvae_loss_backward": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeLossWeights), c_int64, _P, _P, _P, _P, _P]),
     "dmvae_cond_encode": (c_int, [_CFG, _P, _P, _P, c_int64, _P]),
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
 }
 
 _lib = None
-# TODO(round 1, in progress): entry points being brought up; emptied once they land
-_PENDING = {"dmvae_grad_count", "dmvae_train_workspace_bytes", "dmvae_train_fwd_bwd", "dmvae_adam_step",
-            "dmvae_stash_bytes", "dmvae_forward", "dmvae_backward", "dmvae_loss"}
-
 
 def lib() -> ctypes.CDLL:
     """Load libdmvae.so (once).  Raises if it has not been built."""
@@ -73,8 +72,6 @@ def lib() -> ctypes.CDLL:
             "(or defensive-model-vae_b200/csrc/build.sh).  dmvae has no CPU or PyTorch fallback.")
     handle = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
-        if name in _PENDING and not hasattr(handle, name):
-            continue
         fn = getattr(handle, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args

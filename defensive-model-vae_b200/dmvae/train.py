@@ -1,0 +1,159 @@
+"""Fused training step: the throughput path behind ``Training_VAE.py``'s loop.
+
+One call = relative-offset transform + forward + five-term loss + backward
+(``train_kernel``), fixed-order slab reduction + Adam (``reduce_kernel``) and the
+refresh of the kernel-layout weights (``pack_kernel``): Training_VAE.py:345-363
+without a single host synchronisation.  The five loss terms of the step stay on
+the device in the tail of the gradient buffer; ``LossMeter`` accumulates them
+there and is read back once per epoch (the reference does five ``.item()`` per
+step, Training_VAE.py:366-370).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import DmvaeAdam, DmvaeLossWeights, byref, check, ptr, stream_ptr
+
+LOSS_KEYS = ("total_loss", "recon_loss", "kld_loss", "start_loss", "time_loss")  # Training_VAE.py:337
+
+
+class FusedTrainer:
+    """Owns the Adam state (flat m, v, step), the gradient buffer and the kernel
+    workspace for a ``ConditionalTrajectoryVAE``.
+
+    ``step(batch)``              single-GPU fused step (3 launches)
+    ``loss_and_grads(batch)``    fused forward+loss+backward only -> (losses, grads)
+    ``apply(grads)``             Adam + repack from an (all-reduced) gradient buffer
+    """
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weights: Sequence[float] = (0.1, 0.1, 1.0, 1.0), seed: int = 0):
+        self.model = model
+        self.lib = _lib.lib()
+        self.cfg = model._cfg
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.weights = DmvaeLossWeights(*[float(w) for w in weights])
+        self.seed = int(seed)
+        self.t = 0                                   # Adam step count (torch: state['step'])
+        arena = model.flat_parameters()
+        self.device = arena.device
+        self.n_params = arena.numel()
+        with torch.cuda.device(self.device):
+            n = check(self.lib.dmvae_grad_count(byref(self.cfg)), "dmvae_grad_count")
+        self.m = torch.zeros_like(arena)
+        self.v = torch.zeros_like(arena)
+        self.grad_buf = torch.zeros(n, dtype=torch.float32, device=self.device)   # grads + 5 loss terms
+        self._ws = {}
+        self._cfg_ref = byref(self.cfg)
+        self._w_ref = byref(self.weights)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def grads(self) -> torch.Tensor:
+        return self.grad_buf[: self.n_params]
+
+    @property
+    def losses(self) -> torch.Tensor:
+        """[total, recon, kld, start, time] of the last pass (device tensor, no sync)."""
+        return self.grad_buf[self.n_params:]
+
+    def _workspace(self, B: int) -> torch.Tensor:
+        ws = self._ws.get(B)
+        if ws is None:
+            with torch.cuda.device(self.device):
+                nbytes = check(self.lib.dmvae_train_workspace_bytes(self._cfg_ref, B), "dmvae_train_workspace_bytes")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws = {B: ws}       # keep only the latest size
+        return ws
+
+    def _check_batch(self, batch: torch.Tensor) -> torch.Tensor:
+        if batch.device != self.device or batch.dtype != torch.float32 or not batch.is_contiguous():
+            batch = batch.to(device=self.device, dtype=torch.float32).contiguous()
+        if batch.dim() != 3 or batch.shape[1] != self.model.seq_len or batch.shape[2] != 3 or batch.shape[0] == 0:
+            raise ValueError(f"batch must be a non-empty (B, {self.model.seq_len}, 3) tensor, got {tuple(batch.shape)}")
+        return batch
+
+    def _check_eps(self, eps, B):
+        if eps is None:
+            return None
+        eps = eps.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(eps.shape) != (B, self.model.latent_dim):
+            raise ValueError(f"eps must be (B, {self.model.latent_dim})")
+        return eps
+
+    # ------------------------------------------------------------------ passes
+    def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
+                       global_batch: Optional[int] = None, sample_offset: int = 0):
+        """Fused forward + loss + backward.  ``global_batch`` is the size the means
+        are taken over (data-parallel: sum of the ranks' batches).  Returns
+        (losses[5], grads[n_params]) as views of the internal buffer."""
+        batch = self._check_batch(batch)
+        B = batch.shape[0]
+        eps = self._check_eps(eps, B)
+        packed = self.model.packed_weights()
+        ws = self._workspace(B)
+        inv = 1.0 / float(global_batch if global_batch is not None else B)
+        with torch.cuda.device(self.device):
+            check(self.lib.dmvae_train_fwd_bwd(self._cfg_ref, ptr(packed), ptr(batch), ptr(eps),
+                                               ctypes.c_uint64(self.seed), ctypes.c_uint64(sample_offset),
+                                               ctypes.c_uint64(self.t + 1), self._w_ref, ctypes.c_float(inv), B,
+                                               ptr(ws), ptr(self.grad_buf), stream_ptr()), "dmvae_train_fwd_bwd")
+        return self.losses, self.grads
+
+    def _adam(self) -> DmvaeAdam:
+        return DmvaeAdam(self.lr, self.betas[0], self.betas[1], self.eps, self.t)
+
+    def apply(self, grads: Optional[torch.Tensor] = None) -> None:
+        """optimizer.step() from ``grads`` (default: the internal buffer, e.g. after an
+        in-place all-reduce) + refresh of the packed weights."""
+        g = self.grad_buf if grads is None else grads
+        arena = self.model.flat_parameters()
+        packed = self.model.packed_weights()
+        self.t += 1
+        h = self._adam()
+        with torch.cuda.device(self.device):
+            check(self.lib.dmvae_adam_step(self._cfg_ref, ptr(arena), ptr(g), ptr(self.m), ptr(self.v), byref(h),
+                                           ptr(packed), stream_ptr()), "dmvae_adam_step")
+        self.model.mark_packed_current()
+
+    def step(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None, sample_offset: int = 0) -> torch.Tensor:
+        """One full single-GPU training step; returns the 5 loss terms (device view)."""
+        batch = self._check_batch(batch)
+        B = batch.shape[0]
+        eps = self._check_eps(eps, B)
+        arena = self.model.flat_parameters()
+        packed = self.model.packed_weights()
+        ws = self._workspace(B)
+        self.t += 1
+        h = self._adam()
+        with torch.cuda.device(self.device):
+            check(self.lib.dmvae_train_step(self._cfg_ref, ptr(arena), ptr(packed), ptr(self.m), ptr(self.v),
+                                            ptr(batch), ptr(eps), ctypes.c_uint64(self.seed),
+                                            ctypes.c_uint64(sample_offset), self._w_ref, ctypes.c_float(1.0 / B), B,
+                                            byref(h), ptr(ws), ptr(self.grad_buf), stream_ptr()), "dmvae_train_step")
+        self.model.mark_packed_current()
+        return self.losses
+
+
+class LossMeter:
+    """Sample-weighted running sums of the five loss terms, kept on the device
+    (Training_VAE.py:339, :366-380 without the per-step host syncs)."""
+
+    def __init__(self, device):
+        self.sums = torch.zeros(5, dtype=torch.float64, device=device)
+        self.count = 0
+
+    def update(self, losses: torch.Tensor, batch_size: int) -> None:
+        self.sums += losses.double() * batch_size
+        self.count += batch_size
+
+    def means(self):
+        """One device->host read: the epoch means in LOSS_KEYS order."""
+        vals = (self.sums / max(self.count, 1)).cpu().tolist()
+        self.sums.zero_()
+        self.count = 0
+        return vals

@@ -107,52 +107,66 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
                                 float* out, int64_t B, void* stream);
 
 /* ---- training ---------------------------------------------------------------
- * One fused pass over a batch: relative-offset transform (Training_VAE.py:345-348),
- * forward (:217-226), five-term loss (:229-268) and the full backward (:362).
- *   params/packed   torch-layout parameters and their packed copy
+ * dmvae_train_fwd_bwd: one fused pass over a batch - relative-offset transform
+ * (Training_VAE.py:345-348), forward (:217-226), five-term loss (:229-268) and
+ * the full backward (:362) - followed by the fixed-order reduction of the
+ * per-CTA gradient slabs.
+ *   packed          kernel-layout weights (dmvae_pack_weights)
  *   x               (B, T, 3) absolute trajectories
  *   eps             (B, L) reparameterisation noise, or NULL for Philox
- *                   (key seed, counter = sample_offset + row, stream id `step`)
+ *                   (key `seed`, counter = sample_offset + row, stream = step + 1)
  *   inv_batch       1 / (global batch size): the loss is a mean over the
  *                   GLOBAL batch, so data-parallel ranks pass the global size
- *   workspace       dmvae_train_workspace_bytes(cfg, B) bytes
- *   grads           out: dmvae_grad_count(cfg) floats = gradient of the total
- *                   loss in state_dict order followed by the five loss terms
- *                   [total, recon, kld, start, time] (sums already scaled by
- *                   inv_batch, i.e. this rank's share of the global means) */
+ *   workspace       dmvae_train_workspace_bytes(cfg, B) bytes, 16-byte aligned
+ *   grads           out: dmvae_grad_count(cfg) = param_count + 5 floats: the
+ *                   gradient of the total loss in state_dict order, then
+ *                   [total, recon, kld, start, time] (this rank's share of the
+ *                   global means; a SUM all-reduce over ranks completes both)
+ * dmvae_train_step: the same followed by the Adam update in the reduction
+ * kernel and a refresh of `packed`: the whole single-GPU step
+ * (Training_VAE.py:351-363) in three launches, no host synchronisation. */
 int64_t dmvae_grad_count(const DmvaeCfg* cfg);
 int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
-int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* params, const float* packed,
-                        const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
-                        uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
-                        void* workspace, float* grads, void* stream);
-/* optimizer.step() of torch.optim.Adam (Training_VAE.py:363): updates params,
- * m, v in place from grads (n = dmvae_param_count floats each) and refreshes
- * `packed` (may be NULL). */
+int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps,
+                        uint64_t seed, uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w,
+                        float inv_batch, int64_t B, void* workspace, float* grads, void* stream);
+int dmvae_train_step(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
+                     const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
+                     const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
+                     void* workspace, float* grads, void* stream);
+/* optimizer.step() of torch.optim.Adam (Training_VAE.py:363; torch
+ * optim/adam.py::_single_tensor_adam): updates params, m, v in place from
+ * grads (dmvae_param_count floats each) and refreshes `packed` (may be NULL).
+ * Data-parallel training calls this after the gradient all-reduce. */
 int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v,
-                    const DmvaeAdam* h, float* packed, void* stream);
+                    const DmvaeAdam* adam, float* packed, void* stream);
 
 /* ---- unfused pieces behind the nn.Module / autograd surface ---------------
- * forward (Training_VAE.py:217-226) on already-relative trajectories:
- *   x_rel (B,T,3), start (B,2), eps (B,L)  ->  recon (B,T,3), mu, logvar (B,L),
- *   h_c (B,128); activations needed by dmvae_backward are kept in `stash`
- *   (dmvae_stash_bytes(cfg, B) bytes). */
+ * dmvae_forward: model.forward (Training_VAE.py:217-226) on already-relative
+ * trajectories: x_rel (B,T,3), start (B,2), eps (B,L) -> recon (B,T,3), mu,
+ * logvar (B,L), h_c (B,128).  Activations needed by dmvae_backward are kept
+ * in `stash` (dmvae_stash_bytes(cfg, B) bytes). */
 int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B);
 int dmvae_forward(const DmvaeCfg* cfg, const float* packed, const float* x_rel, const float* start,
                   const float* eps, float* recon, float* mu, float* logvar, float* h_c, void* stash,
                   int64_t B, void* stream);
-/* backward of dmvae_forward for upstream gradients g_recon (B,T,3), g_mu,
- * g_logvar (B,L), g_hc (B,128) (any may be NULL = zero): parameter gradients
- * (dmvae_param_count floats, overwritten). */
-int dmvae_backward(const DmvaeCfg* cfg, const float* params, const float* g_recon, const float* g_mu,
+/* dmvae_backward: what autograd computes for the module's parameters given the
+ * upstream gradients g_recon (B,T,3), g_mu, g_logvar (B,L), g_hc (B,128) (any
+ * may be NULL = zero).  workspace: dmvae_train_workspace_bytes(cfg, B) bytes.
+ * grads: dmvae_grad_count floats (the 5-float tail is zero). */
+int dmvae_backward(const DmvaeCfg* cfg, const float* packed, const float* g_recon, const float* g_mu,
                    const float* g_logvar, const float* g_hc, const void* stash, void* workspace,
                    float* grads, int64_t B, void* stream);
 /* conditional_vae_loss (Training_VAE.py:229-268): losses[5] = total, recon,
- * kld, start, time; when g_recon/g_mu/g_logvar are non-NULL also the gradient
- * of `total` scaled by *g_total (device scalar, or NULL for 1). */
+ * kld, start, time (a term whose weight is <= 0 is reported as 0 and left out
+ * of the total, as the reference does). */
 int dmvae_loss(const DmvaeCfg* cfg, const float* recon, const float* x, const float* mu,
-               const float* logvar, const DmvaeLossWeights* w, int64_t B, float* losses,
-               float* g_recon, float* g_mu, float* g_logvar, void* stream);
+               const float* logvar, const DmvaeLossWeights* w, int64_t B, float* losses, void* stream);
+/* its backward for upstream gradients g_out[5] of the five outputs (device
+ * pointer, NULL = d(total) = 1): g_recon (B,T,3), g_mu, g_logvar (B,L). */
+int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x, const float* mu,
+                        const float* logvar, const DmvaeLossWeights* w, int64_t B, const float* g_out,
+                        float* g_recon, float* g_mu, float* g_logvar, void* stream);
 
 #ifdef __cplusplus
 }
