@@ -115,19 +115,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 static AdamScalars make_scalars(const DmvaeAdam& a) {
   // host double arithmetic, exactly as the Python floats in torch/optim/adam.py
-  const double b1 = (double)a.beta1, b2 = (double)a.beta2;
-  double p1 = 1.0, p2 = 1.0;
-  // beta ** step with the same repeated-squaring-free semantics as Python's float pow
-  p1 = pow(b1, (double)a.step);
-  p2 = pow(b2, (double)a.step);
-  const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+  const double b1 = a.beta1, b2 = a.beta2;
+  const double bc1 = 1.0 - pow(b1, (double)a.step), bc2 = 1.0 - pow(b2, (double)a.step);  // beta ** step
   AdamScalars h;
   h.w1 = (float)(1.0 - b1);
   h.b2 = (float)b2;
   h.w2 = (float)(1.0 - b2);
-  h.step_size = (float)((double)a.lr / bc1);
+  h.step_size = (float)(a.lr / bc1);
   h.bc2_sqrt = (float)sqrt(bc2);
-  h.eps = a.eps;
+  h.eps = (float)a.eps;
   return h;
 }
 

@@ -220,8 +220,7 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
   if (B <= 0) return fail(DMVAE_ERR_ARG, "%s: batch must be positive", what);
-  if (!packed || !x || !w || !workspace || !grads || !aligned16(packed) || !aligned16(workspace) || !aligned16(grads) ||
-      !aligned16(x))
+  if (!packed || !x || !w || !workspace || !grads || !aligned16(packed) || !aligned16(workspace) || !aligned16(grads))
     return fail(DMVAE_ERR_ARG, "%s: null or misaligned pointer", what);
   if (adam && (!params || !m || !v || !aligned16(params) || !aligned16(m) || !aligned16(v)))
     return fail(DMVAE_ERR_ARG, "%s: null or misaligned optimizer state", what);

@@ -59,7 +59,9 @@ __device__ __forceinline__ void store_relu(const float (&acc)[C::TI][C::TJ], flo
 }
 
 template <int NP3>
-__global__ void __maxnreg__(224) decode_kernel(const __grid_constant__ DecodeArgs a) {
+// 9 warps: one SM sub-partition holds 3 of them, so 3*32*regs <= 16384 -> at most 168
+// registers per thread (what __launch_bounds__(288, 1) makes ptxas target).
+__global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_constant__ DecodeArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Layout& lo = a.lo;
   const int L = lo.L, Lq = lo.Lq, I = lo.I;

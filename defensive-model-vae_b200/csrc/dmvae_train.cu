@@ -337,7 +337,7 @@ __device__ __forceinline__ void dgrad_small(const Layout& lo, const Smem<M>& s, 
 }
 
 template <int M>
-__global__ void __maxnreg__(224) train_kernel(const __grid_constant__ TrainArgs a) {
+__global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_constant__ TrainArgs a) {
   constexpr int LD = M + 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const Layout& lo = a.lo;

@@ -28,7 +28,8 @@ class DmvaeLossWeights(ctypes.Structure):
 
 
 class DmvaeAdam(ctypes.Structure):
-    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("step", c_int64)]
+    _fields_ = [("lr", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double),
+                ("eps", ctypes.c_double), ("step", c_int64)]
 
 
 # name -> (restype, argtypes); mirrors include/dmvae.h one to one

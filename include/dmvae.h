@@ -58,11 +58,12 @@ typedef struct DmvaeLossWeights {
 } DmvaeLossWeights;
 
 /* torch.optim.Adam hyper-parameters (Training_VAE.py:332; torch optim/adam.py). */
+/* Doubles, like the Python floats torch computes its step scalars from. */
 typedef struct DmvaeAdam {
-  float lr;
-  float beta1;
-  float beta2;
-  float eps;
+  double lr;
+  double beta1;
+  double beta2;
+  double eps;
   int64_t step; /* 1-based index of the update being applied */
 } DmvaeAdam;
 

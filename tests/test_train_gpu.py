@@ -47,8 +47,11 @@ def synth_batch(B, T, seed, scale=50.0):
 
 def check_losses(got, ref):
     got = [float(v) for v in got]
+    scale = max(abs(float(r)) for r in ref)
     for g, r in zip(got, ref):
-        assert abs(g - r) <= LOSS_TOL * abs(r) + 1e-9, (got, ref)
+        # a term that is tiny next to the others (start_loss ~1e-3 vs kld ~10) is a sum of
+        # squared cancellations: allow 1e-8 of the largest term in absolute
+        assert abs(g - r) <= LOSS_TOL * abs(r) + 1e-8 * scale + 1e-9, (got, ref)
 
 
 def per_tensor_err(grads, grads_ref):
