@@ -5,6 +5,10 @@
 
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
+#include "dmvae_prof.h"
+
+// count (and, when profiling, time) the kernel launched by `call`
+#define PROF(kernel, stream, call) [&] { dmvae::ProfScope _ps((kernel), (stream)); return (call); }()
 
 namespace {
 
@@ -113,7 +117,8 @@ int dmvae_pack_weights(const DmvaeCfg* cfg, const float* params, float* packed, 
   if (rc != DMVAE_OK) return rc;
   if (!params || !packed || !aligned16(packed)) return fail(DMVAE_ERR_ARG, "pack_weights: null or misaligned pointer");
   if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
-  const cudaError_t e = dmvae::launch_pack(lo, params, packed, static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "pack_weights");
 }
 
@@ -128,9 +133,10 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
   if (!packed || !start || !out || !aligned16(packed)) return fail(DMVAE_ERR_ARG, "decode: null or misaligned pointer");
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
-  const cudaError_t e =
-      dmvae::launch_decode(lo, start_is_shared ? 1 : 0, packed, z, seed, sample_offset, start, nullptr, nullptr, out,
-                           z_out, B, add_start ? 1 : 0, sms, static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_DECODE, st,
+                             dmvae::launch_decode(lo, start_is_shared ? 1 : 0, packed, z, seed, sample_offset, start,
+                                                  nullptr, nullptr, out, z_out, B, add_start ? 1 : 0, sms, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "decode");
 }
 
@@ -144,8 +150,9 @@ int dmvae_cond_encode(const DmvaeCfg* cfg, const float* packed, const float* sta
   if (!packed || !start || !h_c || !aligned16(packed)) return fail(DMVAE_ERR_ARG, "cond_encode: null or misaligned pointer");
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
-  const cudaError_t e = dmvae::launch_decode(lo, 3, packed, nullptr, 0, 0, start, nullptr, h_c, nullptr, nullptr, B, 0,
-                                             sms, static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_DECODE, st, dmvae::launch_decode(lo, 3, packed, nullptr, 0, 0, start, nullptr, h_c,
+                                                                        nullptr, nullptr, B, 0, sms, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "cond_encode");
 }
 
@@ -160,8 +167,9 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
     return fail(DMVAE_ERR_ARG, "decode_from_condition: null or misaligned pointer");
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
-  const cudaError_t e = dmvae::launch_decode(lo, 2, packed, z, 0, 0, nullptr, h_c, nullptr, out, nullptr, B, 0, sms,
-                                             static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_DECODE, st, dmvae::launch_decode(lo, 2, packed, z, 0, 0, nullptr, h_c, nullptr, out,
+                                                                        nullptr, B, 0, sms, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "decode_from_condition");
 }
 
@@ -233,13 +241,14 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   io.packed = packed; io.x = x; io.eps = eps; io.stash = ws.stash; io.slabs = ws.slabs;
   io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.B = B;
   io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
-  cudaError_t e = dmvae::launch_train(lo, plan, 0, io, st);
+  cudaError_t e = PROF(dmvae::K_TRAIN_FUSED, st, dmvae::launch_train(lo, plan, 0, io, st));
   if (e != cudaSuccess) return cuda_fail(e, what);
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
-  e = dmvae::launch_reduce(lo, ws.slabs, plan.grid, plan.slab_stride, wv, grads, adam, params, m, v, st);
+  e = PROF(adam ? dmvae::K_REDUCE_ADAM : dmvae::K_REDUCE, st,
+           dmvae::launch_reduce(lo, ws.slabs, plan.grid, plan.slab_stride, wv, grads, adam, params, m, v, st));
   if (e != cudaSuccess) return cuda_fail(e, what);
   if (adam && packed_rw) {
-    e = dmvae::launch_pack(lo, params, packed_rw, st);
+    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed_rw, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
   }
   return DMVAE_OK;
@@ -270,10 +279,10 @@ int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, floa
   if (adam->step < 1) return fail(DMVAE_ERR_ARG, "adam_step: step must be >= 1");
   if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = dmvae::launch_adam(lo, params, grads, m, v, *adam, st);
+  cudaError_t e = PROF(dmvae::K_ADAM, st, dmvae::launch_adam(lo, params, grads, m, v, *adam, st));
   if (e != cudaSuccess) return cuda_fail(e, "adam_step");
   if (packed) {
-    e = dmvae::launch_pack(lo, params, packed, st);
+    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed, st));
     if (e != cudaSuccess) return cuda_fail(e, "adam_step(pack)");
   }
   return DMVAE_OK;
@@ -295,7 +304,8 @@ int dmvae_forward(const DmvaeCfg* cfg, const float* packed, const float* x_rel, 
   dmvae::TrainIO io;
   io.packed = packed; io.x = x_rel; io.start = start; io.eps = eps; io.stash = static_cast<float*>(stash);
   io.recon = recon; io.mu = mu; io.logvar = logvar; io.hc = h_c; io.B = B;
-  const cudaError_t e = dmvae::launch_train(lo, plan, 1, io, static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_TRAIN_FWD, st, dmvae::launch_train(lo, plan, 1, io, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "forward");
 }
 
@@ -318,10 +328,11 @@ int dmvae_backward(const DmvaeCfg* cfg, const float* packed, const float* g_reco
   io.slabs = static_cast<float*>(workspace);
   io.g_recon = g_recon; io.g_mu = g_mu; io.g_logvar = g_logvar; io.g_hc = g_hc; io.B = B;
   io.inv_batch = 0.f;  // the KLD / loss seeds arrive through the upstream gradients
-  cudaError_t e = dmvae::launch_train(lo, plan, 2, io, st);
+  cudaError_t e = PROF(dmvae::K_TRAIN_BWD, st, dmvae::launch_train(lo, plan, 2, io, st));
   if (e != cudaSuccess) return cuda_fail(e, "backward");
   const float wv[4] = {0.f, 0.f, 0.f, 0.f};
-  e = dmvae::launch_reduce(lo, io.slabs, plan.grid, plan.slab_stride, wv, grads, nullptr, nullptr, nullptr, nullptr, st);
+  e = PROF(dmvae::K_REDUCE, st,
+           dmvae::launch_reduce(lo, io.slabs, plan.grid, plan.slab_stride, wv, grads, nullptr, nullptr, nullptr, nullptr, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "backward(reduce)");
 }
 
@@ -334,7 +345,8 @@ int dmvae_loss(const DmvaeCfg* cfg, const float* recon, const float* x, const fl
   if (!recon || !x || !mu || !logvar || !w || !losses) return fail(DMVAE_ERR_ARG, "loss: null pointer");
   if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
-  const cudaError_t e = dmvae::launch_loss(lo, B, recon, x, mu, logvar, wv, losses, static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_LOSS, st, dmvae::launch_loss(lo, B, recon, x, mu, logvar, wv, losses, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "loss");
 }
 
@@ -348,9 +360,39 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
   if (!recon || !x || !mu || !logvar || !w) return fail(DMVAE_ERR_ARG, "loss_backward: null pointer");
   if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
-  const cudaError_t e = dmvae::launch_loss_grad(lo, B, recon, x, mu, logvar, wv, g_out, g_recon, g_mu, g_logvar,
-                                                static_cast<cudaStream_t>(stream));
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_LOSS_GRAD, st,
+                             dmvae::launch_loss_grad(lo, B, recon, x, mu, logvar, wv, g_out, g_recon, g_mu, g_logvar, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "loss_backward");
+}
+
+// ---------------------------------------------------------------------------- instrumentation
+const char* dmvae_kernel_name(int kernel) { return dmvae::kernel_name(kernel); }
+int64_t dmvae_launch_count(int kernel) { return dmvae::launch_count(kernel); }
+
+int dmvae_profile_begin(void) {
+  const int rc = require_device(nullptr);
+  if (rc != DMVAE_OK) return rc;
+  dmvae::profile_enable(1);
+  return DMVAE_OK;
+}
+
+int dmvae_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n) {
+  if (!ms_by_kernel || !launches_by_kernel || n < 1 || n > DMVAE_KERNEL_COUNT)
+    return fail(DMVAE_ERR_ARG, "profile_end: need two arrays of 1..%d entries", DMVAE_KERNEL_COUNT);
+  long long cnt[DMVAE_KERNEL_COUNT];
+  const cudaError_t e = dmvae::profile_collect(ms_by_kernel, cnt, n);
+  for (int i = 0; i < n; ++i) launches_by_kernel[i] = cnt[i];
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "profile_end");
+}
+
+int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream) {
+  if (!sink || iters < 1) return fail(DMVAE_ERR_ARG, "ffma_probe: null sink or iters < 1");
+  int sms = 0;
+  const int rc = require_device(&sms);
+  if (rc != DMVAE_OK) return rc;
+  const cudaError_t e = dmvae::launch_ffma_probe(iters, sink, sms, flop_out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "ffma_probe");
 }
 
 }  // extern "C"

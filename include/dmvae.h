@@ -169,6 +169,26 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
                         const float* logvar, const DmvaeLossWeights* w, int64_t B, const float* g_out,
                         float* g_recon, float* g_mu, float* g_logvar, void* stream);
 
+/* ---- instrumentation -------------------------------------------------------
+ * Nothing in the reference corresponds to these: they let bench.py report what the
+ * library launched and how long the dominant kernel ran inside the timed region.
+ * Kernel ids: 0 pack, 1 decode, 2 train (fused), 3 train (forward), 4 train
+ * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe. */
+#define DMVAE_KERNEL_COUNT 11
+const char* dmvae_kernel_name(int kernel);
+/* Kernels launched by this process since the library was loaded (kernel < 0: all). */
+int64_t dmvae_launch_count(int kernel);
+/* Between begin and end every launch is bracketed by a cudaEvent pair on its stream;
+ * end synchronises on them and returns, per kernel id, the summed duration in
+ * milliseconds and the number of launches (arrays of n <= DMVAE_KERNEL_COUNT). */
+int dmvae_profile_begin(void);
+int dmvae_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n);
+/* FP32 roofline probe: a pure FFMA kernel over every SM (16 independent chains per
+ * thread, 2 x 1024 threads per SM); *flop_out receives the FLOPs it executes.  Timed
+ * by the caller (or through the profile calls) it yields the FFMA peak the fused
+ * kernels are measured against.  sink: any device float. */
+int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

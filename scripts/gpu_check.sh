@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# One gpurun call: GPU tests, smoke, bench (both arms), ncu launch list + full capture.
+# usage: scripts/gpu_check.sh <tag>   (outputs under gpurun_out/<tag>_*)
+set -u
+tag=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
+python -m pytest tests -x -q -m gpu > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/${tag}_smoke.log
+python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "bench ref rc=$?"
+python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/${tag}_bench.json
+SMALL="python bench.py --steps 6 --warmup 3 --no-cpu --dataset-rows 65536 --decode-rows 262144"
+$SMALL > gpurun_out/${tag}_small.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu1.log 2>&1
+echo "ncu list rc=$?"
+$SMALL > gpurun_out/${tag}_small2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'train_kernel|decode_kernel' -s 12 -c 3 -f -o gpurun_out/${tag}_prof $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
+echo "ncu full rc=$?"
+ls -la gpurun_out
