@@ -15,6 +15,8 @@ $SMALL > gpurun_out/${tag}_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu list rc=$?"
 $SMALL > gpurun_out/${tag}_small2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'train_kernel|decode_kernel' -s 12 -c 3 -f -o gpurun_out/${tag}_prof $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
-echo "ncu full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:train_kernel -s 5 -c 2 -f -o gpurun_out/${tag}_prof_train $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
+echo "ncu full train rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 4 -c 2 -f -o gpurun_out/${tag}_prof_decode $SMALL > gpurun_out/${tag}_ncu3.log 2>&1
+echo "ncu full decode rc=$?"
 ls -la gpurun_out
