@@ -335,14 +335,15 @@ def run_cuda(args):
     n_batches = rows // B
     Bg = B * world
 
+    from dmvae.parallel import DataParallelTrainer
+    dp = DataParallelTrainer(trainer)    # N > 1: fwd+bwd, ONE NCCL all-reduce of [grads | 5 losses], replicated Adam
+
     def train_step(i):
         b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
         if world == 1:
-            trainer.step(b, sample_offset=0)
+            trainer.step(b, sample_offset=0)             # 3 launches: train_kernel, reduce+Adam, pack
         else:
-            trainer.loss_and_grads(b, global_batch=Bg, sample_offset=rank * B)
-            dist.all_reduce(trainer.grad_buf)            # grads + 5 loss terms, SUM over ranks (NCCL, NVLink)
-            trainer.apply()
+            dp.step(b)
 
     K, W = args.steps, max(args.warmup, 3)
     clocks = ClockSampler(local).start() if rank == 0 else None
@@ -379,13 +380,7 @@ def run_cuda(args):
 
     def e2e_step(i, blocking=True):
         dbuf.copy_(host_batches[i % 8], non_blocking=True)
-        if world == 1:
-            losses = trainer.step(dbuf)
-        else:
-            trainer.loss_and_grads(dbuf, global_batch=Bg, sample_offset=rank * B)
-            dist.all_reduce(trainer.grad_buf)
-            trainer.apply()
-            losses = trainer.losses
+        losses = trainer.step(dbuf) if world == 1 else dp.step(dbuf)
         host_losses.copy_(losses, non_blocking=True)
         if blocking:
             torch.cuda.current_stream().synchronize()
