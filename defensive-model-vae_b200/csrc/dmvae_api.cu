@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
@@ -57,6 +58,9 @@ int require_device(int* sm_count) {
   if (sm_count) *sm_count = g_dev.sm_count;
   return DMVAE_OK;
 }
+
+// 0 = tensor cores (tcgen05, 3xTF32; default), 1 = FP32 FFMA kernel
+std::atomic<int> g_decode_impl{0};
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -134,9 +138,15 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const cudaError_t e = PROF(dmvae::K_DECODE, st,
-                             dmvae::launch_decode(lo, start_is_shared ? 1 : 0, packed, z, seed, sample_offset, start,
-                                                  nullptr, nullptr, out, z_out, B, add_start ? 1 : 0, sms, st));
+  cudaError_t e;
+  if (g_decode_impl.load() == 0)
+    e = PROF(dmvae::K_DECODE_TC, st,
+             dmvae::launch_decode_tc(lo, start_is_shared != 0, packed, z, seed, sample_offset, start, out, z_out, B,
+                                     add_start ? 1 : 0, sms, st));
+  else
+    e = PROF(dmvae::K_DECODE, st,
+             dmvae::launch_decode(lo, start_is_shared ? 1 : 0, packed, z, seed, sample_offset, start, nullptr, nullptr,
+                                  out, z_out, B, add_start ? 1 : 0, sms, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "decode");
 }
 
@@ -364,6 +374,12 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
   const cudaError_t e = PROF(dmvae::K_LOSS_GRAD, st,
                              dmvae::launch_loss_grad(lo, B, recon, x, mu, logvar, wv, g_out, g_recon, g_mu, g_logvar, st));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "loss_backward");
+}
+
+int dmvae_set_decode_impl(int impl) {
+  if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_decode_impl: 0 (tensor cores) or 1 (FFMA)");
+  g_decode_impl.store(impl);
+  return DMVAE_OK;
 }
 
 // ---------------------------------------------------------------------------- instrumentation

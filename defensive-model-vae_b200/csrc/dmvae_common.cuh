@@ -30,6 +30,19 @@ constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;  // + one producer warp
 constexpr int STAGE_FLOATS = 8192;                    // 32 KB ring stage
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 
+// Tensor-core (tcgen05 kind::tf32, 3xTF32 split) operands: the five dense layers of the
+// generation path.  Each is stored stage by stage in the exact shared-memory image the
+// UMMA descriptors expect (K-major, no swizzle: 8x4 core matrices of 128 B), high and low
+// TF32 halves side by side, so one TMA bulk copy fills a ring stage (dmvae_decode_tc.cu).
+enum TcId { TC_COND1 = 0, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, NUM_TC };
+struct TcLayer {
+  int off;       // float offset in the packed arena
+  int K;         // contraction length (multiple of 8): dec0 = 128 (h_c) + Lp8 (z, zero padded)
+  int N;         // output width (multiple of 16): 128, or Ip for dec3
+  int kps;       // K-steps (of 8) per 32 KB stage: 8192 / (16 N)
+  int n_stages;
+};
+
 enum LayerId { L_COND0 = 0, L_COND1, L_ENC0, L_ENC1, L_ENC2, L_ENC3, L_HEADS, L_DEC0, L_DEC1, L_DEC2, L_DEC3 };
 
 __host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -63,6 +76,8 @@ struct Layout {
   int r_heads_c;
   int r_dec0z, Lzp;
   int Lq;            // L rounded up to 4 (rows of the latent tiles in shared memory)
+  int Lp8;           // L rounded up to 8 (K granularity of a TF32 MMA)
+  TcLayer tc[NUM_TC];
 };
 
 __host__ __device__ inline int pad_width(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
@@ -112,6 +127,17 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   }
   l.Lzp = l.L <= 32 ? 32 : 64;
   l.r_dec0z = q; q += H * l.Lzp;
+  q = round_up(q, 32);  // 128-byte aligned stages for the TMA bulk copies
+  l.Lp8 = round_up(l.L, 8);
+  for (int t = 0; t < NUM_TC; ++t) {
+    TcLayer& c = l.tc[t];
+    c.K = (t == TC_DEC0) ? H + l.Lp8 : H;
+    c.N = (t == TC_DEC3) ? l.Ip : H;
+    c.kps = STAGE_FLOATS / (16 * c.N);
+    c.n_stages = (c.K / 8 + c.kps - 1) / c.kps;
+    c.off = q;
+    q += c.n_stages * STAGE_FLOATS;
+  }
   l.n_packed = round_up(q, 4);
   return DMVAE_OK;
 }

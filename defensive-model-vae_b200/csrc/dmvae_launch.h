@@ -14,6 +14,11 @@ cudaError_t launch_decode(const Layout& lo, int mode, const float* packed, const
                           uint64_t sample_offset, const float* start, const float* hc_in, float* hc_out, float* out,
                           float* z_out, long long B, int add_start, int sm_count, cudaStream_t stream);
 
+// Tensor-core generation kernel (tcgen05 kind::tf32, 3xTF32): per-row or shared start point.
+cudaError_t launch_decode_tc(const Layout& lo, bool shared_start, const float* packed, const float* z, uint64_t seed,
+                             uint64_t sample_offset, const float* start, float* out, float* z_out, long long B,
+                             int add_start, int sm_count, cudaStream_t stream);
+
 // Tiling of one training pass over B rows.
 struct TrainPlan {
   int M;                   // rows per tile: 64 or 32

@@ -21,6 +21,27 @@ __device__ __forceinline__ float fwd_bias(const Layout& lo, const float* __restr
   return p[lo.p_b[l] + n];
 }
 
+// Round-to-nearest TF32 (10 explicit mantissa bits) of an fp32 value, as an fp32 value.
+__device__ __forceinline__ float tf32_rn(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+// Weight (k, n) of a tensor-core layer in torch layout; dec0's contraction is ordered
+// [h_c (128) ; z (L, zero padded to Lp8)] so that the shared-start path can skip the h_c stages.
+__device__ __forceinline__ float tc_weight(const Layout& lo, const float* __restrict__ p, int t, int k, int n) {
+  switch (t) {
+    case TC_COND1: return p[lo.p_w[L_COND1] + n * H + k];
+    case TC_DEC0: {
+      const int Kd = lo.L + H;
+      if (k < H) return p[lo.p_w[L_DEC0] + n * Kd + lo.L + k];
+      return (k - H) < lo.L ? p[lo.p_w[L_DEC0] + n * Kd + (k - H)] : 0.f;
+    }
+    case TC_DEC1: return p[lo.p_w[L_DEC1] + n * H + k];
+    case TC_DEC2: return p[lo.p_w[L_DEC2] + n * H + k];
+    default: return n < lo.I ? p[lo.p_w[L_DEC3] + n * H + k] : 0.f;
+  }
+}
+
 __global__ void pack_kernel(const __grid_constant__ Layout lo, const float* __restrict__ p, float* __restrict__ q) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nth = gridDim.x * blockDim.x;
@@ -46,6 +67,29 @@ __global__ void pack_kernel(const __grid_constant__ Layout lo, const float* __re
     } else {
       const int cnt = lo.N[l] * lo.K[l];  // [N][K] plain copy (K == 128 for all of these)
       for (int idx = tid; idx < cnt; idx += nth) q[lo.r_w[l] + idx] = p[lo.p_w[l] + idx];
+    }
+  }
+  // tensor-core stages: [stage][term hi|lo][k-step][k-chunk of 4][n-group of 8][8 n][4 k]
+  for (int t = 0; t < NUM_TC; ++t) {
+    const TcLayer c = lo.tc[t];
+    const int ksteps = c.K / 8;
+    for (int idx = tid; idx < c.n_stages * STAGE_FLOATS; idx += nth) {
+      const int stage = idx / STAGE_FLOATS, r = idx - stage * STAGE_FLOATS;
+      const int nks = min(c.kps, ksteps - stage * c.kps);
+      const int term_floats = nks * c.N * 8;
+      const int term = r / term_floats;
+      float v = 0.f;
+      if (term < 2) {
+        const int r2 = r - term * term_floats;
+        const int ks = r2 / (c.N * 8), r3 = r2 - ks * (c.N * 8);
+        const int kc = r3 / (c.N * 4), r4 = r3 - kc * (c.N * 4);
+        const int n = (r4 >> 5) * 8 + ((r4 & 31) >> 2);
+        const int k = (stage * c.kps + ks) * 8 + kc * 4 + (r4 & 3);
+        const float w = tc_weight(lo, p, t, k, n);
+        const float hi = tf32_rn(w);
+        v = term == 0 ? hi : tf32_rn(w - hi);
+      }
+      q[c.off + idx] = v;
     }
   }
 }

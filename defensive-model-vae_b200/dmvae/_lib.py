@@ -58,13 +58,14 @@ SIGNATURES = {
     "dmvae_loss_backward": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeLossWeights), c_int64, _P, _P, _P, _P, _P]),
     "dmvae_cond_encode": (c_int, [_CFG, _P, _P, _P, c_int64, _P]),
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
+    "dmvae_set_decode_impl": (c_int, [c_int]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),
     "dmvae_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 11
+KERNEL_COUNT = 12
 
 _lib = None
 

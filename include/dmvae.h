@@ -98,6 +98,12 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
                  uint64_t sample_offset, const float* start, int start_is_shared, float* out,
                  float* z_out, int64_t B, int add_start, void* stream);
 
+/* Which kernel dmvae_decode launches: 0 (default) = decode_tc_kernel, the dense layers on the
+ * tcgen05 tensor cores as error-compensated 3xTF32 with activations resident in tensor
+ * memory; 1 = decode_kernel, everything in FP32 FFMA.  Both hold the 1e-5 tolerance; the
+ * switch exists so that bench.py can report the two side by side. */
+int dmvae_set_decode_impl(int impl);
+
 /* model.condition_encoder(c) on its own (Training_VAE.py:132-137; called directly
  * at Tools.py:55, :898): start (B,2) -> h_c (B,128). */
 int dmvae_cond_encode(const DmvaeCfg* cfg, const float* packed, const float* start, float* h_c, int64_t B,
@@ -173,8 +179,9 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
  * Nothing in the reference corresponds to these: they let bench.py report what the
  * library launched and how long the dominant kernel ran inside the timed region.
  * Kernel ids: 0 pack, 1 decode, 2 train (fused), 3 train (forward), 4 train
- * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe. */
-#define DMVAE_KERNEL_COUNT 11
+ * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe,
+ * 11 decode (tensor cores). */
+#define DMVAE_KERNEL_COUNT 12
 const char* dmvae_kernel_name(int kernel);
 /* Kernels launched by this process since the library was loaded (kernel < 0: all). */
 int64_t dmvae_launch_count(int kernel);
