@@ -139,7 +139,7 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (g_decode_impl.load() == 0)
+  if (g_decode_impl.load() == 0 && dmvae::decode_tc_supported(lo, start_is_shared != 0))
     e = PROF(dmvae::K_DECODE_TC, st,
              dmvae::launch_decode_tc(lo, start_is_shared != 0, packed, z, seed, sample_offset, start, out, z_out, B,
                                      add_start ? 1 : 0, sms, st));
@@ -379,6 +379,11 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
 int dmvae_set_decode_impl(int impl) {
   if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_decode_impl: 0 (tensor cores) or 1 (FFMA)");
   g_decode_impl.store(impl);
+  return DMVAE_OK;
+}
+
+int dmvae_debug_decode_trace(void* device_int64x128) {
+  dmvae::set_decode_tc_trace(static_cast<long long*>(device_int64x128));
   return DMVAE_OK;
 }
 

@@ -34,10 +34,11 @@ constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 // generation path.  Each is stored stage by stage in the exact shared-memory image the
 // UMMA descriptors expect (K-major, no swizzle: 8x4 core matrices of 128 B), high and low
 // TF32 halves side by side, so one TMA bulk copy fills a ring stage (dmvae_decode_tc.cu).
-enum TcId { TC_COND1 = 0, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, NUM_TC };
+enum TcId { TC_COND1 = 0, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, TC_COND0, NUM_TC };
 struct TcLayer {
   int off;       // float offset in the packed arena
-  int K;         // contraction length (multiple of 8): dec0 = 128 (h_c) + Lp8 (z, zero padded)
+  int K;         // contraction length (multiple of 8): dec0 = 128 (h_c) + Lp8 (z, zero padded);
+                 // cond0 = 8: [x0, y0, 1 (bias row), 0...]
   int N;         // output width (multiple of 16): 128, or Ip for dec3
   int kps;       // K-steps (of 8) per 32 KB stage: 8192 / (16 N)
   int n_stages;
@@ -131,7 +132,7 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   l.Lp8 = round_up(l.L, 8);
   for (int t = 0; t < NUM_TC; ++t) {
     TcLayer& c = l.tc[t];
-    c.K = (t == TC_DEC0) ? H + l.Lp8 : H;
+    c.K = (t == TC_DEC0) ? H + l.Lp8 : (t == TC_COND0 ? 8 : H);
     c.N = (t == TC_DEC3) ? l.Ip : H;
     c.kps = STAGE_FLOATS / (16 * c.N);
     c.n_stages = (c.K / 8 + c.kps - 1) / c.kps;

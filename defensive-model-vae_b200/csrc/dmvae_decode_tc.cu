@@ -13,21 +13,30 @@
 //     TMEM columns [  0,128)  D      fp32 accumulator of the layer in flight (lane = row)
 //                  [128,320)  A_hi   TF32 high halves of the layer input: 128 hidden + <=64 latent
 //                  [320,512)  A_lo   TF32 low halves
-//   MMA warp      one elected thread issues  D = A(TMEM) x B(smem)  per 8-deep K step, three terms
-//   producer warp streams the B operands (weights, pre-split and pre-laid-out by pack_kernel in
-//                 the UMMA K-major core-matrix image) L2 -> smem ring with TMA bulk copies
-//   8 epilogue warps  tcgen05.ld D -> bias + ReLU -> hi/lo split -> tcgen05.st A for the next
-//                 layer (warp w owns TMEM lanes 32*(w%4).., column half w/4); draw / load the
-//                 latents; the last layer goes registers -> smem -> one TMA bulk store per tile.
-// The narrow layers stay FFMA: cond0 (2 -> 128) in the epilogue threads, and with a shared start
+//   MMA warp        walks the layer program convergently, one elected lane issues
+//                   D = A(TMEM) x B(smem)  per 8-deep K step, three terms
+//   producer warp   streams the B operands (weights, pre-split and pre-laid-out by pack_kernel in
+//                   the UMMA K-major core-matrix image) L2 -> smem ring with TMA bulk copies
+//   8 hidden warps  tcgen05.ld D -> bias + ReLU -> hi/lo split -> tcgen05.st A for the next layer
+//                   (warp w owns TMEM lanes 32*(w%4).., column half w/4)
+//   4 output warps  off the critical path: draw / load the latents and start points of the NEXT
+//                   tile into the spare A columns while the hidden layers run; drain the last
+//                   layer D -> registers -> smem -> one TMA bulk store per tile.
+// With a per-row start point the first condition-encoder layer (2 -> 128) is one more tiny MMA
+// over the columns [x0, y0, 1, 0...] (the bias rides on the ones column); with a shared start
 // point the whole condition encoder is folded once per CTA into the bias of dec0.
 #include "dmvae_common.cuh"
 
 namespace dmvae {
 
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 8;                  // hidden-layer epilogue warps
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = TC_EPI_THREADS + 64;  // + producer warp + MMA warp
+constexpr int TC_OUT_WARPS = 4;                  // staging + output warps
+constexpr int TC_OUT_THREADS = TC_OUT_WARPS * 32;
+constexpr int TC_PRODUCER_WARP = TC_EPI_WARPS + TC_OUT_WARPS;
+constexpr int TC_MMA_WARP = TC_PRODUCER_WARP + 1;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
+constexpr int TC_MAX_OPS = 6;
 constexpr int TC_M = 128;
 constexpr uint32_t TM_D = 0, TM_AHI = 128, TM_ALO = 320, TM_Z = 128 /* within an A region */, TM_COLS = 512;
 
@@ -41,6 +50,7 @@ struct TcArgs {
   unsigned long long seed, sample_offset;
   long long B;
   int shared_start, add_start, stages, out_bufs, bulk_ok;
+  long long* trace;   // development aid: per-op clock64 stamps of CTA 0 (null in production)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -110,7 +120,21 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void out_sync() { asm volatile("bar.sync 3, %0;" ::"n"(TC_OUT_THREADS) : "memory"); }
 
 // x = hi + lo with hi = round-to-nearest TF32 of x; lo is cut to TF32 by the tensor core itself
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -140,13 +164,16 @@ struct TcOp {
   int N;
   int a_col;    // first A column inside the A regions
 };
-__device__ __forceinline__ int tc_program(const Layout& lo, bool shared_start, TcOp (&ops)[NUM_TC]) {
+// shared start:  dec0 (latent rows only) -> dec1 -> dec2 -> dec3
+// per-row start: cond0 -> cond1 -> dec0 -> dec1 -> dec2 -> dec3
+__device__ __forceinline__ int tc_program(const Layout& lo, bool shared_start, TcOp (&ops)[TC_MAX_OPS]) {
   int n = 0;
-  if (!shared_start) ops[n++] = TcOp{lo.tc[TC_COND1].off, H / 8, lo.tc[TC_COND1].kps, H, 0};
-  if (shared_start) {  // only the latent rows of dec0: skip the stages of the h_c rows
+  if (shared_start) {  // skip the stages of dec0's h_c rows
     const TcLayer& c = lo.tc[TC_DEC0];
     ops[n++] = TcOp{c.off + (H / 8 / c.kps) * STAGE_FLOATS, lo.Lp8 / 8, c.kps, H, (int)TM_Z};
   } else {
+    ops[n++] = TcOp{lo.tc[TC_COND0].off, 1, lo.tc[TC_COND0].kps, H, (int)TM_Z + lo.Lp8};
+    ops[n++] = TcOp{lo.tc[TC_COND1].off, H / 8, lo.tc[TC_COND1].kps, H, 0};
     ops[n++] = TcOp{lo.tc[TC_DEC0].off, (H + lo.Lp8) / 8, lo.tc[TC_DEC0].kps, H, 0};
   }
   ops[n++] = TcOp{lo.tc[TC_DEC1].off, H / 8, lo.tc[TC_DEC1].kps, H, 0};
@@ -156,13 +183,13 @@ __device__ __forceinline__ int tc_program(const Layout& lo, bool shared_start, T
 }
 
 struct TcSmem {
-  float *ring, *outs, *bias, *w0, *hb, *tmp;
-  uint64_t *full, *empty, *d_full, *a_ready;
+  float *ring, *outs, *bias, *tmp;
+  uint64_t *full, *empty, *d_hid, *d_out, *z_free, *a_ready, *tile_ready;
   uint32_t* tmem_slot;
 };
-// bias rows: 0 cond0, 1 cond1, 2 dec0, 3 dec1, 4 dec2, 5 dec3 (each 128 floats)
+// bias: one 128-float row per op in program order (the last row = dec3's bias, Ip entries)
 __host__ __device__ inline size_t tc_smem_floats(const Layout& lo, int stages, int out_bufs) {
-  return (size_t)stages * STAGE_FLOATS + (size_t)out_bufs * TC_M * lo.I + 6 * H + 2 * H + H + 2 * H;
+  return (size_t)stages * STAGE_FLOATS + (size_t)out_bufs * TC_M * lo.I + TC_MAX_OPS * H + 2 * H;
 }
 __host__ __device__ inline size_t tc_smem_bytes(const Layout& lo, int stages, int out_bufs) {
   return tc_smem_floats(lo, stages, out_bufs) * 4 + 32 * 8 + 16 + 1024;
@@ -180,14 +207,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     s.ring = reinterpret_cast<float*>(p);
     s.outs = s.ring + (size_t)a.stages * STAGE_FLOATS;
     s.bias = s.outs + (size_t)a.out_bufs * TC_M * I;
-    s.w0 = s.bias + 6 * H;
-    s.hb = s.w0 + 2 * H;
-    s.tmp = s.hb + H;
+    s.tmp = s.bias + TC_MAX_OPS * H;
     s.full = reinterpret_cast<uint64_t*>(s.tmp + 2 * H);
     s.empty = s.full + 8;
-    s.d_full = s.empty + 8;
-    s.a_ready = s.d_full + 1;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.a_ready + 1);
+    s.d_hid = s.empty + 8;
+    s.d_out = s.d_hid + 1;
+    s.z_free = s.d_out + 1;
+    s.a_ready = s.z_free + 1;
+    s.tile_ready = s.a_ready + 1;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.tile_ready + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
@@ -199,20 +227,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       mbar_init(&s.full[st], 1);
       mbar_init(&s.empty[st], 1);
     }
-    mbar_init(s.d_full, 1);
+    // Every barrier completes exactly one phase per hand-shake with its consumers, so no waiter
+    // can fall two phases behind:  d_hid  MMA -> hidden warps (one phase per hidden layer),
+    // d_out  MMA -> output warps (last layer), z_free  MMA -> output warps (latent columns read),
+    // a_ready  hidden warps -> MMA,  tile_ready  output warps -> MMA.
+    mbar_init(s.d_hid, 1);
+    mbar_init(s.d_out, 1);
+    mbar_init(s.z_free, 1);
     mbar_init(s.a_ready, TC_EPI_WARPS);
+    mbar_init(s.tile_ready, TC_OUT_WARPS);
     mbar_fence_init();
   }
-  if (warp == TC_EPI_WARPS) tmem_alloc(s.tmem_slot, TM_COLS);  // whole warp; this warp also frees it
+  if (warp == TC_PRODUCER_WARP) tmem_alloc(s.tmem_slot, TM_COLS);  // whole warp; this warp also frees it
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s.tmem_slot;
 
-  TcOp ops[NUM_TC];
+  TcOp ops[TC_MAX_OPS];
   const int n_ops = tc_program(lo, shared_start, ops);
+  const int zop = shared_start ? 0 : 2;  // the op that reads the staged latent columns last (dec0)
 
-  if (warp == TC_EPI_WARPS) {
+  if (warp == TC_PRODUCER_WARP) {
     // ===================== producer warp: weights L2 -> smem ring ============================
     if (lane == 0) {
       RingStateRt rs(a.stages);
@@ -229,70 +265,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
           }
         }
     }
-  } else if (warp == TC_EPI_WARPS + 1) {
-    // ===================== MMA warp: one thread issues every tcgen05.mma =====================
-    if (lane == 0) {
-      RingStateRt rs(a.stages);
-      uint32_t a_phase = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int o = 0; o < n_ops; ++o) {
-          const TcOp op = ops[o];
-          const uint32_t idesc = umma_idesc_tf32(TC_M, op.N);
-          const uint32_t kstep_bytes = (uint32_t)op.N * 32u;  // one 8-deep K step of B: N x 8 TF32
-          mbar_wait(s.a_ready, a_phase);  // the layer input is in A, and D has been drained
+  } else if (warp == TC_MMA_WARP) {
+    // ===================== MMA warp ===========================================================
+    // The whole warp walks the program convergently so that every operand of tcgen05.mma is
+    // warp-uniform (uniform registers, no per-thread fix-up code); one elected lane issues.
+    RingStateRt rs(a.stages);
+    uint32_t a_phase = 0, t_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int o = 0; o < n_ops; ++o) {
+        const TcOp op = ops[o];
+        const uint32_t idesc = umma_idesc_tf32(TC_M, op.N);
+        const uint32_t kstep_bytes = (uint32_t)op.N * 32u;  // one 8-deep K step of B: N x 8 TF32
+        const uint64_t desc_hi_bits = umma_desc_kmajor(0u, (uint32_t)op.N * 16u, 128u);
+        if (o == 0) {  // latents / start points of this tile staged, D of the previous tile drained
+          mbar_wait(s.tile_ready, t_phase);
+          t_phase ^= 1u;
+        } else {       // the previous layer's output is in A
+          mbar_wait(s.a_ready, a_phase);
           a_phase ^= 1u;
+        }
+        tc_fence_after();
+        const long long tix = (tile - blockIdx.x) / gridDim.x;
+        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tix < 4 && lane == 0;
+        if (tr) a.trace[(tix * 8 + o) * 4 + 0] = clock64();
+        uint32_t acc = 0;
+        uint32_t a_hi = tmem + TM_AHI + (uint32_t)op.a_col, a_lo = tmem + TM_ALO + (uint32_t)op.a_col;
+        for (int k0 = 0; k0 < op.ksteps; k0 += op.kps) {
+          const int nks = min(op.kps, op.ksteps - k0);
+          mbar_wait(&s.full[rs.stage], rs.phase);
           tc_fence_after();
-          uint32_t acc = 0;
-          for (int k0 = 0; k0 < op.ksteps; k0 += op.kps) {
-            const int nks = min(op.kps, op.ksteps - k0);
-            mbar_wait(&s.full[rs.stage], rs.phase);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(s.ring + rs.stage * STAGE_FLOATS);
-            const uint32_t b_lo = b_hi + (uint32_t)nks * kstep_bytes;
+          const uint32_t b_hi = smem_u32(s.ring + rs.stage * STAGE_FLOATS);
+          uint64_t dh = desc_hi_bits | (uint64_t)(b_hi >> 4);
+          uint64_t dl = desc_hi_bits | (uint64_t)((b_hi + (uint32_t)nks * kstep_bytes) >> 4);
+          const uint64_t dinc = (uint64_t)(kstep_bytes >> 4);
+          if (elect_one()) {
+#pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
-              const uint32_t col = (uint32_t)op.a_col + 8u * (uint32_t)(k0 + ks);
-              const uint64_t dh = umma_desc_kmajor(b_hi + ks * kstep_bytes, (uint32_t)op.N * 16u, 128u);
-              const uint64_t dl = umma_desc_kmajor(b_lo + ks * kstep_bytes, (uint32_t)op.N * 16u, 128u);
-              umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + col, dh, idesc, acc);   // a_hi * b_hi
-              umma_tf32_ts(tmem + TM_D, tmem + TM_ALO + col, dh, idesc, 1u);    // a_lo * b_hi
-              umma_tf32_ts(tmem + TM_D, tmem + TM_AHI + col, dl, idesc, 1u);    // a_hi * b_lo
+              umma_tf32_ts(tmem + TM_D, a_hi, dh, idesc, acc);   // a_hi * b_hi
+              umma_tf32_ts(tmem + TM_D, a_lo, dh, idesc, 1u);    // a_lo * b_hi
+              umma_tf32_ts(tmem + TM_D, a_hi, dl, idesc, 1u);    // a_hi * b_lo
               acc = 1u;
+              a_hi += 8u; a_lo += 8u; dh += dinc; dl += dinc;
             }
             umma_commit(&s.empty[rs.stage]);  // the stage is free once these MMAs have read it
-            rs.advance();
           }
-          umma_commit(s.d_full);  // accumulator complete -> epilogue
+          __syncwarp();
+          a_hi = tmem + TM_AHI + (uint32_t)op.a_col + 8u * (uint32_t)(k0 + nks);
+          a_lo = tmem + TM_ALO + (uint32_t)op.a_col + 8u * (uint32_t)(k0 + nks);
+          acc = 1u;
+          rs.advance();
         }
-    }
-  } else {
-    // ===================== epilogue warps ====================================================
+        if (elect_one()) {
+          if (o == zop) umma_commit(s.z_free);                       // the staged columns have been read
+          umma_commit(o == n_ops - 1 ? s.d_out : s.d_hid);           // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (tr) a.trace[(tix * 8 + o) * 4 + 1] = clock64();
+      }
+  } else if (warp < TC_EPI_WARPS) {
+    // ===================== hidden-layer epilogue warps ======================================
     const int q = warp & 3, h = warp >> 2;     // TMEM lane quarter, column half
-    const int m = q * 32 + lane;               // row of the tile owned by this thread
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    const float* __restrict__ bias_of[6] = {s.bias, s.bias + H, s.bias + 2 * H, s.bias + 3 * H, s.bias + 4 * H, s.bias + 5 * H};
 
-    // biases and cond0 weights to shared memory (broadcast reads in the epilogues)
+    // bias rows in program order (broadcast reads in the epilogues)
     for (int i = tid; i < H; i += TC_EPI_THREADS) {
-      s.bias[0 * H + i] = pk[lo.q_b[L_COND0] + i];
-      s.bias[1 * H + i] = pk[lo.q_b[L_COND1] + i];
-      s.bias[2 * H + i] = pk[lo.q_b[L_DEC0] + i];
-      s.bias[3 * H + i] = pk[lo.q_b[L_DEC1] + i];
-      s.bias[4 * H + i] = pk[lo.q_b[L_DEC2] + i];
-      s.bias[5 * H + i] = i < lo.Ip ? pk[lo.q_b[L_DEC3] + i] : 0.f;
-      s.w0[i] = pk[lo.q_w[L_COND0] + i];
-      s.w0[H + i] = pk[lo.q_w[L_COND0] + H + i];
+      int r = 0;
+      if (!shared_start) {
+        s.bias[r++ * H + i] = 0.f;                                  // cond0: the bias rides on the ones column
+        s.bias[r++ * H + i] = pk[lo.q_b[L_COND1] + i];
+      }
+      s.bias[r++ * H + i] = pk[lo.q_b[L_DEC0] + i];
+      s.bias[r++ * H + i] = pk[lo.q_b[L_DEC1] + i];
+      s.bias[r++ * H + i] = pk[lo.q_b[L_DEC2] + i];
+      s.bias[r++ * H + i] = i < lo.Ip ? pk[lo.q_b[L_DEC3] + i] : 0.f;
     }
-    float sx_sh = 0.f, sy_sh = 0.f;
     if (shared_start) {
       // one start point for the whole launch: condition encoder once per CTA, folded into
       // the bias of dec0:  hb[n] = b_dec0[n] + sum_k Wdec0[n][L+k] * h_c[k]
-      sx_sh = a.start[0];
-      sy_sh = a.start[1];
+      const float sx = a.start[0], sy = a.start[1];
       if (tid < H) {
         const float* w0 = pk + lo.q_w[L_COND0];
         float v = pk[lo.q_b[L_COND0] + tid];
-        v = fmaf(w0[tid], sx_sh, v);
-        v = fmaf(w0[H + tid], sy_sh, v);
+        v = fmaf(w0[tid], sx, v);
+        v = fmaf(w0[H + tid], sy, v);
         s.tmp[tid] = fmaxf(v, 0.f);
       }
       epi_sync();
@@ -307,19 +362,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
         const float* wd = pk + lo.q_w[L_DEC0] + L * H;
         float v = pk[lo.q_b[L_DEC0] + tid];
         for (int k = 0; k < H; ++k) v = fmaf(wd[k * H + tid], s.tmp[H + k], v);
-        s.hb[tid] = v;
+        s.bias[tid] = v;
       }
     }
     epi_sync();
-    if (shared_start) bias_of[2] = s.hb;
+    // the output warps read the dec3 bias row: everybody meets once before the tile loop
+    asm volatile("bar.sync 4, %0;" ::"n"(TC_EPI_THREADS + TC_OUT_THREADS) : "memory");
 
-    // writes the layer input of a tile: latents (both modes) and cond0 (per-row start) -> A
-    float sx = sx_sh, sy = sy_sh;   // start point of the row this thread owns, for the tile being STAGED
+    uint32_t d_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int o = 0; o < n_ops - 1; ++o) {
+        const float* __restrict__ bias = s.bias + o * H + h * 64;
+        mbar_wait(s.d_hid, d_phase);
+        d_phase ^= 1u;
+        tc_fence_after();
+        const long long tix = (tile - blockIdx.x) / gridDim.x;
+        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tix < 4 && tid == 0;
+        if (tr) a.trace[(tix * 8 + o) * 4 + 2] = clock64();
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + TM_D + h * 64 + c * 16, v[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[16], lw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_tf32(fmaxf(__uint_as_float(v[c][j]) + bias[c * 16 + j], 0.f), hi[j], lw[j]);
+          tmem_st16(lane_base + TM_AHI + h * 64 + c * 16, hi);
+          tmem_st16(lane_base + TM_ALO + h * 64 + c * 16, lw);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s.a_ready);
+        if (tr) a.trace[(tix * 8 + o) * 4 + 3] = clock64();
+      }
+    }
+  } else {
+    // ===================== staging + output warps ===========================================
+    const int q = warp - TC_EPI_WARPS;         // TMEM lane quarter (warp 8..11 -> warp % 4 = 0..3)
+    const int otid = tid - TC_EPI_THREADS;
+    const int m = q * 32 + lane;               // row of the tile owned by this thread
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    float sx_cur = 0.f, sy_cur = 0.f, sx_nxt = 0.f, sy_nxt = 0.f;
+    if (shared_start) { sx_cur = sx_nxt = a.start[0]; sy_cur = sy_nxt = a.start[1]; }
+
+    // latents (and, per-row, the start point as [x0, y0, 1, 0, 0, 0, 0, 0]) of a tile -> spare A columns
     auto stage_tile = [&](long long tile) {
-      const long long m0 = tile * TC_M;
-      const bool row_ok = m0 + m < a.B;
-      const long long row = m0 + m;
-      for (int jb = h; jb < Lp8 / 4; jb += 2) {
+      const long long row = tile * TC_M + m;
+      const bool row_ok = row < a.B;
+      for (int jb = 0; jb < Lp8 / 4; ++jb) {
         float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (row_ok) {
           if (a.z != nullptr) {
@@ -343,121 +435,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
         tmem_st4(lane_base + TM_ALO + TM_Z + 4 * jb, lw[0], lw[1], lw[2], lw[3]);
       }
       if (!shared_start) {
-        sx = row_ok ? __ldg(a.start + row * 2) : 0.f;
-        sy = row_ok ? __ldg(a.start + row * 2 + 1) : 0.f;
-        // cond0 (Training_VAE.py:132-133): relu(W0 [x0, y0] + b0), 64 of the 128 features per thread
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[16], lw[16];
-          const int n0 = h * 64 + c * 16;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float v = s.bias[n0 + j];
-            v = fmaf(s.w0[n0 + j], sx, v);
-            v = fmaf(s.w0[H + n0 + j], sy, v);
-            split_tf32(fmaxf(v, 0.f), hi[j], lw[j]);
-          }
-          tmem_st16(lane_base + TM_AHI + n0, hi);
-          tmem_st16(lane_base + TM_ALO + n0, lw);
-        }
+        sx_nxt = row_ok ? __ldg(a.start + row * 2) : 0.f;
+        sy_nxt = row_ok ? __ldg(a.start + row * 2 + 1) : 0.f;
+        uint32_t xh, xl, yh, yl;
+        split_tf32(sx_nxt, xh, xl);
+        split_tf32(sy_nxt, yh, yl);
+        const uint32_t one = __float_as_uint(1.0f);
+        tmem_st4(lane_base + TM_AHI + TM_Z + Lp8, xh, yh, one, 0u);
+        tmem_st4(lane_base + TM_AHI + TM_Z + Lp8 + 4, 0u, 0u, 0u, 0u);
+        tmem_st4(lane_base + TM_ALO + TM_Z + Lp8, xl, yl, 0u, 0u);
+        tmem_st4(lane_base + TM_ALO + TM_Z + Lp8 + 4, 0u, 0u, 0u, 0u);
       }
-    };
-    auto publish = [&]() {  // A written / D read by this warp -> MMA warp
       tmem_st_wait();
+    };
+    auto release_tile = [&]() {  // staged columns written, D drained by this warp -> MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s.a_ready);
+      if (lane == 0) mbar_arrive(s.tile_ready);
     };
 
+    asm volatile("bar.sync 4, %0;" ::"n"(TC_EPI_THREADS + TC_OUT_THREADS) : "memory");  // bias rows are in smem
+    const float* __restrict__ b3 = s.bias + (n_ops - 1) * H;
+    // start-point add per column class n % 3 (0: time, 1: x, 2: y), Tools.py:61-63
     uint32_t d_phase = 0;
     int out_buf = 0;
-    if ((long long)blockIdx.x < n_tiles) {
-      stage_tile(blockIdx.x);
-      publish();
-    }
+    stage_tile(blockIdx.x);
+    sx_cur = sx_nxt; sy_cur = sy_nxt;
+    release_tile();
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long m0 = tile * TC_M;
       const int valid = (int)min((long long)TC_M, a.B - m0);
-      const float out_sx = sx, out_sy = sy;  // start point of THIS tile's row (stage_tile overwrites sx, sy)
-      // ---- hidden layers: D -> relu(D + bias) -> A ------------------------------------------
-      for (int o = 0; o < n_ops - 1; ++o) {
-        const float* __restrict__ bias = bias_of[shared_start ? o + 2 : o + 1];
-        mbar_wait(s.d_full, d_phase);
-        d_phase ^= 1u;
+      const long long next = tile + gridDim.x;
+      mbar_wait(s.z_free, d_phase);  // the staged columns of this tile have been consumed:
+      if (next < n_tiles) {          // stage the next tile while the hidden layers run
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int n0 = h * 64 + c * 16;
-          uint32_t v[16], hi[16], lw[16];
-          tmem_ld16(lane_base + TM_D + n0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) split_tf32(fmaxf(__uint_as_float(v[j]) + bias[n0 + j], 0.f), hi[j], lw[j]);
-          tmem_st16(lane_base + TM_AHI + n0, hi);
-          tmem_st16(lane_base + TM_ALO + n0, lw);
-        }
-        publish();
+        stage_tile(next);
       }
-      // ---- last layer: D (Ip columns) -> registers; release D; stage the next tile; store ----
-      mbar_wait(s.d_full, d_phase);
+      mbar_wait(s.d_out, d_phase);
       d_phase ^= 1u;
       tc_fence_after();
-      const int half = lo.Ip >> 1;          // columns per column-half: 16, 32 or 64
-      uint32_t o[4][16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c * 16 < half) tmem_ld16(lane_base + TM_D + h * half + c * 16, o[c]);
-      tmem_ld_wait();
-      const long long next = tile + gridDim.x;
-      if (next < n_tiles) stage_tile(next);
-      publish();  // also for the last tile: keeps the arrival count per phase uniform (nobody waits on it)
+      const long long tix = (tile - blockIdx.x) / gridDim.x;
+      const bool tr = a.trace != nullptr && blockIdx.x == 0 && tix < 4 && otid == 0;
+      if (tr) a.trace[(tix * 8 + n_ops - 1) * 4 + 2] = clock64();
 
       float* stage_out = s.outs + (size_t)out_buf * TC_M * I;
-      if (a.out_bufs > 1) {
-        if (tid == 0) tma_store_wait_read<1>();  // the store that last read this buffer has drained it
-      } else {
-        if (tid == 0) tma_store_wait_read<0>();
+      if (otid == 0) {  // the bulk store that last read this buffer has drained it
+        if (a.out_bufs > 1) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
       }
-      epi_sync();
-      if (m < valid) {
-        const float* __restrict__ b3 = bias_of[5];
+      out_sync();
+      const float add0 = 0.f, add1 = a.add_start ? sx_cur : 0.f, add2 = a.add_start ? sy_cur : 0.f;
+      const int n_chunks = lo.Ip >> 4;  // 2, 4 or 8
+      for (int c0 = 0; c0 < n_chunks; c0 += 4) {
+        uint32_t o[4][16];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c * 16 < half) {
+          if (c0 + c < n_chunks) tmem_ld16(lane_base + TM_D + (c0 + c) * 16, o[c]);
+        tmem_ld_wait();
+        if (c0 + 4 >= n_chunks) {  // D is in registers: the next tile may start
+          release_tile();
+          if (tr) a.trace[(tix * 8 + n_ops - 1) * 4 + 3] = clock64();
+        }
+        if (m < valid) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = h * half + c * 16 + j;
-              if (n < I) {
-                float val = __uint_as_float(o[c][j]) + b3[n];
-                if (a.add_start) {
-                  const int d = n % 3;
-                  if (d == 1) val = out_sx + val;
-                  else if (d == 2) val = out_sy + val;
+          for (int c = 0; c < 4; ++c)
+            if (c0 + c < n_chunks) {
+              const int nb = (c0 + c) * 16;
+              const int r0 = nb % 3;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = nb + j;
+                if (n < I) {
+                  const int d = (r0 + j) % 3;
+                  const float rel = __uint_as_float(o[c][j]) + b3[n];
+                  stage_out[m * I + n] = rel + (d == 0 ? add0 : (d == 1 ? add1 : add2));
                 }
-                stage_out[m * I + n] = val;
               }
             }
-          }
+        }
       }
+      sx_cur = sx_nxt; sy_cur = sy_nxt;
       const uint32_t bytes = (uint32_t)valid * (uint32_t)I * 4u;
       float* gdst = a.out + m0 * I;
       if (a.bulk_ok && (bytes & 15u) == 0) {
         fence_proxy_async_smem();
-        epi_sync();
-        if (tid == 0) tma_store_1d(gdst, stage_out, bytes);
+        out_sync();
+        if (otid == 0) tma_store_1d(gdst, stage_out, bytes);
       } else {
-        epi_sync();
-        for (int idx = tid; idx < valid * I; idx += TC_EPI_THREADS) gdst[idx] = stage_out[idx];
-        epi_sync();  // stage_out may be rewritten two tiles from now (or next tile with one buffer)
+        out_sync();
+        for (int idx = otid; idx < valid * I; idx += TC_OUT_THREADS) gdst[idx] = stage_out[idx];
+        out_sync();  // stage_out may be rewritten two tiles from now (or next tile with one buffer)
       }
       if (a.out_bufs > 1) out_buf ^= 1;
     }
-    if (tid == 0) tma_store_wait_all();
+    if (otid == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_EPI_WARPS) tmem_dealloc(tmem, TM_COLS);
+  if (warp == TC_PRODUCER_WARP) tmem_dealloc(tmem, TM_COLS);
+}
+
+static long long* g_tc_trace = nullptr;
+void set_decode_tc_trace(long long* p) { g_tc_trace = p; }
+
+// false when the configuration needs more spare A columns than tensor memory has
+bool decode_tc_supported(const Layout& lo, bool shared_start) {
+  return shared_start ? lo.Lp8 <= 64 : lo.Lp8 + 8 <= 64;
 }
 
 cudaError_t launch_decode_tc(const Layout& lo, bool shared_start, const float* packed, const float* z, uint64_t seed,
@@ -469,6 +552,7 @@ cudaError_t launch_decode_tc(const Layout& lo, bool shared_start, const float* p
   a.seed = seed; a.sample_offset = sample_offset; a.B = B;
   a.shared_start = shared_start ? 1 : 0;
   a.add_start = add_start;
+  a.trace = g_tc_trace;
   int stages = 4, out_bufs = 2;
   constexpr size_t LIMIT = 232448;
   if (tc_smem_bytes(lo, stages, out_bufs) > LIMIT) out_bufs = 1;

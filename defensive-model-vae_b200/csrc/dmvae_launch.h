@@ -19,6 +19,9 @@ cudaError_t launch_decode_tc(const Layout& lo, bool shared_start, const float* p
                              uint64_t sample_offset, const float* start, float* out, float* z_out, long long B,
                              int add_start, int sm_count, cudaStream_t stream);
 
+bool decode_tc_supported(const Layout& lo, bool shared_start);
+void set_decode_tc_trace(long long* device_buffer);  // development aid (128 int64), null = off
+
 // Tiling of one training pass over B rows.
 struct TrainPlan {
   int M;                   // rows per tile: 64 or 32

@@ -30,6 +30,8 @@ __device__ __forceinline__ float tf32_rn(float x) {
 // [h_c (128) ; z (L, zero padded to Lp8)] so that the shared-start path can skip the h_c stages.
 __device__ __forceinline__ float tc_weight(const Layout& lo, const float* __restrict__ p, int t, int k, int n) {
   switch (t) {
+    case TC_COND0:  // rows: weight of x0, weight of y0, bias (multiplies the ones column), zeros
+      return k < 2 ? p[lo.p_w[L_COND0] + n * 2 + k] : (k == 2 ? p[lo.p_b[L_COND0] + n] : 0.f);
     case TC_COND1: return p[lo.p_w[L_COND1] + n * H + k];
     case TC_DEC0: {
       const int Kd = lo.L + H;

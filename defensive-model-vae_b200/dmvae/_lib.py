@@ -59,6 +59,7 @@ SIGNATURES = {
     "dmvae_cond_encode": (c_int, [_CFG, _P, _P, _P, c_int64, _P]),
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
     "dmvae_set_decode_impl": (c_int, [c_int]),
+    "dmvae_debug_decode_trace": (c_int, [_P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),

@@ -103,6 +103,9 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
  * memory; 1 = decode_kernel, everything in FP32 FFMA.  Both hold the 1e-5 tolerance; the
  * switch exists so that bench.py can report the two side by side. */
 int dmvae_set_decode_impl(int impl);
+/* Development aid: device buffer of 128 int64 that CTA 0 of decode_tc_kernel fills with
+ * clock64 stamps per layer step (NULL = off, the default). */
+int dmvae_debug_decode_trace(void* device_int64x128);
 
 /* model.condition_encoder(c) on its own (Training_VAE.py:132-137; called directly
  * at Tools.py:55, :898): start (B,2) -> h_c (B,128). */
