@@ -5,12 +5,12 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v)
 SRCS=(dmvae_api.cu dmvae_pack.cu dmvae_decode.cu dmvae_decode_tc.cu)
-for extra in dmvae_train.cu dmvae_adam.cu dmvae_loss.cu dmvae_prof.cu; do [ -f "$extra" ] && SRCS+=("$extra"); done
+for extra in dmvae_train.cu dmvae_train_tc.cu dmvae_adam.cu dmvae_loss.cu dmvae_prof.cu; do [ -f "$extra" ] && SRCS+=("$extra"); done
 mkdir -p build
 objs=()
 for s in "${SRCS[@]}"; do
   o="build/${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ dmvae_common.cuh -nt "$o" ] || [ dmvae_launch.h -nt "$o" ] || [ dmvae_prof.h -nt "$o" ] || [ ../../include/dmvae.h -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ dmvae_common.cuh -nt "$o" ] || [ dmvae_tc.cuh -nt "$o" ] || [ dmvae_launch.h -nt "$o" ] || [ dmvae_prof.h -nt "$o" ] || [ ../../include/dmvae.h -nt "$o" ]; then
     echo "nvcc $s"
     "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" 2> "build/${s%.cu}.ptxas.log" || { cat "build/${s%.cu}.ptxas.log"; exit 1; }
   fi

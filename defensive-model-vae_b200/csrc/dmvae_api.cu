@@ -61,6 +61,8 @@ int require_device(int* sm_count) {
 
 // 0 = tensor cores (tcgen05, 3xTF32; default), 1 = FP32 FFMA kernel
 std::atomic<int> g_decode_impl{0};
+// 0 = tensor cores where supported (default), 1 = FFMA kernels
+std::atomic<int> g_train_impl{0};
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -216,7 +218,13 @@ int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B) {
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const dmvae::TrainPlan p = dmvae::plan_train(lo, B > 0 ? B : 1, sms, false);
-  return (int64_t)(workspace_floats(p) * sizeof(float));
+  size_t floats = workspace_floats(p);
+  if (dmvae::train_tc_supported(lo)) {  // covers both implementations (dmvae_set_train_impl)
+    const dmvae::TrainTcPlan t = dmvae::plan_train_tc(lo, B > 0 ? B : 1, sms);
+    const size_t tc = t.stash_floats + t.slab_floats + t.loss_floats;
+    if (tc > floats) floats = tc;
+  }
+  return (int64_t)(floats * sizeof(float));
 }
 
 int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B) {
@@ -245,18 +253,34 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   int sms = 0;
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, false);
-  const Workspace ws = carve(workspace, plan);
   dmvae::TrainIO io;
-  io.packed = packed; io.x = x; io.eps = eps; io.stash = ws.stash; io.slabs = ws.slabs;
+  io.packed = packed; io.x = x; io.eps = eps;
   io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.B = B;
   io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
-  cudaError_t e = PROF(dmvae::K_TRAIN_FUSED, st, dmvae::launch_train(lo, plan, 0, io, st));
-  if (e != cudaSuccess) return cuda_fail(e, what);
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
-  e = PROF(adam ? dmvae::K_REDUCE_ADAM : dmvae::K_REDUCE, st,
-           dmvae::launch_reduce(lo, ws.slabs, plan.grid, plan.slab_stride, wv, grads, adam, params, m, v, st));
-  if (e != cudaSuccess) return cuda_fail(e, what);
+  cudaError_t e;
+  if (g_train_impl.load() == 0 && dmvae::train_tc_supported(lo)) {
+    // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)
+    const dmvae::TrainTcPlan tp = dmvae::plan_train_tc(lo, B, sms);
+    float* stash = static_cast<float*>(workspace);
+    float* slabs = stash + tp.stash_floats;
+    float* loss_part = slabs + tp.slab_floats;
+    e = PROF(dmvae::K_CHAIN, st, dmvae::launch_chain(lo, tp, io, stash, loss_part, st));
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    e = PROF(dmvae::K_WGRAD, st, dmvae::launch_wgrad(lo, tp, stash, slabs, st));
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    e = PROF(dmvae::K_REDUCE_TC, st, dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, st));
+    if (e != cudaSuccess) return cuda_fail(e, what);
+  } else {
+    const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, false);
+    const Workspace ws = carve(workspace, plan);
+    io.stash = ws.stash; io.slabs = ws.slabs;
+    e = PROF(dmvae::K_TRAIN_FUSED, st, dmvae::launch_train(lo, plan, 0, io, st));
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    e = PROF(adam ? dmvae::K_REDUCE_ADAM : dmvae::K_REDUCE, st,
+             dmvae::launch_reduce(lo, ws.slabs, plan.grid, plan.slab_stride, wv, grads, adam, params, m, v, st));
+    if (e != cudaSuccess) return cuda_fail(e, what);
+  }
   if (adam && packed_rw) {
     e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed_rw, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
@@ -379,6 +403,12 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
 int dmvae_set_decode_impl(int impl) {
   if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_decode_impl: 0 (tensor cores) or 1 (FFMA)");
   g_decode_impl.store(impl);
+  return DMVAE_OK;
+}
+
+int dmvae_set_train_impl(int impl) {
+  if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (tensor cores) or 1 (FFMA)");
+  g_train_impl.store(impl);
   return DMVAE_OK;
 }
 

@@ -30,18 +30,39 @@ constexpr int BLOCK_THREADS = CONSUMER_THREADS + 32;  // + one producer warp
 constexpr int STAGE_FLOATS = 8192;                    // 32 KB ring stage
 constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 
-// Tensor-core (tcgen05 kind::tf32, 3xTF32 split) operands: the five dense layers of the
-// generation path.  Each is stored stage by stage in the exact shared-memory image the
-// UMMA descriptors expect (K-major, no swizzle: 8x4 core matrices of 128 B), high and low
-// TF32 halves side by side, so one TMA bulk copy fills a ring stage (dmvae_decode_tc.cu).
-enum TcId { TC_COND1 = 0, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, TC_COND0, NUM_TC };
+// Tensor-core (tcgen05 kind::tf32, 3xTF32 split) weight images, one per dense layer.  Each is
+// stored as two planes (TF32 high halves, then low halves); a plane is the exact shared-memory
+// image the UMMA descriptors expect, K-step by K-step: [k-step of 8][k-chunk of 4][n-group of 8]
+// [8 n][4 k], i.e. 128-byte core matrices, no swizzle.  Any run of consecutive K-steps is a
+// contiguous byte range of each plane, so a ring stage is filled by two TMA bulk copies.  Read
+// K-major the image is the forward operand W[n][k].  The data-gradient GEMM contracts over n
+// instead; it reads W MN-major, which for TF32 the tensor core only accepts in the 32-byte
+// swizzled layout of dmvae_tc.cuh, so layers with a data gradient carry a second image ("t"
+// planes): per slice of 32 input features k, per 8-deep step of n, two 512-byte atoms
+// [4 n][32 k swizzled].  A ring stage holds whole slices; one slice = 32 output columns.
+enum TcId {
+  TC_COND0 = 0, TC_COND1, TC_ENC0, TC_ENC1, TC_ENC2, TC_ENC3, TC_HEADS, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, NUM_TC
+};
 struct TcLayer {
-  int off;       // float offset in the packed arena
-  int K;         // contraction length (multiple of 8): dec0 = 128 (h_c) + Lp8 (z, zero padded);
-                 // cond0 = 8: [x0, y0, 1 (bias row), 0...]
-  int N;         // output width (multiple of 16): 128, or Ip for dec3
-  int kps;       // K-steps (of 8) per 32 KB stage: 8192 / (16 N)
-  int n_stages;
+  int off_hi;    // float offset of the high plane in the packed arena
+  int off_lo;    // ... of the low plane
+  int K;         // contraction length (multiple of 8).  cond0 = 8: [x0, y0, 1 (bias row), 0...];
+                 // enc0 = Ip (zero rows past I); heads = 256: [h_traj ; h_c];
+                 // dec0 = 128 (h_c) + Lp16 (z, zero padded)
+  int N;         // output width (multiple of 16): 128; heads = NH; dec3 = Ip
+  int kps;       // K-steps per 32 KB ring stage (both planes): 512 / N
+  int off_thi;   // data-gradient image (high plane), -1 if the layer needs none
+  int off_tlo;
+  int Kt;        // its output width: K rounded up to 32 (dec0: 128 + Lz32)
+  int sps;       // slices (of 32 outputs) per ring stage: min(Kt / 32, 128 / N)
+};
+
+// Training stash: what the forward / backward chain kernel leaves for the weight-gradient
+// kernel, per 128-row tile: every layer input X and every pre-activation gradient G as a raw
+// fp32 operand image [row group of 8][feature chunk of 4][8 rows][4 features].
+enum TcSlot {
+  SX_START = 0, SX_HC1, SX_HC, SX_X, SX_E1, SX_E2, SX_E3, SX_E4, SX_Z, SX_D1, SX_D2, SX_D3,
+  SG_REC, SG_D3, SG_D2, SG_D1, SG_ML, SG_HC, SG_HC1, SG_E4, SG_E3, SG_E2, SG_E1, NUM_SLOTS
 };
 
 enum LayerId { L_COND0 = 0, L_COND1, L_ENC0, L_ENC1, L_ENC2, L_ENC3, L_HEADS, L_DEC0, L_DEC1, L_DEC2, L_DEC3 };
@@ -78,7 +99,13 @@ struct Layout {
   int r_dec0z, Lzp;
   int Lq;            // L rounded up to 4 (rows of the latent tiles in shared memory)
   int Lp8;           // L rounded up to 8 (K granularity of a TF32 MMA)
+  int Lp16;          // L rounded up to 16 (N granularity of an M = 128 MMA)
+  int NH;            // 2L padded to 16, 32, 64 or 128: width of the heads layer on the tensor cores
   TcLayer tc[NUM_TC];
+  int slot_off[NUM_SLOTS];  // float offset of a stash slot inside a tile's stash
+  int slot_w[NUM_SLOTS];    // features per row of the slot in memory (multiple of 32)
+  int slot_n[NUM_SLOTS];    // features that carry data (multiple of 16): the N of an MMA that reads the slot
+  int tile_stash;           // floats per tile
 };
 
 __host__ __device__ inline int pad_width(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : 128); }
@@ -130,14 +157,40 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   l.r_dec0z = q; q += H * l.Lzp;
   q = round_up(q, 32);  // 128-byte aligned stages for the TMA bulk copies
   l.Lp8 = round_up(l.L, 8);
+  l.Lp16 = round_up(l.L, 16);
+  l.NH = 2 * l.L <= 16 ? 16 : l.L2p;
   for (int t = 0; t < NUM_TC; ++t) {
     TcLayer& c = l.tc[t];
-    c.K = (t == TC_DEC0) ? H + l.Lp8 : (t == TC_COND0 ? 8 : H);
-    c.N = (t == TC_DEC3) ? l.Ip : H;
+    c.K = H; c.N = H;
+    if (t == TC_COND0) c.K = 8;
+    else if (t == TC_ENC0) c.K = l.Ip;
+    else if (t == TC_HEADS) { c.K = 2 * H; c.N = l.NH; }
+    else if (t == TC_DEC0) c.K = H + l.Lp16;
+    else if (t == TC_DEC3) c.N = l.Ip;
     c.kps = STAGE_FLOATS / (16 * c.N);
-    c.n_stages = (c.K / 8 + c.kps - 1) / c.kps;
-    c.off = q;
-    q += c.n_stages * STAGE_FLOATS;
+    c.off_hi = q; q += c.K * c.N;
+    c.off_lo = q; q += c.K * c.N;
+    c.off_thi = c.off_tlo = -1; c.Kt = 0; c.sps = 0;
+    if (t != TC_COND0 && t != TC_ENC0) {
+      c.Kt = (t == TC_DEC0) ? H + round_up(l.L, 32) : c.K;
+      c.sps = c.Kt / 32 < 128 / c.N ? c.Kt / 32 : 128 / c.N;
+      if (c.sps < 1) c.sps = 1;
+      c.off_thi = q; q += c.Kt * c.N;
+      c.off_tlo = q; q += c.Kt * c.N;
+    }
+  }
+  {
+    int o = 0;
+    for (int sl = 0; sl < NUM_SLOTS; ++sl) {
+      int w = H;
+      if (sl == SX_START) w = 16;
+      else if (sl == SX_X || sl == SG_REC) w = l.Ip;
+      else if (sl == SX_Z) w = l.Lp16;
+      else if (sl == SG_ML) w = l.NH;
+      l.slot_off[sl] = o; l.slot_n[sl] = w; l.slot_w[sl] = round_up(w, 32);
+      o += 128 * l.slot_w[sl];
+    }
+    l.tile_stash = o;
   }
   l.n_packed = round_up(q, 4);
   return DMVAE_OK;

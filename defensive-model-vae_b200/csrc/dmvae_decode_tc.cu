@@ -26,6 +26,7 @@
 // over the columns [x0, y0, 1, 0...] (the bias rides on the ones column); with a shared start
 // point the whole condition encoder is folded once per CTA into the bias of dec0.
 #include "dmvae_common.cuh"
+#include "dmvae_tc.cuh"
 
 namespace dmvae {
 
@@ -53,132 +54,38 @@ struct TcArgs {
   long long* trace;   // development aid: per-op clock64 stamps of CTA 0 (null in production)
 };
 
-// ---------------------------------------------------------------------------------------
-// tcgen05 / TMEM PTX
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem descriptor], kind::tf32, issued by one thread for the CTA
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once every tcgen05 operation issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-          taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes stored as
-// 128 contiguous bytes; LBO = byte distance between the two 4-wide K chunks of one MMA, SBO = byte
-// distance between consecutive 8-row groups along N (bit layout: cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
-  return d;                // base offset 0, layout type 0 = no swizzle
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, TF32 x TF32, both K-major.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// true in exactly one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void out_sync() { asm volatile("bar.sync 3, %0;" ::"n"(TC_OUT_THREADS) : "memory"); }
-
-// x = hi + lo with hi = round-to-nearest TF32 of x; lo is cut to TF32 by the tensor core itself
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
-// TMA bulk store shared -> global (bulk async-group completion)
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------
 // the per-tile GEMM program, identical for the producer and the MMA warp
 // ---------------------------------------------------------------------------------------
 struct TcOp {
-  int off;      // float offset of the first stage in the packed arena
+  int off_hi;   // float offset of the layer's high plane in the packed arena
+  int off_lo;   // ... low plane
+  int k0;       // first K step of the plane this op reads
   int ksteps;   // 8-deep K steps
   int kps;      // K steps per stage
   int N;
   int a_col;    // first A column inside the A regions
 };
+__device__ __forceinline__ TcOp tc_op(const TcLayer& c, int k0, int ksteps, int a_col) {
+  return TcOp{c.off_hi, c.off_lo, k0, ksteps, c.kps, c.N, a_col};
+}
 // shared start:  dec0 (latent rows only) -> dec1 -> dec2 -> dec3
 // per-row start: cond0 -> cond1 -> dec0 -> dec1 -> dec2 -> dec3
 __device__ __forceinline__ int tc_program(const Layout& lo, bool shared_start, TcOp (&ops)[TC_MAX_OPS]) {
   int n = 0;
-  if (shared_start) {  // skip the stages of dec0's h_c rows
-    const TcLayer& c = lo.tc[TC_DEC0];
-    ops[n++] = TcOp{c.off + (H / 8 / c.kps) * STAGE_FLOATS, lo.Lp8 / 8, c.kps, H, (int)TM_Z};
+  if (shared_start) {  // skip the K steps of dec0's h_c rows
+    ops[n++] = tc_op(lo.tc[TC_DEC0], H / 8, lo.Lp8 / 8, (int)TM_Z);
   } else {
-    ops[n++] = TcOp{lo.tc[TC_COND0].off, 1, lo.tc[TC_COND0].kps, H, (int)TM_Z + lo.Lp8};
-    ops[n++] = TcOp{lo.tc[TC_COND1].off, H / 8, lo.tc[TC_COND1].kps, H, 0};
-    ops[n++] = TcOp{lo.tc[TC_DEC0].off, (H + lo.Lp8) / 8, lo.tc[TC_DEC0].kps, H, 0};
+    ops[n++] = tc_op(lo.tc[TC_COND0], 0, 1, (int)TM_Z + lo.Lp8);
+    ops[n++] = tc_op(lo.tc[TC_COND1], 0, H / 8, 0);
+    ops[n++] = tc_op(lo.tc[TC_DEC0], 0, (H + lo.Lp8) / 8, 0);
   }
-  ops[n++] = TcOp{lo.tc[TC_DEC1].off, H / 8, lo.tc[TC_DEC1].kps, H, 0};
-  ops[n++] = TcOp{lo.tc[TC_DEC2].off, H / 8, lo.tc[TC_DEC2].kps, H, 0};
-  ops[n++] = TcOp{lo.tc[TC_DEC3].off, H / 8, lo.tc[TC_DEC3].kps, lo.Ip, 0};
+  ops[n++] = tc_op(lo.tc[TC_DEC1], 0, H / 8, 0);
+  ops[n++] = tc_op(lo.tc[TC_DEC2], 0, H / 8, 0);
+  ops[n++] = tc_op(lo.tc[TC_DEC3], 0, H / 8, 0);
   return n;
 }
 
@@ -255,12 +162,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int o = 0; o < n_ops; ++o) {
           const TcOp op = ops[o];
-          for (int k0 = 0, st = 0; k0 < op.ksteps; k0 += op.kps, ++st) {
+          for (int k0 = 0; k0 < op.ksteps; k0 += op.kps) {
             const int nks = min(op.kps, op.ksteps - k0);
-            const uint32_t bytes = (uint32_t)(2 * nks * op.N * 8 * 4);
+            const int fl = nks * op.N * 8;                       // floats per plane
+            const size_t src = (size_t)(op.k0 + k0) * op.N * 8;  // K steps are contiguous in a plane
+            float* dst = s.ring + rs.stage * STAGE_FLOATS;
             mbar_wait(&s.empty[rs.stage], rs.phase ^ 1u);
-            mbar_arrive_expect_tx(&s.full[rs.stage], bytes);
-            tma_load_1d(s.ring + rs.stage * STAGE_FLOATS, pk + op.off + (size_t)st * STAGE_FLOATS, bytes, &s.full[rs.stage]);
+            mbar_arrive_expect_tx(&s.full[rs.stage], (uint32_t)(2 * fl * 4));
+            tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &s.full[rs.stage]);
+            tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &s.full[rs.stage]);
             rs.advance();
           }
         }
@@ -276,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
         const TcOp op = ops[o];
         const uint32_t idesc = umma_idesc_tf32(TC_M, op.N);
         const uint32_t kstep_bytes = (uint32_t)op.N * 32u;  // one 8-deep K step of B: N x 8 TF32
-        const uint64_t desc_hi_bits = umma_desc_kmajor(0u, (uint32_t)op.N * 16u, 128u);
+        const uint64_t desc_hi_bits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
         if (o == 0) {  // latents / start points of this tile staged, D of the previous tile drained
           mbar_wait(s.tile_ready, t_phase);
           t_phase ^= 1u;

@@ -51,6 +51,25 @@ struct TrainIO {
 // mode: 0 fused forward+loss+backward, 1 forward only, 2 backward only
 cudaError_t launch_train(const Layout& lo, const TrainPlan& plan, int mode, const TrainIO& io, cudaStream_t stream);
 
+// Tensor-core training pass (dmvae_train_tc.cu): chain kernel -> weight-gradient kernel -> reduction.
+struct TrainTcPlan {
+  long long n_tiles;          // 128-row tiles
+  int chain_grid, chain_stages;
+  size_t chain_smem;
+  int wgrad_grid;             // = number of partial slabs
+  int role_begin[3], role_count[3];
+  int slab_stride;
+  size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials]
+};
+bool train_tc_supported(const Layout& lo);
+TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count);
+cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
+                         cudaStream_t stream);
+cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream);
+cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
+                             const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
+                             cudaStream_t stream);
+
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],
                           float* grads, const DmvaeAdam* adam, float* p, float* m, float* v, cudaStream_t stream);

@@ -1,0 +1,1112 @@
+// dmvae_train_tc.cu - the training pass on the 5th-generation tensor cores (tcgen05, 3xTF32).
+//
+// Replaces, per step, the reference's  offset transform -> model(...) -> conditional_vae_loss(...)
+// -> loss.backward()  (Training_VAE.py:345-362; model :180-226, loss :229-268) with two kernels:
+//
+//   chain_kernel   one persistent CTA per SM walks 128-row tiles.  The activations of a tile
+//                  never leave tensor memory: forward (cond0, cond1, enc0-3, heads, reparameterise,
+//                  dec0-3), the five loss terms, and the whole data-gradient chain back to the
+//                  first layers run as  D(TMEM) = A(TMEM) x B(smem)  with the layer input / the
+//                  pre-activation gradient resident as the A operand (TF32 high and low halves)
+//                  and the weights streamed L2 -> smem by TMA.  One weight image serves both
+//                  directions: K-major it is W (forward), MN-major the same bytes are W^T (data
+//                  gradient), one 8-column output slice per K step.  relu' masks stay in registers
+//                  between the forward and the backward half of a tile.  Every layer input X and
+//                  every pre-activation gradient G is also written once, as a raw fp32 operand
+//                  image, to the tile's stash in global memory.
+//   wgrad_kernel   the weight gradients  dW = G^T X  summed over all rows: a streaming GEMM whose
+//                  contraction runs over the batch rows.  CTAs are specialised by role (a group of
+//                  layers whose accumulators fit the 512 tensor-memory columns together) and by
+//                  tile subset; X and G stream through a TMA ring, are split into TF32 halves in
+//                  shared memory, and both operands are read MN-major.  Bias gradients ride along
+//                  as products with a constant ones operand.  Accumulators stay in tensor memory
+//                  across all tiles of a CTA and are written once, to the CTA's partial slab.
+//   reduce_tc_kernel  fixed-order sum of the partial slabs (+ the loss partials), optionally with
+//                  the Adam update (torch optim/adam.py::_single_tensor_adam) in the same thread.
+//
+// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 32 (the reference uses 10/12 and 8);
+// anything else inside the ABI envelope runs the FFMA kernel of dmvae_train.cu.
+#include "dmvae_common.cuh"
+#include "dmvae_launch.h"
+#include "dmvae_tc.cuh"
+
+namespace dmvae {
+
+// =========================================================================================
+// chain kernel
+// =========================================================================================
+constexpr int CH_EPI_WARPS = 8;
+constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
+constexpr int CH_PRODUCER_WARP = CH_EPI_WARPS;
+constexpr int CH_MMA_WARP = CH_EPI_WARPS + 1;
+constexpr int CH_THREADS = (CH_MMA_WARP + 1) * 32;
+constexpr int CH_M = 128;
+constexpr int CH_MAX_OPS = 24;
+// tensor-memory columns: accumulator, then the A operand regions (128 main + 64 extra each)
+constexpr uint32_t CT_D = 0, CT_AHI = 128, CT_ALO = 320, CT_X = 128, CT_COLS = 512;
+constexpr uint32_t CT_DX = CT_AHI + CT_X;  // small accumulators (heads, d/dz) live in the extra A_hi columns
+
+struct COp {
+  int off_hi, off_lo;  // planes of the layer image in the packed arena (floats): forward or data-gradient image
+  int N;               // output width of the layer (forward N; the contraction length of its data gradient)
+  int k0, nk;          // forward: K-step range of the image; data gradient: slice range (32 outputs each)
+  int kps;             // forward: K steps per ring stage; data gradient: slices per ring stage
+  int dgrad;           // 0 forward (B read K-major); 1 data gradient (B read MN-major)
+  int a_col;           // column inside the A regions of the first contraction step
+  int d_col;           // tensor-memory column of the accumulator (dgrad: of the first slice)
+  int acc;             // accumulate onto what the accumulator already holds
+  int wait_a;          // wait for the epilogue warps before issuing (A operand written, D drained)
+  int commit_d;        // signal the epilogue warps when the accumulator is complete
+};
+
+struct ChainArgs {
+  Layout lo;
+  const float* packed;
+  const float* x;     // (B, T, 3) absolute
+  const float* eps;   // (B, L) or null (Philox)
+  float* stash;       // [n_tiles][tile_stash]
+  float* loss_part;   // [grid][4 warps][4 terms]
+  unsigned long long seed, sample_offset, step;
+  long long B;
+  float w_recon, w_kld, w_start, w_time, inv_batch;
+  int stages;
+};
+
+__device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
+                                    int wait_a = 1, int commit_d = 1) {
+  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.sps, 1, a_col, d_col, acc, wait_a, commit_d};
+  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, a_col, d_col, acc, wait_a, commit_d};
+}
+
+// The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
+// commit_d is followed by exactly one epilogue of the tile body below (same order).
+__device__ inline int chain_program(const Layout& lo, COp* ops) {
+  const int zs = lo.Lp16 / 8;
+  int n = 0;
+  ops[n++] = c_op(lo.tc[TC_COND0], 0, 1, 0, 0, CT_D, 0);               // start -> hc1
+  ops[n++] = c_op(lo.tc[TC_COND1], 0, 16, 0, 0, CT_D, 0);              // hc1 -> hc
+  ops[n++] = c_op(lo.tc[TC_HEADS], 16, 16, 0, 0, CT_DX, 0);            // hc share of the heads (kept aside)
+  ops[n++] = c_op(lo.tc[TC_ENC0], 0, lo.Ip / 8, 0, 0, CT_D, 0);        // x_rel -> e1
+  ops[n++] = c_op(lo.tc[TC_ENC1], 0, 16, 0, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_ENC2], 0, 16, 0, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_ENC3], 0, 16, 0, 0, CT_D, 0);               // -> e4
+  ops[n++] = c_op(lo.tc[TC_HEADS], 0, 16, 0, 0, CT_DX, 1);             // + h_traj share -> mu, logvar
+  ops[n++] = c_op(lo.tc[TC_DEC0], 0, 16 + zs, 0, 0, CT_D, 0);          // [hc ; z] -> d1
+  ops[n++] = c_op(lo.tc[TC_DEC1], 0, 16, 0, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_DEC2], 0, 16, 0, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_DEC3], 0, 16, 0, 0, CT_D, 0);               // -> recon
+  ops[n++] = c_op(lo.tc[TC_DEC3], 0, 4, 1, 0, CT_D, 0);                // d recon -> d d3 (4 slices of 32 columns)
+  ops[n++] = c_op(lo.tc[TC_DEC2], 0, 4, 1, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_DEC1], 0, 4, 1, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_DEC0], 0, 4, 1, 0, CT_D, 0, 1, 0);          // d d1 -> d hc (decoder share)
+  ops[n++] = c_op(lo.tc[TC_DEC0], 4, 1, 1, 0, CT_DX, 0, 0, 1);         //      -> d z (one slice)
+  ops[n++] = c_op(lo.tc[TC_HEADS], 4, 4, 1, CT_X, CT_D, 1);            // d (mu, logvar) -> + encoder share of d hc
+  ops[n++] = c_op(lo.tc[TC_COND1], 0, 4, 1, 0, CT_D, 0);               // d hc -> d hc1
+  ops[n++] = c_op(lo.tc[TC_HEADS], 0, 4, 1, CT_X, CT_D, 0);            // d (mu, logvar) -> d e4
+  ops[n++] = c_op(lo.tc[TC_ENC3], 0, 4, 1, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_ENC2], 0, 4, 1, 0, CT_D, 0);
+  ops[n++] = c_op(lo.tc[TC_ENC1], 0, 4, 1, 0, CT_D, 0);                // -> d e1
+  return n;
+}
+
+// bias rows kept in shared memory
+enum BiasRow { BR_COND1 = 0, BR_ENC0, BR_ENC1, BR_ENC2, BR_ENC3, BR_HEADS, BR_DEC0, BR_DEC1, BR_DEC2, BR_DEC3, BR_COUNT };
+// relu' mask slots (registers of the epilogue threads)
+enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_D3, MK_COUNT };
+
+__host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
+  return (size_t)stages * STAGE_FLOATS + 64 * CH_EPI_THREADS /* hc / recon scratch */ + (size_t)lo.NH * 128 /* mu, logvar */ +
+         (size_t)lo.Lp16 * 128 /* eps */ + BR_COUNT * H;
+}
+__host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
+  return chain_smem_floats(lo, stages) * 4 + CH_MAX_OPS * sizeof(COp) + 24 * 8 + 16 + 1024;
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  const Layout& lo = a.lo;
+  const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
+  float *ring, *scratch, *mlb, *epb, *bias;
+  COp* ops;
+  uint64_t *full, *empty, *d_ready, *a_ready;
+  uint32_t* tmem_slot;
+  {
+    const uint32_t base = smem_u32(smem_dyn);
+    unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
+    ring = reinterpret_cast<float*>(p);
+    scratch = ring + (size_t)a.stages * STAGE_FLOATS;
+    mlb = scratch + 64 * CH_EPI_THREADS;
+    epb = mlb + (size_t)NH * 128;
+    bias = epb + (size_t)Lp16 * 128;
+    ops = reinterpret_cast<COp*>(bias + BR_COUNT * H);
+    full = reinterpret_cast<uint64_t*>(ops + CH_MAX_OPS);
+    empty = full + 8;
+    d_ready = empty + 8;
+    a_ready = d_ready + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* __restrict__ pk = a.packed;
+  const long long n_tiles = (a.B + CH_M - 1) / CH_M;
+
+  if (tid == 0) {
+    for (int st = 0; st < a.stages; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], 1);
+    }
+    mbar_init(d_ready, 1);
+    mbar_init(a_ready, CH_EPI_WARPS);
+    mbar_fence_init();
+    chain_program(lo, ops);
+  }
+  if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
+  if (tid < CH_EPI_THREADS) {
+    for (int i = tid; i < H; i += CH_EPI_THREADS) {
+      bias[BR_COND1 * H + i] = pk[lo.q_b[L_COND1] + i];
+      bias[BR_ENC0 * H + i] = pk[lo.q_b[L_ENC0] + i];
+      bias[BR_ENC1 * H + i] = pk[lo.q_b[L_ENC1] + i];
+      bias[BR_ENC2 * H + i] = pk[lo.q_b[L_ENC2] + i];
+      bias[BR_ENC3 * H + i] = pk[lo.q_b[L_ENC3] + i];
+      bias[BR_HEADS * H + i] = i < 2 * L ? pk[lo.q_b[L_HEADS] + i] : 0.f;
+      bias[BR_DEC0 * H + i] = pk[lo.q_b[L_DEC0] + i];
+      bias[BR_DEC1 * H + i] = pk[lo.q_b[L_DEC1] + i];
+      bias[BR_DEC2 * H + i] = pk[lo.q_b[L_DEC2] + i];
+      bias[BR_DEC3 * H + i] = i < I ? pk[lo.q_b[L_DEC3] + i] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr int n_ops = 23;
+
+  if (warp == CH_PRODUCER_WARP) {
+    // ===================== producer warp: weight planes L2 -> smem ring =======================
+    if (lane == 0) {
+      RingStateRt rs(a.stages);
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int o = 0; o < n_ops; ++o) {
+          const COp op = ops[o];
+          for (int k = 0; k < op.nk; k += op.kps) {
+            const int nks = min(op.kps, op.nk - k);
+            // forward: nks K steps of N*8 floats; data gradient: nks slices of N*32 floats - contiguous either way
+            const int unit = op.dgrad ? op.N * 32 : op.N * 8;
+            const int fl = nks * unit;
+            const size_t src = (size_t)(op.k0 + k) * unit;
+            float* dst = ring + rs.stage * STAGE_FLOATS;
+            mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+            mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
+            tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
+            tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+            rs.advance();
+          }
+        }
+    }
+  } else if (warp == CH_MMA_WARP) {
+    // ===================== MMA warp (warp-uniform walk, one elected lane issues) ===============
+    RingStateRt rs(a.stages);
+    uint32_t a_phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int o = 0; o < n_ops; ++o) {
+        const COp op = ops[o];
+        if (op.wait_a) {
+          mbar_wait(a_ready, a_phase);
+          a_phase ^= 1u;
+        }
+        tc_fence_after();
+        const uint32_t unit_bytes = op.dgrad ? (uint32_t)op.N * 128u : (uint32_t)op.N * 32u;  // slice / K step of a plane
+        for (int k = 0; k < op.nk; k += op.kps) {
+          const int nks = min(op.kps, op.nk - k);
+          mbar_wait(&full[rs.stage], rs.phase);
+          tc_fence_after();
+          const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
+          const uint32_t b_lo = b_hi + (uint32_t)nks * unit_bytes;
+          if (!op.dgrad) {
+            // D[128 x N] (+)= A[:, 8 (k + ks) ..] x W^T, B K-major: LBO = chunk stride N*16, SBO = 128
+            const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
+            const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
+            uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)(b_lo >> 4);
+            const uint64_t dinc = (uint64_t)(unit_bytes >> 4);
+            uint32_t a_hi = tmem + CT_AHI + (uint32_t)(op.a_col + 8 * k), a_lo = tmem + CT_ALO + (uint32_t)(op.a_col + 8 * k);
+            uint32_t accf = (op.acc || k > 0) ? 1u : 0u;
+            if (elect_one()) {
+#pragma unroll 4
+              for (int ks = 0; ks < nks; ++ks) {
+                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_hi, dh, idesc, accf);
+                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_lo, dh, idesc, 1u);
+                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_hi, dl, idesc, 1u);
+                accf = 1u;
+                a_hi += 8u; a_lo += 8u; dh += dinc; dl += dinc;
+              }
+              umma_commit(&empty[rs.stage]);
+            }
+          } else {
+            // columns [32 k, 32 (k + nks)) of D  (+)=  G[128 x N] x W[:, those inputs]; B MN-major (32-byte
+            // swizzle): LBO = slice stride (next 32 outputs), SBO = 512 (next 4 of the contraction); the
+            // 8-deep contraction step j starts 1024 bytes into a slice
+            const uint32_t idesc = umma_idesc_tf32(CH_M, 32 * nks, UMMA_B_MN);
+            const uint64_t dbits = umma_desc(0u, unit_bytes, 512u, 1u);
+            uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)(b_lo >> 4);
+            const uint32_t d = tmem + (uint32_t)(op.d_col + 32 * k);
+            uint32_t a_hi = tmem + CT_AHI + (uint32_t)op.a_col, a_lo = tmem + CT_ALO + (uint32_t)op.a_col;
+            uint32_t accf = op.acc ? 1u : 0u;
+            const int nj = op.N >> 3;
+            if (elect_one()) {
+#pragma unroll 4
+              for (int j = 0; j < nj; ++j) {
+                umma_tf32_ts(d, a_hi, dh, idesc, accf);
+                umma_tf32_ts(d, a_lo, dh, idesc, 1u);
+                umma_tf32_ts(d, a_hi, dl, idesc, 1u);
+                accf = 1u;
+                a_hi += 8u; a_lo += 8u; dh += 64u; dl += 64u;  // + 1024 bytes
+              }
+              umma_commit(&empty[rs.stage]);
+            }
+          }
+          __syncwarp();
+          rs.advance();
+        }
+        if (op.commit_d) {
+          if (elect_one()) umma_commit(d_ready);
+          __syncwarp();
+        }
+      }
+  } else {
+    // ===================== epilogue warps =======================================================
+    const int q = warp & 3, h = warp >> 2;   // tensor-memory lane quarter, column half
+    const int m = q * 32 + lane;             // row of the tile owned by this thread
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t d_phase = 0;
+    uint32_t mk[MK_COUNT][2];
+    float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float* my_scr = scratch + tid;   // [j * 256 + tid]: the 64 values this thread parks (hc, then recon)
+    float* my_ml = mlb + m;          // [n * 128 + m], h == 0 threads
+    float* my_ep = epb + m;
+
+    auto wait_d = [&]() {
+      mbar_wait(d_ready, d_phase);
+      d_phase ^= 1u;
+      tc_fence_after();
+    };
+    auto release_a = [&]() {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+    };
+    // a 4-feature chunk of this thread's row in a stash image (MN-major, 32-byte swizzle: dmvae_tc.cuh)
+    auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
+      return reinterpret_cast<float4*>(tile_stash + lo.slot_off[slot] + mn_image_index(4 * chunk, m, 128, lo.slot_w[slot] * 4));
+    };
+    // start point of the tile's row -> A columns [x0, y0, 1, 0...] and the 16-wide stash image
+    auto stage_start = [&](long long tile) {
+      if (h == 0) {
+        const long long row = tile * CH_M + m;
+        float sx = 0.f, sy = 0.f;
+        if (row < a.B) { sx = __ldg(a.x + row * I + 1); sy = __ldg(a.x + row * I + 2); }
+        uint32_t xh, xl, yh, yl;
+        split_tf32(sx, xh, xl);
+        split_tf32(sy, yh, yl);
+        tmem_st4(lane_base + CT_AHI, xh, yh, __float_as_uint(1.0f), 0u);
+        tmem_st4(lane_base + CT_AHI + 4, 0u, 0u, 0u, 0u);
+        tmem_st4(lane_base + CT_ALO, xl, yl, 0u, 0u);
+        tmem_st4(lane_base + CT_ALO + 4, 0u, 0u, 0u, 0u);
+        float* ts = a.stash + (size_t)tile * lo.tile_stash;
+        *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) *stash_ptr(ts, SX_START, c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+
+    stage_start(blockIdx.x);
+    release_a();
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long long row = tile * CH_M + m;
+      const bool row_ok = row < a.B;
+      float* ts = a.stash + (size_t)tile * lo.tile_stash;
+
+      // hidden layer: D -> (+ bias) -> relu -> mask, stash image, A operand (optionally parked in smem)
+      auto epi_hidden = [&](const float* brow, int mslot, int xslot, bool park) {
+        wait_d();
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + CT_D + h * 64 + c * 16, v[c]);
+        tmem_ld_wait();
+        uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[16], lw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(v[c][j]);
+            if (brow != nullptr) x += brow[h * 64 + c * 16 + j];
+            x = fmaxf(x, 0.f);
+            const uint32_t bit = x > 0.f ? 1u : 0u;
+            if (c < 2) m0 |= bit << (c * 16 + j); else m1 |= bit << ((c - 2) * 16 + j);
+            split_tf32(x, hi[j], lw[j]);
+            v[c][j] = __float_as_uint(x);
+            if (park) my_scr[(c * 16 + j) * CH_EPI_THREADS] = x;
+          }
+          tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
+          tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *stash_ptr(ts, xslot, h * 16 + c * 4 + j4) =
+                make_float4(__uint_as_float(v[c][4 * j4]), __uint_as_float(v[c][4 * j4 + 1]),
+                            __uint_as_float(v[c][4 * j4 + 2]), __uint_as_float(v[c][4 * j4 + 3]));
+        }
+        mk[mslot][0] = m0; mk[mslot][1] = m1;
+        release_a();
+      };
+      // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand)
+      auto epi_dgrad = [&](int mslot, int gslot, bool write_a) {
+        wait_d();
+        uint32_t v[4][16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + CT_D + h * 64 + c * 16, v[c]);
+        tmem_ld_wait();
+        const uint32_t m0 = mk[mslot][0], m1 = mk[mslot][1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[16], lw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t bit = c < 2 ? (m0 >> (c * 16 + j)) & 1u : (m1 >> ((c - 2) * 16 + j)) & 1u;
+            const float gr = bit ? __uint_as_float(v[c][j]) : 0.f;
+            v[c][j] = __float_as_uint(gr);
+            split_tf32(gr, hi[j], lw[j]);
+          }
+          if (write_a) {
+            tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
+            tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            *stash_ptr(ts, gslot, h * 16 + c * 4 + j4) =
+                make_float4(__uint_as_float(v[c][4 * j4]), __uint_as_float(v[c][4 * j4 + 1]),
+                            __uint_as_float(v[c][4 * j4 + 2]), __uint_as_float(v[c][4 * j4 + 3]));
+        }
+      };
+
+      // ---------------------------------- forward ---------------------------------------------
+      epi_hidden(nullptr, MK_HC1, SX_HC1, false);                 // cond0 (bias rides on the ones column)
+      epi_hidden(bias + BR_COND1 * H, MK_HC, SX_HC, true);        // cond1 -> hc (parked for dec0)
+      // hc share of the heads issued: now the encoder input, x_rel = x - start on the x, y columns
+      // (Training_VAE.py:345-348), zero beyond I
+      wait_d();
+      if (h * 64 < Ip) {
+        const int nc = min(Ip - h * 64, 64) >> 2;
+        for (int c4 = 0; c4 < nc; ++c4) {
+          float xv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = h * 64 + c4 * 4 + i;
+            float val = 0.f;
+            if (row_ok && n < I) {
+              val = __ldg(a.x + row * I + n);
+              const int d = n % 3;
+              if (d == 1) val = val - __ldg(a.x + row * I + 1);
+              else if (d == 2) val = val - __ldg(a.x + row * I + 2);
+            }
+            xv[i] = val;
+          }
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + h * 64 + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + h * 64 + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SX_X, h * 16 + c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        }
+      }
+      release_a();
+      epi_hidden(bias + BR_ENC0 * H, MK_E1, SX_E1, false);
+      epi_hidden(bias + BR_ENC1 * H, MK_E2, SX_E2, false);
+      epi_hidden(bias + BR_ENC2 * H, MK_E3, SX_E3, false);
+      epi_hidden(bias + BR_ENC3 * H, MK_E4, SX_E4, false);
+      // heads: mu, logvar (Training_VAE.py:193-196); z = mu + eps * exp(0.5 logvar) (:199-206);
+      // then [hc ; z] becomes the A operand of dec0
+      wait_d();
+      if (h == 0) {
+        const float* bh = bias + BR_HEADS * H;
+        for (int c = 0; c < NH / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + CT_DX + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bh[c * 16 + j];
+        }
+        for (int jb = 0; jb < Lp16 / 4; ++jb) {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (row_ok && jb * 4 < L) {
+            if (a.eps != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
+            } else {
+              const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
+                                              (uint32_t)(a.step + 1));
+              e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
+            }
+          }
+          float zv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = jb * 4 + i;
+            float z = 0.f, e = 0.f;
+            if (j < L) {
+              e = e4[i];
+              z = my_ml[j * 128] + e * expf(0.5f * my_ml[(L + j) * 128]);
+            }
+            my_ep[j * 128] = e;
+            zv[i] = z;
+          }
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(zv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + CT_X + jb * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + CT_X + jb * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SX_Z, jb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        }
+        for (int jb = Lp16 / 4; jb < lo.slot_w[SX_Z] / 4; ++jb) *stash_ptr(ts, SX_Z, jb) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {  // hc back from its parking place
+        uint32_t hi[16], lw[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_tf32(my_scr[(c * 16 + j) * CH_EPI_THREADS], hi[j], lw[j]);
+        tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
+        tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+      }
+      release_a();
+      epi_hidden(bias + BR_DEC0 * H, MK_D1, SX_D1, false);
+      epi_hidden(bias + BR_DEC1 * H, MK_D2, SX_D2, false);
+      epi_hidden(bias + BR_DEC2 * H, MK_D3, SX_D3, false);
+
+      // ---------------------------------- loss (Training_VAE.py:229-268) -----------------------
+      // recon -> the five terms and d(total)/d(recon), which becomes the A operand of dec3's
+      // data gradient; one thread per row walks the time steps in order
+      wait_d();
+      if (h == 0) {
+        float* rb = scratch + m;   // [n * 128 + m]
+        const float* b3 = bias + BR_DEC3 * H;
+        for (int c = 0; c < Ip / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + CT_D + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]) + b3[c * 16 + j];
+        }
+        if (row_ok) {
+          const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
+          const float c_start = a.w_start * a.inv_batch;
+          const float c_t0 = a.w_time * 2.f * a.inv_batch;
+          const float c_mono = T > 1 ? a.w_time * a.inv_batch / (float)(T - 1) : 0.f;
+          const float* xr = a.x + row * I;
+          const float sx = __ldg(xr + 1), sy = __ldg(xr + 2);
+          float s_rec = 0.f, s_start = 0.f, s_t0 = 0.f, s_mono = 0.f;
+          float g_prev = 0.f, r_prev = 0.f;
+          for (int t = 0; t < T; ++t) {
+            {
+              const float r = rb[(3 * t) * 128], xv = __ldg(xr + 3 * t);
+              const float diff = r - xv;
+              s_rec = fmaf(diff, diff, s_rec);
+              float g = c_rec * diff;
+              if (t == 0) {
+                s_t0 = r * r;
+                g = fmaf(c_t0, r, g);
+              } else {
+                const float dt = r - r_prev;
+                if (dt < 0.f) {  // relu'(0) = 0: strict
+                  s_mono -= dt;
+                  g -= c_mono;
+                  g_prev += c_mono;
+                }
+                rb[(3 * (t - 1)) * 128] = g_prev;
+              }
+              g_prev = g;
+              r_prev = r;
+            }
+#pragma unroll
+            for (int d = 1; d < 3; ++d) {
+              const int n = 3 * t + d;
+              const float r = rb[n * 128], xv = __ldg(xr + n) - (d == 1 ? sx : sy);
+              const float diff = r - xv;
+              s_rec = fmaf(diff, diff, s_rec);
+              float g = c_rec * diff;
+              if (t == 0) {
+                s_start = fmaf(diff, diff, s_start);
+                g = fmaf(c_start, diff, g);
+              }
+              rb[n * 128] = g;
+            }
+          }
+          rb[(3 * (T - 1)) * 128] = g_prev;
+          float s_k = 0.f;
+          for (int j = 0; j < L; ++j) {
+            const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128];
+            s_k += 1.f + lv - mu * mu - expf(lv);
+          }
+          loss_acc[0] += s_rec * (a.inv_batch / (float)I);
+          loss_acc[1] += -0.5f * s_k * (a.inv_batch / (float)L);
+          loss_acc[2] += s_start * (a.inv_batch * 0.5f);
+          loss_acc[3] += s_t0 * a.inv_batch + (T > 1 ? s_mono * (a.inv_batch / (float)(T - 1)) : 0.f);
+        }
+        for (int c4 = 0; c4 < Ip / 4; ++c4) {
+          float gv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = c4 * 4 + i;
+            gv[i] = (row_ok && n < I) ? rb[n * 128] : 0.f;   // rows past the batch end carry no gradient
+          }
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(gv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SG_REC, c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+      }
+      release_a();
+
+      // ---------------------------------- backward ----------------------------------------------
+      epi_dgrad(MK_D3, SG_D3, true); release_a();
+      epi_dgrad(MK_D2, SG_D2, true); release_a();
+      epi_dgrad(MK_D1, SG_D1, true); release_a();
+      // dec0: d/dz is in the small accumulator; reparameterisation + KLD backward (Training_VAE.py:243):
+      //   d/dmu = w_k mu / (B L) + g_z ;  d/dlogvar = -0.5 w_k (1 - e^lv) / (B L) + 0.5 g_z eps e^(lv/2)
+      // -> the (mu, logvar) gradient becomes the A operand (extra columns) of the heads' data gradients.
+      // The decoder share of d/dhc stays in the main accumulator and is completed by the next op.
+      wait_d();
+      if (h == 0) {
+        const float c_k = a.w_kld * a.inv_batch / (float)L;
+        for (int c = 0; c < Lp16 / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + CT_DX + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j16 = 0; j16 < 16; ++j16) {
+            const int j = c * 16 + j16;
+            if (j < L) {
+              float gmu = 0.f, glv = 0.f;
+              if (row_ok) {
+                const float gz = __uint_as_float(v[j16]);
+                const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128], ep = my_ep[j * 128];
+                gmu = fmaf(c_k, mu, gz);
+                glv = -0.5f * c_k * (1.f - expf(lv)) + 0.5f * gz * ep * expf(0.5f * lv);
+              }
+              my_ml[j * 128] = gmu;
+              my_ml[(L + j) * 128] = glv;
+            }
+          }
+        }
+        for (int c4 = 0; c4 < NH / 4; ++c4) {
+          float gv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = c4 * 4 + i;
+            gv[i] = n < 2 * L ? my_ml[n * 128] : 0.f;
+          }
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(gv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + CT_X + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + CT_X + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SG_ML, c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+        for (int c4 = NH / 4; c4 < lo.slot_w[SG_ML] / 4; ++c4) *stash_ptr(ts, SG_ML, c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      release_a();
+      epi_dgrad(MK_HC, SG_HC, true); release_a();     // both shares of d/dhc -> d hc
+      epi_dgrad(MK_HC1, SG_HC1, false); release_a();  // -> d hc1 (cond0 needs no data gradient)
+      epi_dgrad(MK_E4, SG_E4, true); release_a();
+      epi_dgrad(MK_E3, SG_E3, true); release_a();
+      epi_dgrad(MK_E2, SG_E2, true); release_a();
+      epi_dgrad(MK_E1, SG_E1, false);                 // enc0 needs no data gradient
+      const long long next = tile + gridDim.x;
+      if (next < n_tiles) stage_start(next);
+      release_a();
+    }
+
+    // loss partials: fixed-order tree inside the warp, one slot per (CTA, row quarter)
+    if (h == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) loss_acc[t4] += __shfl_xor_sync(0xffffffffu, loss_acc[t4], o);
+      if (lane == 0) {
+        float* dst = a.loss_part + ((size_t)blockIdx.x * 4 + q) * 4;
+        dst[0] = loss_acc[0]; dst[1] = loss_acc[1]; dst[2] = loss_acc[2]; dst[3] = loss_acc[3];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == CH_PRODUCER_WARP) tmem_dealloc(tmem, CT_COLS);
+}
+
+// =========================================================================================
+// weight-gradient kernel
+// =========================================================================================
+constexpr int WG_WORK_WARPS = 8;
+constexpr int WG_WORK_THREADS = WG_WORK_WARPS * 32;
+constexpr int WG_PRODUCER_WARP = WG_WORK_WARPS;
+constexpr int WG_MMA_WARP = WG_WORK_WARPS + 1;
+constexpr int WG_THREADS = (WG_MMA_WARP + 1) * 32;
+constexpr int WG_ROWS = 16;                 // batch rows per ring stage (two 8-deep contraction steps)
+constexpr int WG_STAGE_FLOATS = 8192;       // [A_hi 2048][B_hi <= 2048][A_lo 2048][B_lo <= 2048]
+constexpr int WG_MAX_OPS = 6;
+constexpr int WG_ROLES = 3;
+constexpr int WG_STAGES = 6;
+
+enum WKind { WK_COND0 = 0, WK_COND1, WK_ENC0, WK_ENC1, WK_ENC2, WK_ENC3, WK_HEADS_E, WK_HEADS_C, WK_DEC0_C, WK_DEC0_Z,
+             WK_DEC1, WK_DEC2, WK_DEC3 };
+
+struct WOp {
+  int kind;
+  int slotA, slotB;  // A: the 128-wide image that supplies the M dimension (tensor-memory lanes); B supplies N
+  int FB;            // width of B
+  int d_col;         // accumulator column
+  int bias;          // 0 none; 1: A x ones -> column 0 of a 16-wide accumulator (lane = feature);
+                     // 2: ones x B -> lane 0 of an FB-wide accumulator
+  int d_col_b;
+};
+
+// Layer groups whose accumulators fit tensor memory together; 128-wide layers are spread so that
+// the MMA time of the roles is comparable.
+__host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* ops) {
+  int n = 0, col = 0;
+  auto add = [&](int kind, int sa, int sb, int FB, int bias) {
+    WOp w;
+    w.kind = kind; w.slotA = sa; w.slotB = sb; w.FB = FB; w.d_col = col; col += FB;
+    w.bias = bias; w.d_col_b = col;
+    if (bias == 1) col += 16;
+    else if (bias == 2) col += FB;
+    ops[n++] = w;
+  };
+  if (role == 0) {
+    add(WK_COND1, SG_HC, SX_HC1, H, 1);
+    add(WK_ENC1, SG_E2, SX_E1, H, 1);
+    add(WK_ENC2, SG_E3, SX_E2, H, 1);
+    add(WK_COND0, SG_HC1, SX_START, 16, 0);   // columns 0, 1 = dW, column 2 = db (the ones column of the start image)
+  } else if (role == 1) {
+    add(WK_ENC3, SG_E4, SX_E3, H, 1);
+    add(WK_DEC1, SG_D2, SX_D1, H, 1);
+    add(WK_DEC2, SG_D3, SX_D2, H, 1);
+    add(WK_ENC0, SG_E1, SX_X, lo.Ip, 1);
+  } else {
+    add(WK_DEC0_C, SG_D1, SX_HC, H, 1);
+    add(WK_DEC0_Z, SG_D1, SX_Z, lo.Lp16, 0);
+    add(WK_HEADS_E, SX_E4, SG_ML, lo.NH, 2);  // transposed: lanes = input features, columns = (mu, logvar) index
+    add(WK_HEADS_C, SX_HC, SG_ML, lo.NH, 0);
+    add(WK_DEC3, SX_D3, SG_REC, lo.Ip, 2);    // transposed: lanes = input features, columns = output index
+  }
+  return n;
+}
+__host__ __device__ inline int wgrad_role_cols(const Layout& lo, int role) {
+  WOp ops[WG_MAX_OPS];
+  const int n = wgrad_program(lo, role, ops);
+  const WOp& w = ops[n - 1];
+  return w.bias == 0 ? w.d_col + w.FB : (w.bias == 1 ? w.d_col_b + 16 : w.d_col_b + w.FB);
+}
+
+struct WgradArgs {
+  Layout lo;
+  const float* stash;
+  float* slabs;        // [grid][slab_stride]
+  long long n_tiles;
+  int slab_stride;
+  int role_end[WG_ROLES];  // CTA index ranges: role r owns [role_end[r-1], role_end[r])
+};
+
+constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 /* ones (A side) */ + 1024 /* ones (B side) */ +
+                                 WG_MAX_OPS * sizeof(WOp) + 32 * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  const Layout& lo = a.lo;
+  float *ring, *ones_a, *ones_b;
+  WOp* ops;
+  uint64_t *raw_full, *split_full, *empty, *d_done;
+  uint32_t* tmem_slot;
+  {
+    const uint32_t base = smem_u32(smem_dyn);
+    unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
+    ring = reinterpret_cast<float*>(p);
+    ones_a = ring + (size_t)WG_STAGES * WG_STAGE_FLOATS;
+    ones_b = ones_a + 1024;
+    ops = reinterpret_cast<WOp*>(ones_b + 256);
+    raw_full = reinterpret_cast<uint64_t*>(ops + WG_MAX_OPS);
+    split_full = raw_full + 8;
+    empty = split_full + 8;
+    d_done = empty + 8;
+    tmem_slot = reinterpret_cast<uint32_t*>(d_done + 1);
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int role = 0;
+  while (role < WG_ROLES - 1 && (int)blockIdx.x >= a.role_end[role]) ++role;
+  const int role_begin = role == 0 ? 0 : a.role_end[role - 1];
+  const int role_ctas = a.role_end[role] - role_begin;
+  const int my_index = (int)blockIdx.x - role_begin;
+
+  if (tid == 0) {
+    for (int st = 0; st < WG_STAGES; ++st) {
+      mbar_init(&raw_full[st], 1);
+      mbar_init(&split_full[st], WG_WORK_WARPS);
+      mbar_init(&empty[st], 1);
+    }
+    mbar_init(d_done, 1);
+    mbar_fence_init();
+    wgrad_program(lo, role, ops);
+  }
+  // constant "ones" operands (MN-major images of one 8-row group): feature 0 is 1 in every row
+  for (int i = tid; i < 1024 + 256; i += WG_THREADS) ones_a[i] = 0.f;
+  __syncthreads();
+  if (tid < 8) {
+    ones_a[mn_image_index(0, tid, 128, 512)] = 1.0f;   // 128 features: 4 feature atoms per 4-row atom
+    ones_b[mn_image_index(0, tid, 128, 128)] = 1.0f;   // one feature atom
+  }
+  if (warp == WG_PRODUCER_WARP) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  WOp tmp_ops[WG_MAX_OPS];
+  const int n_ops = wgrad_program(lo, role, tmp_ops);
+  constexpr int chunks = CH_M / WG_ROWS;  // 8 ring stages per (tile, op)
+
+  if (warp == WG_PRODUCER_WARP) {
+    if (lane == 0) {
+      RingStateRt rs(WG_STAGES);
+      for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas) {
+        const float* ts = a.stash + (size_t)tile * lo.tile_stash;
+        for (int o = 0; o < n_ops; ++o) {
+          const WOp op = ops[o];
+          const float* srcA = ts + lo.slot_off[op.slotA];
+          const float* srcB = ts + lo.slot_off[op.slotB];
+          const int FBm = lo.slot_w[op.slotB];  // width of the B image in memory
+          const uint32_t bytesA = WG_ROWS * H * 4, bytesB = (uint32_t)(WG_ROWS * FBm * 4);
+          for (int c = 0; c < chunks; ++c) {
+            float* dst = ring + rs.stage * WG_STAGE_FLOATS;
+            mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+            mbar_arrive_expect_tx(&raw_full[rs.stage], bytesA + bytesB);
+            tma_load_1d(dst, srcA + (size_t)c * WG_ROWS * H, bytesA, &raw_full[rs.stage]);
+            tma_load_1d(dst + 2048, srcB + (size_t)c * WG_ROWS * FBm, bytesB, &raw_full[rs.stage]);
+            rs.advance();
+          }
+        }
+      }
+    }
+  } else if (warp == WG_MMA_WARP) {
+    RingStateRt rs(WG_STAGES);
+    bool first_tile = true;
+    for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas) {
+      for (int o = 0; o < n_ops; ++o) {
+        const WOp op = ops[o];
+        const uint32_t idesc = umma_idesc_tf32(128, op.FB, UMMA_A_MN | UMMA_B_MN);
+        const uint32_t idesc_b1 = umma_idesc_tf32(128, 16, UMMA_A_MN | UMMA_B_MN);
+        // MN-major images: LBO = feature-atom stride (512 bytes), SBO = 4-row-atom stride (width * 16 bytes)
+        const uint32_t FBm = (uint32_t)lo.slot_w[op.slotB];
+        const uint64_t a_bits = umma_desc(0u, 512u, H * 16u, 1u), b_bits = umma_desc(0u, 512u, FBm * 16u, 1u);
+        const uint64_t ones_a_desc = umma_desc(smem_u32(ones_a), 512u, 2048u, 1u);
+        const uint64_t ones_b_desc = umma_desc(smem_u32(ones_b), 512u, 512u, 1u);
+        for (int c = 0; c < chunks; ++c) {
+          mbar_wait(&split_full[rs.stage], rs.phase);
+          tc_fence_after();
+          const uint32_t s0 = smem_u32(ring + rs.stage * WG_STAGE_FLOATS);
+          if (elect_one()) {
+#pragma unroll
+            for (int g = 0; g < WG_ROWS / 8; ++g) {
+              const uint64_t a_hi = a_bits | (uint64_t)((s0 + (uint32_t)g * (H * 32u)) >> 4);
+              const uint64_t a_lo = a_bits | (uint64_t)((s0 + 16384u + (uint32_t)g * (H * 32u)) >> 4);
+              const uint64_t b_hi = b_bits | (uint64_t)((s0 + 8192u + (uint32_t)g * (FBm * 32u)) >> 4);
+              const uint64_t b_lo = b_bits | (uint64_t)((s0 + 24576u + (uint32_t)g * (FBm * 32u)) >> 4);
+              const uint32_t accf = (first_tile && c == 0 && g == 0) ? 0u : 1u;
+              umma_tf32_ss(tmem + (uint32_t)op.d_col, a_hi, b_hi, idesc, accf);
+              umma_tf32_ss(tmem + (uint32_t)op.d_col, a_lo, b_hi, idesc, 1u);
+              umma_tf32_ss(tmem + (uint32_t)op.d_col, a_hi, b_lo, idesc, 1u);
+              if (op.bias == 1) {
+                umma_tf32_ss(tmem + (uint32_t)op.d_col_b, a_hi, ones_b_desc, idesc_b1, accf);
+                umma_tf32_ss(tmem + (uint32_t)op.d_col_b, a_lo, ones_b_desc, idesc_b1, 1u);
+              } else if (op.bias == 2) {
+                umma_tf32_ss(tmem + (uint32_t)op.d_col_b, ones_a_desc, b_hi, idesc, accf);
+                umma_tf32_ss(tmem + (uint32_t)op.d_col_b, ones_a_desc, b_lo, idesc, 1u);
+              }
+            }
+            umma_commit(&empty[rs.stage]);
+          }
+          __syncwarp();
+          rs.advance();
+        }
+      }
+      first_tile = false;
+    }
+    if (elect_one()) umma_commit(d_done);
+    __syncwarp();
+  } else {
+    // ===================== work warps: TF32 split of the raw stages, then the final write-out ======
+    RingStateRt rs(WG_STAGES);
+    for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas)
+      for (int o = 0; o < n_ops; ++o) {
+        const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
+        for (int c = 0; c < chunks; ++c) {
+          float4* st4 = reinterpret_cast<float4*>(ring + rs.stage * WG_STAGE_FLOATS);
+          mbar_wait(&raw_full[rs.stage], rs.phase);
+          for (int i = tid; i < 512 + nB4; i += WG_WORK_THREADS) {
+            const int idx = i;  // A part [0,512), B part [512, 512 + nB4)
+            const float4 x = st4[idx];
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
+            st4[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+            st4[idx + 1024] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_full[rs.stage]);
+          rs.advance();
+        }
+      }
+
+    // ---- write-out: accumulators -> this CTA's partial slab (torch layout of each tensor) ----------
+    mbar_wait(d_done, 0);
+    tc_fence_after();
+    const int q = warp & 3, hh = warp >> 2;
+    const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    float* slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+    const int L = lo.L, I = lo.I;
+    for (int o = 0; o < n_ops; ++o) {
+      const WOp op = ops[o];
+      // columns of this op are shared between the two warps of a lane quarter in 16-column chunks
+      for (int c = hh; c < op.FB / 16; c += 2) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + (uint32_t)(op.d_col + c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c * 16 + j;
+          const float val = __uint_as_float(v[j]);
+          switch (op.kind) {
+            case WK_COND0:
+              if (col < 2) slab[lo.p_w[L_COND0] + ln * 2 + col] = val;
+              else if (col == 2) slab[lo.p_b[L_COND0] + ln] = val;
+              break;
+            case WK_COND1: slab[lo.p_w[L_COND1] + ln * H + col] = val; break;
+            case WK_ENC0: if (col < I) slab[lo.p_w[L_ENC0] + ln * I + col] = val; break;
+            case WK_ENC1: slab[lo.p_w[L_ENC1] + ln * H + col] = val; break;
+            case WK_ENC2: slab[lo.p_w[L_ENC2] + ln * H + col] = val; break;
+            case WK_ENC3: slab[lo.p_w[L_ENC3] + ln * H + col] = val; break;
+            case WK_DEC0_C: slab[lo.p_w[L_DEC0] + ln * (L + H) + L + col] = val; break;
+            case WK_DEC0_Z: if (col < L) slab[lo.p_w[L_DEC0] + ln * (L + H) + col] = val; break;
+            case WK_DEC1: slab[lo.p_w[L_DEC1] + ln * H + col] = val; break;
+            case WK_DEC2: slab[lo.p_w[L_DEC2] + ln * H + col] = val; break;
+            case WK_HEADS_E:
+            case WK_HEADS_C: {
+              const int koff = op.kind == WK_HEADS_C ? H : 0;
+              if (col < L) slab[lo.p_w[L_HEADS] + col * (2 * H) + koff + ln] = val;
+              else if (col < 2 * L) slab[lo.p_wlv + (col - L) * (2 * H) + koff + ln] = val;
+              break;
+            }
+            default:  // WK_DEC3
+              if (col < I) slab[lo.p_w[L_DEC3] + col * H + ln] = val;
+              break;
+          }
+        }
+      }
+      if (op.bias == 1 && hh == 0) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + (uint32_t)op.d_col_b, v);
+        tmem_ld_wait();
+        const float val = __uint_as_float(v[0]);
+        int l = L_COND1;
+        switch (op.kind) {
+          case WK_COND1: l = L_COND1; break;
+          case WK_ENC0: l = L_ENC0; break;
+          case WK_ENC1: l = L_ENC1; break;
+          case WK_ENC2: l = L_ENC2; break;
+          case WK_ENC3: l = L_ENC3; break;
+          case WK_DEC0_C: l = L_DEC0; break;
+          case WK_DEC1: l = L_DEC1; break;
+          default: l = L_DEC2; break;
+        }
+        slab[lo.p_b[l] + ln] = val;
+      } else if (op.bias == 2 && q == 0) {
+        for (int c = hh; c < op.FB / 16; c += 2) {
+          uint32_t v[16];
+          tmem_ld16(lane_base + (uint32_t)(op.d_col_b + c * 16), v);
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = c * 16 + j;
+              const float val = __uint_as_float(v[j]);
+              if (op.kind == WK_HEADS_E) {
+                if (col < L) slab[lo.p_b[L_HEADS] + col] = val;
+                else if (col < 2 * L) slab[lo.p_blv + (col - L)] = val;
+              } else if (col < I) {
+                slab[lo.p_b[L_DEC3] + col] = val;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_PRODUCER_WARP) tmem_dealloc(tmem, 512);
+}
+
+// =========================================================================================
+// reduction of the partial slabs (+ Adam)
+// =========================================================================================
+struct AdamScalarsTc {
+  float w1, b2, w2, step_size, bc2_sqrt, eps;
+};
+struct ReduceTcArgs {
+  int tensor_end[24];   // end offset (floats) of each state_dict tensor
+  int tensor_role[24];
+  int role_begin[WG_ROLES], role_count[WG_ROLES];
+  int n_params, slab_stride, chain_grid;
+  float w_recon, w_kld, w_start, w_time;
+  AdamScalarsTc h;
+  int adam;
+};
+
+__global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* __restrict__ loss_part,
+                                 const __grid_constant__ ReduceTcArgs r, float* __restrict__ grads, float* __restrict__ p,
+                                 float* __restrict__ m, float* __restrict__ v) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < r.n_params) {
+    int t = 0;
+    while (t < 23 && e >= r.tensor_end[t]) ++t;
+    const int role = r.tensor_role[t];
+    const float* src = slabs + (size_t)r.role_begin[role] * r.slab_stride + e;
+    const int n = r.role_count[role];
+    float s = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
+    grads[e] = s;
+    if (r.adam) {
+      // torch optim/adam.py::_single_tensor_adam (see dmvae_adam.cu)
+      float pp = p[e], mm = m[e], vv = v[e];
+      mm = r.h.w1 < 0.5f ? fmaf(r.h.w1, s - mm, mm) : s - (s - mm) * (1.f - r.h.w1);
+      vv = fmaf(r.h.w2 * s, s, vv * r.h.b2);
+      const float denom = sqrtf(vv) / r.h.bc2_sqrt + r.h.eps;
+      pp = pp - r.h.step_size * (mm / denom);
+      p[e] = pp; m[e] = mm; v[e] = vv;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
+    // the five loss terms: lanes stride the (CTA, row quarter) partials, fixed-order shuffle tree
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = threadIdx.x; c < r.chain_grid * 4; c += 32) {
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) t[qd] += __ldcg(loss_part + (size_t)c * 4 + qd);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) t[qd] += __shfl_xor_sync(0xffffffffu, t[qd], o);
+    if (threadIdx.x == 0) {
+      const float start = r.w_start > 0.f ? t[2] : 0.f;
+      const float time = r.w_time > 0.f ? t[3] : 0.f;
+      float total = r.w_recon * t[0] + r.w_kld * t[1];
+      if (r.w_start > 0.f) total += r.w_start * start;
+      if (r.w_time > 0.f) total += r.w_time * time;
+      float* out = grads + r.n_params;
+      out[0] = total; out[1] = t[0]; out[2] = t[1]; out[3] = start; out[4] = time;
+    }
+  }
+}
+
+// =========================================================================================
+// host side
+// =========================================================================================
+bool train_tc_supported(const Layout& lo) { return lo.Ip <= 64 && lo.L <= 32; }
+
+TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
+  TrainTcPlan p;
+  p.n_tiles = (B + CH_M - 1) / CH_M;
+  p.chain_grid = (int)(p.n_tiles < sm_count ? p.n_tiles : sm_count);
+  p.chain_stages = 4;
+  while (p.chain_stages > 2 && chain_smem_bytes(lo, p.chain_stages) > 232448) --p.chain_stages;
+  p.chain_smem = chain_smem_bytes(lo, p.chain_stages);
+  // CTAs per role in proportion to the accumulator columns (= MMA time per tile), at most one per tile
+  int cols[WG_ROLES], total = 0;
+  for (int r = 0; r < WG_ROLES; ++r) { cols[r] = wgrad_role_cols(lo, r); total += cols[r]; }
+  int used = 0;
+  for (int r = 0; r < WG_ROLES; ++r) {
+    long long n = (long long)sm_count * cols[r] / total;
+    if (n < 1) n = 1;
+    if (n > p.n_tiles) n = p.n_tiles;
+    p.role_count[r] = (int)n;
+    p.role_begin[r] = used;
+    used += (int)n;
+  }
+  p.wgrad_grid = used;
+  p.slab_stride = round_up(lo.n_params, 4);
+  p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
+  p.slab_floats = (size_t)p.wgrad_grid * p.slab_stride;
+  p.loss_floats = (size_t)p.chain_grid * 16;
+  return p;
+}
+
+cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
+                         cudaStream_t stream) {
+  ChainArgs a;
+  a.lo = lo; a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
+  a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
+  a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
+  a.stages = plan.chain_stages;
+  cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.chain_smem);
+  if (e != cudaSuccess) return e;
+  chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream) {
+  WgradArgs a;
+  a.lo = lo; a.stash = stash; a.slabs = slabs; a.n_tiles = plan.n_tiles; a.slab_stride = plan.slab_stride;
+  for (int r = 0; r < WG_ROLES; ++r) a.role_end[r] = plan.role_begin[r] + plan.role_count[r];
+  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
+                             const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
+                             cudaStream_t stream) {
+  ReduceTcArgs r;
+  // state_dict order: cond0 (w,b) cond1 enc0 enc1 enc2 enc3 fc_mu fc_logvar dec0 dec1 dec2 dec3
+  static const int role_of_pair[12] = {0, 0, 1, 0, 0, 1, 2, 2, 2, 1, 1, 2};
+  const int w_off[12] = {lo.p_w[L_COND0], lo.p_w[L_COND1], lo.p_w[L_ENC0], lo.p_w[L_ENC1], lo.p_w[L_ENC2], lo.p_w[L_ENC3],
+                         lo.p_w[L_HEADS], lo.p_wlv,        lo.p_w[L_DEC0], lo.p_w[L_DEC1], lo.p_w[L_DEC2], lo.p_w[L_DEC3]};
+  const int b_off[12] = {lo.p_b[L_COND0], lo.p_b[L_COND1], lo.p_b[L_ENC0], lo.p_b[L_ENC1], lo.p_b[L_ENC2], lo.p_b[L_ENC3],
+                         lo.p_b[L_HEADS], lo.p_blv,        lo.p_b[L_DEC0], lo.p_b[L_DEC1], lo.p_b[L_DEC2], lo.p_b[L_DEC3]};
+  for (int i = 0; i < 12; ++i) {
+    r.tensor_end[2 * i] = b_off[i];                                     // the weight ends where its bias starts
+    r.tensor_end[2 * i + 1] = i < 11 ? w_off[i + 1] : lo.n_params;      // the bias ends where the next weight starts
+    r.tensor_role[2 * i] = r.tensor_role[2 * i + 1] = role_of_pair[i];
+  }
+  for (int k = 0; k < WG_ROLES; ++k) { r.role_begin[k] = plan.role_begin[k]; r.role_count[k] = plan.role_count[k]; }
+  r.n_params = lo.n_params; r.slab_stride = plan.slab_stride; r.chain_grid = plan.chain_grid;
+  r.w_recon = w[0]; r.w_kld = w[1]; r.w_start = w[2]; r.w_time = w[3];
+  r.adam = adam != nullptr ? 1 : 0;
+  r.h = AdamScalarsTc{};
+  if (adam != nullptr) {
+    const double b1 = adam->beta1, b2 = adam->beta2;
+    const double bc1 = 1.0 - pow(b1, (double)adam->step), bc2 = 1.0 - pow(b2, (double)adam->step);
+    r.h.w1 = (float)(1.0 - b1); r.h.b2 = (float)b2; r.h.w2 = (float)(1.0 - b2);
+    r.h.step_size = (float)(adam->lr / bc1); r.h.bc2_sqrt = (float)sqrt(bc2); r.h.eps = (float)adam->eps;
+  }
+  const int threads = 256;
+  reduce_tc_kernel<<<(lo.n_params + threads - 1) / threads, threads, 0, stream>>>(slabs, loss_part, r, grads, p, m, v);
+  return cudaGetLastError();
+}
+
+}  // namespace dmvae

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dmvae_cond_encode": (c_int, [_CFG, _P, _P, _P, c_int64, _P]),
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
     "dmvae_set_decode_impl": (c_int, [c_int]),
+    "dmvae_set_train_impl": (c_int, [c_int]),
     "dmvae_debug_decode_trace": (c_int, [_P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
@@ -66,7 +67,7 @@ SIGNATURES = {
     "dmvae_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 12
+KERNEL_COUNT = 15
 
 _lib = None
 
