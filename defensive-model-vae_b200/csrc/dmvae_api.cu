@@ -417,6 +417,11 @@ int dmvae_debug_decode_trace(void* device_int64x128) {
   return DMVAE_OK;
 }
 
+int dmvae_debug_train_trace(void* device_int64x256) {
+  dmvae::set_chain_trace(static_cast<long long*>(device_int64x256));
+  return DMVAE_OK;
+}
+
 // ---------------------------------------------------------------------------- instrumentation
 const char* dmvae_kernel_name(int kernel) { return dmvae::kernel_name(kernel); }
 int64_t dmvae_launch_count(int kernel) { return dmvae::launch_count(kernel); }

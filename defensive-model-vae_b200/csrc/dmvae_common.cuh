@@ -38,8 +38,9 @@ constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
 // K-major the image is the forward operand W[n][k].  The data-gradient GEMM contracts over n
 // instead; it reads W MN-major, which for TF32 the tensor core only accepts in the 32-byte
 // swizzled layout of dmvae_tc.cuh, so layers with a data gradient carry a second image ("t"
-// planes): per slice of 32 input features k, per 8-deep step of n, two 512-byte atoms
-// [4 n][32 k swizzled].  A ring stage holds whole slices; one slice = 32 output columns.
+// planes): [group of gsz 8-deep steps of n][slice of 32 input features k][step][two 512-byte atoms
+// [4 n][32 k swizzled]].  A ring stage holds one group for a run of slices (32 output columns each),
+// so a data-gradient MMA is as wide as a forward one.
 enum TcId {
   TC_COND0 = 0, TC_COND1, TC_ENC0, TC_ENC1, TC_ENC2, TC_ENC3, TC_HEADS, TC_DEC0, TC_DEC1, TC_DEC2, TC_DEC3, NUM_TC
 };
@@ -49,12 +50,13 @@ struct TcLayer {
   int K;         // contraction length (multiple of 8).  cond0 = 8: [x0, y0, 1 (bias row), 0...];
                  // enc0 = Ip (zero rows past I); heads = 256: [h_traj ; h_c];
                  // dec0 = 128 (h_c) + Lp16 (z, zero padded)
+  int Kb;        // K plus the bias step (8 more rows) of the forward planes
   int N;         // output width (multiple of 16): 128; heads = NH; dec3 = Ip
   int kps;       // K-steps per 32 KB ring stage (both planes): 512 / N
   int off_thi;   // data-gradient image (high plane), -1 if the layer needs none
   int off_tlo;
   int Kt;        // its output width: K rounded up to 32 (dec0: 128 + Lz32)
-  int sps;       // slices (of 32 outputs) per ring stage: min(Kt / 32, 128 / N)
+  int gsz;       // contraction steps per group: min(4, N / 8)
 };
 
 // Training stash: what the forward / backward chain kernel leaves for the weight-gradient
@@ -168,13 +170,15 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
     else if (t == TC_DEC0) c.K = H + l.Lp16;
     else if (t == TC_DEC3) c.N = l.Ip;
     c.kps = STAGE_FLOATS / (16 * c.N);
-    c.off_hi = q; q += c.K * c.N;
-    c.off_lo = q; q += c.K * c.N;
-    c.off_thi = c.off_tlo = -1; c.Kt = 0; c.sps = 0;
+    // forward planes carry one more K step: the bias row (k = K) and seven zero rows, multiplied by a
+    // constant ones column of the A operand (cond0 has its bias row inside its K = 8)
+    c.Kb = t == TC_COND0 ? c.K : c.K + 8;
+    c.off_hi = q; q += c.Kb * c.N;
+    c.off_lo = q; q += c.Kb * c.N;
+    c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
     if (t != TC_COND0 && t != TC_ENC0) {
       c.Kt = (t == TC_DEC0) ? H + round_up(l.L, 32) : c.K;
-      c.sps = c.Kt / 32 < 128 / c.N ? c.Kt / 32 : 128 / c.N;
-      if (c.sps < 1) c.sps = 1;
+      c.gsz = c.N / 8 < 4 ? c.N / 8 : 4;
       c.off_thi = q; q += c.Kt * c.N;
       c.off_tlo = q; q += c.Kt * c.N;
     }

@@ -62,6 +62,7 @@ struct TrainTcPlan {
   size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials]
 };
 bool train_tc_supported(const Layout& lo);
+void set_chain_trace(long long* device_buffer);  // development aid (256 int64), null = off
 TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count);
 cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
                          cudaStream_t stream);

@@ -24,13 +24,28 @@
 //   reduce_tc_kernel  fixed-order sum of the partial slabs (+ the loss partials), optionally with
 //                  the Adam update (torch optim/adam.py::_single_tensor_adam) in the same thread.
 //
-// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 32 (the reference uses 10/12 and 8);
+// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 16 (the reference uses 10/12 and 8);
 // anything else inside the ABI envelope runs the FFMA kernel of dmvae_train.cu.
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
 #include "dmvae_tc.cuh"
 
+#include <type_traits>
+
 namespace dmvae {
+
+// 256-bit global accesses (one full 32-byte sector per lane)
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
 
 // =========================================================================================
 // chain kernel
@@ -45,18 +60,21 @@ constexpr int CH_MAX_OPS = 24;
 // tensor-memory columns: accumulator, then the A operand regions (128 main + 64 extra each)
 constexpr uint32_t CT_D = 0, CT_AHI = 128, CT_ALO = 320, CT_X = 128, CT_COLS = 512;
 constexpr uint32_t CT_DX = CT_AHI + CT_X;  // small accumulators (heads, d/dz) live in the extra A_hi columns
+constexpr uint32_t CT_ONES = CT_ALO + CT_X + 56;  // constant A columns [1, 0 x 7]: multiply the bias row of a weight image
 
 struct COp {
   int off_hi, off_lo;  // planes of the layer image in the packed arena (floats): forward or data-gradient image
   int N;               // output width of the layer (forward N; the contraction length of its data gradient)
   int k0, nk;          // forward: K-step range of the image; data gradient: slice range (32 outputs each)
-  int kps;             // forward: K steps per ring stage; data gradient: slices per ring stage
+  int kps;             // forward: K steps per ring stage; data gradient: contraction steps per group (= per stage)
+  int S;               // data gradient: slices in the whole image
   int dgrad;           // 0 forward (B read K-major); 1 data gradient (B read MN-major)
   int a_col;           // column inside the A regions of the first contraction step
   int d_col;           // tensor-memory column of the accumulator (dgrad: of the first slice)
   int acc;             // accumulate onto what the accumulator already holds
   int wait_a;          // wait for the epilogue warps before issuing (A operand written, D drained)
   int commit_d;        // signal the epilogue warps when the accumulator is complete
+  int bias_k;          // forward: K step of the image that holds the bias row (multiplied by the ones column), or -1
 };
 
 struct ChainArgs {
@@ -70,12 +88,13 @@ struct ChainArgs {
   long long B;
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
+  long long* trace;   // development aid: clock64 stamps of CTA 0, first tile (null in production)
 };
 
 __device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
                                     int wait_a = 1, int commit_d = 1) {
-  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.sps, 1, a_col, d_col, acc, wait_a, commit_d};
-  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, a_col, d_col, acc, wait_a, commit_d};
+  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_col, d_col, acc, wait_a, commit_d, -1};
+  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_col, d_col, acc, wait_a, commit_d, -1};
 }
 
 // The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
@@ -83,18 +102,23 @@ __device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad,
 __device__ inline int chain_program(const Layout& lo, COp* ops) {
   const int zs = lo.Lp16 / 8;
   int n = 0;
-  ops[n++] = c_op(lo.tc[TC_COND0], 0, 1, 0, 0, CT_D, 0);               // start -> hc1
-  ops[n++] = c_op(lo.tc[TC_COND1], 0, 16, 0, 0, CT_D, 0);              // hc1 -> hc
-  ops[n++] = c_op(lo.tc[TC_HEADS], 16, 16, 0, 0, CT_DX, 0);            // hc share of the heads (kept aside)
-  ops[n++] = c_op(lo.tc[TC_ENC0], 0, lo.Ip / 8, 0, 0, CT_D, 0);        // x_rel -> e1
-  ops[n++] = c_op(lo.tc[TC_ENC1], 0, 16, 0, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_ENC2], 0, 16, 0, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_ENC3], 0, 16, 0, 0, CT_D, 0);               // -> e4
-  ops[n++] = c_op(lo.tc[TC_HEADS], 0, 16, 0, 0, CT_DX, 1);             // + h_traj share -> mu, logvar
-  ops[n++] = c_op(lo.tc[TC_DEC0], 0, 16 + zs, 0, 0, CT_D, 0);          // [hc ; z] -> d1
-  ops[n++] = c_op(lo.tc[TC_DEC1], 0, 16, 0, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_DEC2], 0, 16, 0, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_DEC3], 0, 16, 0, 0, CT_D, 0);               // -> recon
+  auto fwd = [&](int t, int k0, int nk, int d_col, int acc, bool with_bias) {
+    COp o = c_op(lo.tc[t], k0, nk, 0, 0, d_col, acc);
+    if (with_bias) o.bias_k = lo.tc[t].K / 8;
+    ops[n++] = o;
+  };
+  fwd(TC_COND0, 0, 1, CT_D, 0, false);              // start -> hc1 (bias row inside its K = 8)
+  fwd(TC_COND1, 0, 16, CT_D, 0, true);              // hc1 -> hc
+  fwd(TC_HEADS, 16, 16, CT_DX, 0, false);           // hc share of the heads (kept aside)
+  fwd(TC_ENC0, 0, lo.Ip / 8, CT_D, 0, true);        // x_rel -> e1
+  fwd(TC_ENC1, 0, 16, CT_D, 0, true);
+  fwd(TC_ENC2, 0, 16, CT_D, 0, true);
+  fwd(TC_ENC3, 0, 16, CT_D, 0, true);               // -> e4
+  fwd(TC_HEADS, 0, 16, CT_DX, 1, true);             // + h_traj share + bias -> mu, logvar
+  fwd(TC_DEC0, 0, 16 + zs, CT_D, 0, true);          // [hc ; z] -> d1
+  fwd(TC_DEC1, 0, 16, CT_D, 0, true);
+  fwd(TC_DEC2, 0, 16, CT_D, 0, true);
+  fwd(TC_DEC3, 0, 16, CT_D, 0, true);               // -> recon
   ops[n++] = c_op(lo.tc[TC_DEC3], 0, 4, 1, 0, CT_D, 0);                // d recon -> d d3 (4 slices of 32 columns)
   ops[n++] = c_op(lo.tc[TC_DEC2], 0, 4, 1, 0, CT_D, 0);
   ops[n++] = c_op(lo.tc[TC_DEC1], 0, 4, 1, 0, CT_D, 0);
@@ -109,14 +133,28 @@ __device__ inline int chain_program(const Layout& lo, COp* ops) {
   return n;
 }
 
-// bias rows kept in shared memory
-enum BiasRow { BR_COND1 = 0, BR_ENC0, BR_ENC1, BR_ENC2, BR_ENC3, BR_HEADS, BR_DEC0, BR_DEC1, BR_DEC2, BR_DEC3, BR_COUNT };
-// relu' mask slots (registers of the epilogue threads)
+// relu' mask slots (two words per epilogue thread and slot, in shared memory)
 enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_D3, MK_COUNT };
+// The epilogues of a tile, in the order of the ops that signal them (chain_program).  The tile body is a
+// loop over this table rather than 22 inlined epilogues: the code stays small enough for the instruction
+// cache (the unrolled version spent as many issue slots waiting for instructions as for memory).
+enum EpiType { EP_HIDDEN = 0, EP_XREL, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
+constexpr int CH_EPIS = 22;
+__constant__ int c_epi[CH_EPIS][4] = {
+    // type, mask slot, stash slot, write the A operand
+    {EP_HIDDEN, MK_HC1, SX_HC1, 1}, {EP_HIDDEN, MK_HC, SX_HC, 1},  {EP_XREL, 0, 0, 0},
+    {EP_HIDDEN, MK_E1, SX_E1, 1},   {EP_HIDDEN, MK_E2, SX_E2, 1},  {EP_HIDDEN, MK_E3, SX_E3, 1},
+    {EP_HIDDEN, MK_E4, SX_E4, 1},   {EP_HEADS, 0, 0, 0},           {EP_HIDDEN, MK_D1, SX_D1, 1},
+    {EP_HIDDEN, MK_D2, SX_D2, 1},   {EP_HIDDEN, MK_D3, SX_D3, 1},  {EP_LOSS, 0, 0, 0},
+    {EP_DGRAD, MK_D3, SG_D3, 1},    {EP_DGRAD, MK_D2, SG_D2, 1},   {EP_DGRAD, MK_D1, SG_D1, 1},
+    {EP_BDEC0, 0, 0, 0},            {EP_DGRAD, MK_HC, SG_HC, 1},   {EP_DGRAD, MK_HC1, SG_HC1, 0},
+    {EP_DGRAD, MK_E4, SG_E4, 1},    {EP_DGRAD, MK_E3, SG_E3, 1},   {EP_DGRAD, MK_E2, SG_E2, 1},
+    {EP_DGRAD, MK_E1, SG_E1, 0},
+};
 
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
-  return (size_t)stages * STAGE_FLOATS + 64 * CH_EPI_THREADS /* hc / recon scratch */ + (size_t)lo.NH * 128 /* mu, logvar */ +
-         (size_t)lo.Lp16 * 128 /* eps */ + BR_COUNT * H;
+  return (size_t)stages * STAGE_FLOATS + (size_t)lo.Ip * 128 /* recon scratch */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
+         (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */;
 }
 __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
   return chain_smem_floats(lo, stages) * 4 + CH_MAX_OPS * sizeof(COp) + 24 * 8 + 16 + 1024;
@@ -126,7 +164,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   extern __shared__ unsigned char smem_dyn[];
   const Layout& lo = a.lo;
   const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
-  float *ring, *scratch, *mlb, *epb, *bias;
+  float *ring, *scratch, *xbuf, *mlb, *epb;
+  uint32_t* masks;
   COp* ops;
   uint64_t *full, *empty, *d_ready, *a_ready;
   uint32_t* tmem_slot;
@@ -135,10 +174,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
     ring = reinterpret_cast<float*>(p);
     scratch = ring + (size_t)a.stages * STAGE_FLOATS;
-    mlb = scratch + 64 * CH_EPI_THREADS;
+    xbuf = scratch + (size_t)Ip * 128;
+    mlb = xbuf + round_up(128 * I, 4);
     epb = mlb + (size_t)NH * 128;
-    bias = epb + (size_t)Lp16 * 128;
-    ops = reinterpret_cast<COp*>(bias + BR_COUNT * H);
+    masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
+    ops = reinterpret_cast<COp*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
     full = reinterpret_cast<uint64_t*>(ops + CH_MAX_OPS);
     empty = full + 8;
     d_ready = empty + 8;
@@ -160,20 +200,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     chain_program(lo, ops);
   }
   if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
-  if (tid < CH_EPI_THREADS) {
-    for (int i = tid; i < H; i += CH_EPI_THREADS) {
-      bias[BR_COND1 * H + i] = pk[lo.q_b[L_COND1] + i];
-      bias[BR_ENC0 * H + i] = pk[lo.q_b[L_ENC0] + i];
-      bias[BR_ENC1 * H + i] = pk[lo.q_b[L_ENC1] + i];
-      bias[BR_ENC2 * H + i] = pk[lo.q_b[L_ENC2] + i];
-      bias[BR_ENC3 * H + i] = pk[lo.q_b[L_ENC3] + i];
-      bias[BR_HEADS * H + i] = i < 2 * L ? pk[lo.q_b[L_HEADS] + i] : 0.f;
-      bias[BR_DEC0 * H + i] = pk[lo.q_b[L_DEC0] + i];
-      bias[BR_DEC1 * H + i] = pk[lo.q_b[L_DEC1] + i];
-      bias[BR_DEC2 * H + i] = pk[lo.q_b[L_DEC2] + i];
-      bias[BR_DEC3 * H + i] = i < I ? pk[lo.q_b[L_DEC3] + i] : 0.f;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -187,18 +213,40 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int o = 0; o < n_ops; ++o) {
           const COp op = ops[o];
-          for (int k = 0; k < op.nk; k += op.kps) {
-            const int nks = min(op.kps, op.nk - k);
-            // forward: nks K steps of N*8 floats; data gradient: nks slices of N*32 floats - contiguous either way
-            const int unit = op.dgrad ? op.N * 32 : op.N * 8;
-            const int fl = nks * unit;
-            const size_t src = (size_t)(op.k0 + k) * unit;
-            float* dst = ring + rs.stage * STAGE_FLOATS;
-            mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
-            mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
-            tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
-            tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
-            rs.advance();
+          if (!op.dgrad) {
+            for (int k = 0; k < op.nk; k += op.kps) {  // nks K steps of N*8 floats, contiguous in a plane
+              const int nks = min(op.kps, op.nk - k);
+              const int fl = nks * op.N * 8;
+              const size_t src = (size_t)(op.k0 + k) * op.N * 8;
+              float* dst = ring + rs.stage * STAGE_FLOATS;
+              mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
+              tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              rs.advance();
+            }
+            if (op.bias_k >= 0) {  // one more stage: the K step with the bias row
+              const int fl = op.N * 8;
+              const size_t src = (size_t)op.bias_k * op.N * 8;
+              float* dst = ring + rs.stage * STAGE_FLOATS;
+              mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
+              tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              rs.advance();
+            }
+          } else {
+            const int ngroups = (op.N >> 3) / op.kps;
+            const int fl = op.nk * op.kps * 256;       // nk slices x gsz steps x 1 KB, contiguous inside a group
+            for (int jg = 0; jg < ngroups; ++jg) {
+              const size_t src = (size_t)((jg * op.S + op.k0) * op.kps) * 256;
+              float* dst = ring + rs.stage * STAGE_FLOATS;
+              mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
+              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
+              tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              rs.advance();
+            }
           }
         }
     }
@@ -214,14 +262,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           a_phase ^= 1u;
         }
         tc_fence_after();
-        const uint32_t unit_bytes = op.dgrad ? (uint32_t)op.N * 128u : (uint32_t)op.N * 32u;  // slice / K step of a plane
-        for (int k = 0; k < op.nk; k += op.kps) {
-          const int nks = min(op.kps, op.nk - k);
-          mbar_wait(&full[rs.stage], rs.phase);
-          tc_fence_after();
-          const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
-          const uint32_t b_lo = b_hi + (uint32_t)nks * unit_bytes;
-          if (!op.dgrad) {
+        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tile == blockIdx.x && lane == 0;
+        if (tr) a.trace[o * 4 + 0] = clock64();
+        if (!op.dgrad) {
+          const uint32_t unit_bytes = (uint32_t)op.N * 32u;  // one K step of a plane
+          for (int k = 0; k < op.nk; k += op.kps) {
+            const int nks = min(op.kps, op.nk - k);
+            mbar_wait(&full[rs.stage], rs.phase);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
+            const uint32_t b_lo = b_hi + (uint32_t)nks * unit_bytes;
             // D[128 x N] (+)= A[:, 8 (k + ks) ..] x W^T, B K-major: LBO = chunk stride N*16, SBO = 128
             const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
             const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
@@ -240,20 +290,41 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               }
               umma_commit(&empty[rs.stage]);
             }
-          } else {
-            // columns [32 k, 32 (k + nks)) of D  (+)=  G[128 x N] x W[:, those inputs]; B MN-major (32-byte
-            // swizzle): LBO = slice stride (next 32 outputs), SBO = 512 (next 4 of the contraction); the
-            // 8-deep contraction step j starts 1024 bytes into a slice
-            const uint32_t idesc = umma_idesc_tf32(CH_M, 32 * nks, UMMA_B_MN);
-            const uint64_t dbits = umma_desc(0u, unit_bytes, 512u, 1u);
-            uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)(b_lo >> 4);
-            const uint32_t d = tmem + (uint32_t)(op.d_col + 32 * k);
-            uint32_t a_hi = tmem + CT_AHI + (uint32_t)op.a_col, a_lo = tmem + CT_ALO + (uint32_t)op.a_col;
-            uint32_t accf = op.acc ? 1u : 0u;
-            const int nj = op.N >> 3;
+            __syncwarp();
+            rs.advance();
+          }
+          if (op.bias_k >= 0) {  // D += ones column x bias row (high and low halves)
+            mbar_wait(&full[rs.stage], rs.phase);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
+            const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
+            const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
             if (elect_one()) {
-#pragma unroll 4
-              for (int j = 0; j < nj; ++j) {
+              umma_tf32_ts(tmem + (uint32_t)op.d_col, tmem + CT_ONES, dbits | (uint64_t)(b_hi >> 4), idesc, 1u);
+              umma_tf32_ts(tmem + (uint32_t)op.d_col, tmem + CT_ONES, dbits | (uint64_t)((b_hi + unit_bytes) >> 4), idesc, 1u);
+              umma_commit(&empty[rs.stage]);
+            }
+            __syncwarp();
+            rs.advance();
+          }
+        } else {
+          // D[128 x 32 nk] (+)= G[128 x N] x W[:, those inputs]; B MN-major (32-byte swizzle): LBO = slice
+          // stride (next 32 outputs) = gsz KB, SBO = 512 (next 4 of the contraction); step st of the group
+          // starts st KB into a slice
+          const int ngroups = (op.N >> 3) / op.kps;
+          const uint32_t plane = (uint32_t)(op.nk * op.kps) * 1024u;
+          const uint32_t idesc = umma_idesc_tf32(CH_M, 32 * op.nk, UMMA_B_MN);
+          const uint64_t dbits = umma_desc(0u, (uint32_t)op.kps * 1024u, 512u, 1u);
+          const uint32_t d = tmem + (uint32_t)op.d_col;
+          uint32_t a_hi = tmem + CT_AHI + (uint32_t)op.a_col, a_lo = tmem + CT_ALO + (uint32_t)op.a_col;
+          uint32_t accf = op.acc ? 1u : 0u;
+          for (int jg = 0; jg < ngroups; ++jg) {
+            mbar_wait(&full[rs.stage], rs.phase);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
+            uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)((b_hi + plane) >> 4);
+            if (elect_one()) {
+              for (int st = 0; st < op.kps; ++st) {
                 umma_tf32_ts(d, a_hi, dh, idesc, accf);
                 umma_tf32_ts(d, a_lo, dh, idesc, 1u);
                 umma_tf32_ts(d, a_hi, dl, idesc, 1u);
@@ -262,14 +333,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               }
               umma_commit(&empty[rs.stage]);
             }
+            __syncwarp();
+            a_hi = tmem + CT_AHI + (uint32_t)(op.a_col + 8 * (jg + 1) * op.kps);
+            a_lo = tmem + CT_ALO + (uint32_t)(op.a_col + 8 * (jg + 1) * op.kps);
+            accf = 1u;
+            rs.advance();
           }
-          __syncwarp();
-          rs.advance();
         }
         if (op.commit_d) {
           if (elect_one()) umma_commit(d_ready);
           __syncwarp();
         }
+        if (tr) a.trace[o * 4 + 1] = clock64();
       }
   } else {
     // ===================== epilogue warps =======================================================
@@ -277,22 +352,26 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     const int m = q * 32 + lane;             // row of the tile owned by this thread
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t d_phase = 0;
-    uint32_t mk[MK_COUNT][2];
+    uint32_t* my_mask = masks + tid;   // [(slot * 2 + word) * 256 + tid]
     float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float* my_scr = scratch + tid;   // [j * 256 + tid]: the 64 values this thread parks (hc, then recon)
     float* my_ml = mlb + m;          // [n * 128 + m], h == 0 threads
     float* my_ep = epb + m;
 
+    int epi_no = 0;
+    bool tr_tile = false;
     auto wait_d = [&]() {
       mbar_wait(d_ready, d_phase);
       d_phase ^= 1u;
       tc_fence_after();
+      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
     };
     auto release_a = [&]() {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2 + 1] = clock64();
+      ++epi_no;
     };
     // a 4-feature chunk of this thread's row in a stash image (MN-major, 32-byte swizzle: dmvae_tc.cuh)
     auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
@@ -301,9 +380,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     // start point of the tile's row -> A columns [x0, y0, 1, 0...] and the 16-wide stash image
     auto stage_start = [&](long long tile) {
       if (h == 0) {
-        const long long row = tile * CH_M + m;
-        float sx = 0.f, sy = 0.f;
-        if (row < a.B) { sx = __ldg(a.x + row * I + 1); sy = __ldg(a.x + row * I + 2); }
+        const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];   // zeros past the batch end
         uint32_t xh, xl, yh, yl;
         split_tf32(sx, xh, xl);
         split_tf32(sy, yh, yl);
@@ -318,6 +395,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       }
     };
 
+    // the tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end
+    auto load_x = [&](long long tile) {
+      const long long base = tile * CH_M * I;
+      const long long left = a.B * I - base;
+      const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
+      for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(a.x + base + i) : 0.f;
+    };
+    load_x(blockIdx.x);
+    if (h == 0) {  // the constant ones column (never overwritten)
+      tmem_st4(lane_base + CT_ONES, __float_as_uint(1.0f), 0u, 0u, 0u);
+      tmem_st4(lane_base + CT_ONES + 4, 0u, 0u, 0u, 0u);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
     stage_start(blockIdx.x);
     release_a();
 
@@ -325,75 +415,87 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       const long long row = tile * CH_M + m;
       const bool row_ok = row < a.B;
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
+      tr_tile = a.trace != nullptr && blockIdx.x == 0 && tile == blockIdx.x;
+      epi_no = 0;
 
-      // hidden layer: D -> (+ bias) -> relu -> mask, stash image, A operand (optionally parked in smem)
-      auto epi_hidden = [&](const float* brow, int mslot, int xslot, bool park) {
+      // this thread's 64 features of a 128-wide stash image: base of its row, then per 4-feature chunk
+      // (mn_image_index with the row part hoisted; f = h*64 + c*16 + j4*4)
+      const int row_part = (m >> 2) * 512 + (m & 3) * 32;
+      const int swz = m & 3;
+      auto unit_off = [&](int c, int up) -> int {   // 8 features h*64 + c*16 + up*8 ..: one swizzled 32-byte unit
+        return (h * 2 + (c >> 1)) * 128 + (((((c & 1) << 1) + up) ^ swz) << 3);
+      };
+      // hidden layer (the bias is already in D): relu -> mask, stash image, A operand;
+      // 16 columns at a time, the next tensor-memory load in flight while a chunk is processed.
+      // Mask word w holds columns 32 w .. 32 w + 31 of this thread's 64, first column in the top bit.
+      auto epi_hidden = [&](int ms, int xslot) {
+        float* xs = ts + lo.slot_off[xslot] + row_part;
         wait_d();
-        uint32_t v[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + CT_D + h * 64 + c * 16, v[c]);
-        tmem_ld_wait();
-        uint32_t m0 = 0u, m1 = 0u;
+        uint32_t v[2][16];
+        tmem_ld16(lane_base + CT_D + h * 64, v[0]);
+        uint32_t mw[2] = {0u, 0u};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld16(lane_base + CT_D + h * 64 + (c + 1) * 16, v[(c + 1) & 1]);
           uint32_t hi[16], lw[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(v[c][j]);
-            if (brow != nullptr) x += brow[h * 64 + c * 16 + j];
-            x = fmaxf(x, 0.f);
-            const uint32_t bit = x > 0.f ? 1u : 0u;
-            if (c < 2) m0 |= bit << (c * 16 + j); else m1 |= bit << ((c - 2) * 16 + j);
-            split_tf32(x, hi[j], lw[j]);
-            v[c][j] = __float_as_uint(x);
-            if (park) my_scr[(c * 16 + j) * CH_EPI_THREADS] = x;
+          for (int up = 0; up < 2; ++up) {
+            float xv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = up * 8 + i;
+              const uint32_t bits = v[c & 1][j];
+              // positive <=> the negated bit pattern is negative as an integer: shift its sign into the mask
+              mw[c >> 1] = __funnelshift_l(0u - bits, mw[c >> 1], 1);
+              const float x = fmaxf(__uint_as_float(bits), 0.f);
+              split_tf32_cvt(x, hi[j], lw[j]);
+              xv[i] = x;
+            }
+            st_global_v8(xs + unit_off(c, up), xv);
           }
           tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
           tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            *stash_ptr(ts, xslot, h * 16 + c * 4 + j4) =
-                make_float4(__uint_as_float(v[c][4 * j4]), __uint_as_float(v[c][4 * j4 + 1]),
-                            __uint_as_float(v[c][4 * j4 + 2]), __uint_as_float(v[c][4 * j4 + 3]));
         }
-        mk[mslot][0] = m0; mk[mslot][1] = m1;
+        my_mask[(ms * 2) * CH_EPI_THREADS] = mw[0];
+        my_mask[(ms * 2 + 1) * CH_EPI_THREADS] = mw[1];
         release_a();
       };
       // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand)
-      auto epi_dgrad = [&](int mslot, int gslot, bool write_a) {
+      auto epi_dgrad = [&](int ms, int gslot, bool write_a) {
+        float* gs = ts + lo.slot_off[gslot] + row_part;
         wait_d();
-        uint32_t v[4][16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld16(lane_base + CT_D + h * 64 + c * 16, v[c]);
-        tmem_ld_wait();
-        const uint32_t m0 = mk[mslot][0], m1 = mk[mslot][1];
+        uint32_t v[2][16];
+        tmem_ld16(lane_base + CT_D + h * 64, v[0]);
+        uint32_t mw[2] = {my_mask[(ms * 2) * CH_EPI_THREADS], my_mask[(ms * 2 + 1) * CH_EPI_THREADS]};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld16(lane_base + CT_D + h * 64 + (c + 1) * 16, v[(c + 1) & 1]);
           uint32_t hi[16], lw[16];
+          float gv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const uint32_t bit = c < 2 ? (m0 >> (c * 16 + j)) & 1u : (m1 >> ((c - 2) * 16 + j)) & 1u;
-            const float gr = bit ? __uint_as_float(v[c][j]) : 0.f;
-            v[c][j] = __float_as_uint(gr);
-            split_tf32(gr, hi[j], lw[j]);
+            // all-ones / all-zeros from the top mask bit, then AND: no branch, no select on a predicate
+            const uint32_t keep = (uint32_t)((int32_t)mw[c >> 1] >> 31);
+            mw[c >> 1] <<= 1;
+            gv[j] = __uint_as_float(v[c & 1][j] & keep);
+            split_tf32_cvt(gv[j], hi[j], lw[j]);
+          }
+#pragma unroll
+          for (int up = 0; up < 2; ++up) {
+            const float g8[8] = {gv[up * 8], gv[up * 8 + 1], gv[up * 8 + 2], gv[up * 8 + 3],
+                                 gv[up * 8 + 4], gv[up * 8 + 5], gv[up * 8 + 6], gv[up * 8 + 7]};
+            st_global_v8(gs + unit_off(c, up), g8);
           }
           if (write_a) {
             tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
             tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
           }
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            *stash_ptr(ts, gslot, h * 16 + c * 4 + j4) =
-                make_float4(__uint_as_float(v[c][4 * j4]), __uint_as_float(v[c][4 * j4 + 1]),
-                            __uint_as_float(v[c][4 * j4 + 2]), __uint_as_float(v[c][4 * j4 + 3]));
         }
       };
-
-      // ---------------------------------- forward ---------------------------------------------
-      epi_hidden(nullptr, MK_HC1, SX_HC1, false);                 // cond0 (bias rides on the ones column)
-      epi_hidden(bias + BR_COND1 * H, MK_HC, SX_HC, true);        // cond1 -> hc (parked for dec0)
-      // hc share of the heads issued: now the encoder input, x_rel = x - start on the x, y columns
-      // (Training_VAE.py:345-348), zero beyond I
+      // encoder input: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
+      auto epi_xrel = [&]() {
       wait_d();
       if (h * 64 < Ip) {
         const int nc = min(Ip - h * 64, 64) >> 2;
@@ -403,11 +505,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           for (int i = 0; i < 4; ++i) {
             const int n = h * 64 + c4 * 4 + i;
             float val = 0.f;
-            if (row_ok && n < I) {
-              val = __ldg(a.x + row * I + n);
+            if (n < I) {
+              val = xbuf[m * I + n];
               const int d = n % 3;
-              if (d == 1) val = val - __ldg(a.x + row * I + 1);
-              else if (d == 2) val = val - __ldg(a.x + row * I + 2);
+              if (d == 1) val = val - xbuf[m * I + 1];
+              else if (d == 2) val = val - xbuf[m * I + 2];
             }
             xv[i] = val;
           }
@@ -420,21 +522,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
       release_a();
-      epi_hidden(bias + BR_ENC0 * H, MK_E1, SX_E1, false);
-      epi_hidden(bias + BR_ENC1 * H, MK_E2, SX_E2, false);
-      epi_hidden(bias + BR_ENC2 * H, MK_E3, SX_E3, false);
-      epi_hidden(bias + BR_ENC3 * H, MK_E4, SX_E4, false);
+      };
+      auto epi_heads = [&]() {
       // heads: mu, logvar (Training_VAE.py:193-196); z = mu + eps * exp(0.5 logvar) (:199-206);
-      // then [hc ; z] becomes the A operand of dec0
+      // then [hc ; z] becomes the A operand of dec0.  hc comes back from this thread's own part of its stash
+      // image (L2); the loads are issued before waiting for the accumulator
+      float hcv[8][8];
+      {
+        const float* hs = ts + lo.slot_off[SX_HC] + row_part;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ld_global_v8(hs + unit_off(c, 0), hcv[2 * c]);
+          ld_global_v8(hs + unit_off(c, 1), hcv[2 * c + 1]);
+        }
+      }
       wait_d();
       if (h == 0) {
-        const float* bh = bias + BR_HEADS * H;
         for (int c = 0; c < NH / 16; ++c) {
           uint32_t v[16];
           tmem_ld16(lane_base + CT_DX + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bh[c * 16 + j];
+          for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]);
         }
         for (int jb = 0; jb < Lp16 / 4; ++jb) {
           float e4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -471,44 +580,41 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         for (int jb = Lp16 / 4; jb < lo.slot_w[SX_Z] / 4; ++jb) *stash_ptr(ts, SX_Z, jb) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {  // hc back from its parking place
+      for (int c = 0; c < 4; ++c) {
         uint32_t hi[16], lw[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32(my_scr[(c * 16 + j) * CH_EPI_THREADS], hi[j], lw[j]);
+        for (int j = 0; j < 16; ++j) split_tf32_cvt(hcv[2 * c + (j >> 3)][j & 7], hi[j], lw[j]);
         tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
         tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
       }
       release_a();
-      epi_hidden(bias + BR_DEC0 * H, MK_D1, SX_D1, false);
-      epi_hidden(bias + BR_DEC1 * H, MK_D2, SX_D2, false);
-      epi_hidden(bias + BR_DEC2 * H, MK_D3, SX_D3, false);
-
+      };
+      auto epi_loss = [&]() {
       // ---------------------------------- loss (Training_VAE.py:229-268) -----------------------
       // recon -> the five terms and d(total)/d(recon), which becomes the A operand of dec3's
       // data gradient; one thread per row walks the time steps in order
       wait_d();
       if (h == 0) {
         float* rb = scratch + m;   // [n * 128 + m]
-        const float* b3 = bias + BR_DEC3 * H;
         for (int c = 0; c < Ip / 16; ++c) {
           uint32_t v[16];
           tmem_ld16(lane_base + CT_D + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]) + b3[c * 16 + j];
+          for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]);
         }
         if (row_ok) {
           const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
           const float c_start = a.w_start * a.inv_batch;
           const float c_t0 = a.w_time * 2.f * a.inv_batch;
           const float c_mono = T > 1 ? a.w_time * a.inv_batch / (float)(T - 1) : 0.f;
-          const float* xr = a.x + row * I;
-          const float sx = __ldg(xr + 1), sy = __ldg(xr + 2);
+          const float* xr = xbuf + m * I;
+          const float sx = xr[1], sy = xr[2];
           float s_rec = 0.f, s_start = 0.f, s_t0 = 0.f, s_mono = 0.f;
           float g_prev = 0.f, r_prev = 0.f;
           for (int t = 0; t < T; ++t) {
             {
-              const float r = rb[(3 * t) * 128], xv = __ldg(xr + 3 * t);
+              const float r = rb[(3 * t) * 128], xv = xr[3 * t];
               const float diff = r - xv;
               s_rec = fmaf(diff, diff, s_rec);
               float g = c_rec * diff;
@@ -530,7 +636,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
             for (int d = 1; d < 3; ++d) {
               const int n = 3 * t + d;
-              const float r = rb[n * 128], xv = __ldg(xr + n) - (d == 1 ? sx : sy);
+              const float r = rb[n * 128], xv = xr[n] - (d == 1 ? sx : sy);
               const float diff = r - xv;
               s_rec = fmaf(diff, diff, s_rec);
               float g = c_rec * diff;
@@ -568,11 +674,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         }
       }
       release_a();
-
-      // ---------------------------------- backward ----------------------------------------------
-      epi_dgrad(MK_D3, SG_D3, true); release_a();
-      epi_dgrad(MK_D2, SG_D2, true); release_a();
-      epi_dgrad(MK_D1, SG_D1, true); release_a();
+      };
+      auto epi_bdec0 = [&]() {
       // dec0: d/dz is in the small accumulator; reparameterisation + KLD backward (Training_VAE.py:243):
       //   d/dmu = w_k mu / (B L) + g_z ;  d/dlogvar = -0.5 w_k (1 - e^lv) / (B L) + 0.5 g_z eps e^(lv/2)
       // -> the (mu, logvar) gradient becomes the A operand (extra columns) of the heads' data gradients.
@@ -617,16 +720,36 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
         for (int c4 = NH / 4; c4 < lo.slot_w[SG_ML] / 4; ++c4) *stash_ptr(ts, SG_ML, c4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       release_a();
-      epi_dgrad(MK_HC, SG_HC, true); release_a();     // both shares of d/dhc -> d hc
-      epi_dgrad(MK_HC1, SG_HC1, false); release_a();  // -> d hc1 (cond0 needs no data gradient)
-      epi_dgrad(MK_E4, SG_E4, true); release_a();
-      epi_dgrad(MK_E3, SG_E3, true); release_a();
-      epi_dgrad(MK_E2, SG_E2, true); release_a();
-      epi_dgrad(MK_E1, SG_E1, false);                 // enc0 needs no data gradient
+      };
+
       const long long next = tile + gridDim.x;
-      if (next < n_tiles) stage_start(next);
-      release_a();
+#pragma unroll 1
+      for (int e = 0; e < CH_EPIS; ++e) {
+        const int ty = c_epi[e][0];
+        if (ty == EP_HIDDEN) {
+          epi_hidden(c_epi[e][1], c_epi[e][2]);
+        } else if (ty == EP_DGRAD) {
+          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0);
+          // after the first data gradient every warp is past the loss (that MMA could not finish before all of
+          // them had released its A operand): the x tile can be replaced by the next tile's; after the last one
+          // the next tile's start point is staged
+          if (next < n_tiles) {
+            if (e == 12) load_x(next);
+            else if (e == CH_EPIS - 1) stage_start(next);
+          }
+          release_a();
+        } else if (ty == EP_XREL) {
+          epi_xrel();
+        } else if (ty == EP_HEADS) {
+          epi_heads();
+        } else if (ty == EP_LOSS) {
+          epi_loss();
+        } else {
+          epi_bdec0();
+        }
+      }
     }
+
 
     // loss partials: fixed-order tree inside the warp, one slot per (CTA, row quarter)
     if (h == 0) {
@@ -884,6 +1007,34 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         uint32_t v[16];
         tmem_ld16(lane_base + (uint32_t)(op.d_col + c * 16), v);
         tmem_ld_wait();
+        // layers stored [lane = output feature][column = input feature]: 16 consecutive floats of one row
+        float* rowp = nullptr;
+        int ncols = 16;
+        switch (op.kind) {
+          case WK_COND1: rowp = slab + lo.p_w[L_COND1] + ln * H + c * 16; break;
+          case WK_ENC0: rowp = slab + lo.p_w[L_ENC0] + ln * I + c * 16; ncols = min(16, I - c * 16); break;
+          case WK_ENC1: rowp = slab + lo.p_w[L_ENC1] + ln * H + c * 16; break;
+          case WK_ENC2: rowp = slab + lo.p_w[L_ENC2] + ln * H + c * 16; break;
+          case WK_ENC3: rowp = slab + lo.p_w[L_ENC3] + ln * H + c * 16; break;
+          case WK_DEC0_C: rowp = slab + lo.p_w[L_DEC0] + ln * (L + H) + L + c * 16; break;
+          case WK_DEC0_Z: rowp = slab + lo.p_w[L_DEC0] + ln * (L + H) + c * 16; ncols = min(16, L - c * 16); break;
+          case WK_DEC1: rowp = slab + lo.p_w[L_DEC1] + ln * H + c * 16; break;
+          case WK_DEC2: rowp = slab + lo.p_w[L_DEC2] + ln * H + c * 16; break;
+          default: break;
+        }
+        if (rowp != nullptr) {
+          if (ncols == 16 && (reinterpret_cast<uintptr_t>(rowp) & 15u) == 0) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+              reinterpret_cast<float4*>(rowp)[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                                __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < ncols) rowp[j] = __uint_as_float(v[j]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = c * 16 + j;
@@ -893,23 +1044,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
               if (col < 2) slab[lo.p_w[L_COND0] + ln * 2 + col] = val;
               else if (col == 2) slab[lo.p_b[L_COND0] + ln] = val;
               break;
-            case WK_COND1: slab[lo.p_w[L_COND1] + ln * H + col] = val; break;
-            case WK_ENC0: if (col < I) slab[lo.p_w[L_ENC0] + ln * I + col] = val; break;
-            case WK_ENC1: slab[lo.p_w[L_ENC1] + ln * H + col] = val; break;
-            case WK_ENC2: slab[lo.p_w[L_ENC2] + ln * H + col] = val; break;
-            case WK_ENC3: slab[lo.p_w[L_ENC3] + ln * H + col] = val; break;
-            case WK_DEC0_C: slab[lo.p_w[L_DEC0] + ln * (L + H) + L + col] = val; break;
-            case WK_DEC0_Z: if (col < L) slab[lo.p_w[L_DEC0] + ln * (L + H) + col] = val; break;
-            case WK_DEC1: slab[lo.p_w[L_DEC1] + ln * H + col] = val; break;
-            case WK_DEC2: slab[lo.p_w[L_DEC2] + ln * H + col] = val; break;
             case WK_HEADS_E:
-            case WK_HEADS_C: {
+            case WK_HEADS_C: {  // transposed: for one column the warp writes 32 consecutive floats
               const int koff = op.kind == WK_HEADS_C ? H : 0;
               if (col < L) slab[lo.p_w[L_HEADS] + col * (2 * H) + koff + ln] = val;
               else if (col < 2 * L) slab[lo.p_wlv + (col - L) * (2 * H) + koff + ln] = val;
               break;
             }
-            default:  // WK_DEC3
+            default:  // WK_DEC3, transposed
               if (col < I) slab[lo.p_w[L_DEC3] + col * H + ln] = val;
               break;
           }
@@ -987,7 +1129,7 @@ __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* _
     const float* src = slabs + (size_t)r.role_begin[role] * r.slab_stride + e;
     const int n = r.role_count[role];
     float s = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
     grads[e] = s;
     if (r.adam) {
@@ -1026,7 +1168,11 @@ __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* _
 // =========================================================================================
 // host side
 // =========================================================================================
-bool train_tc_supported(const Layout& lo) { return lo.Ip <= 64 && lo.L <= 32; }
+// the ones column sits in the last 8 extra columns: the widest small operand (NH) must stay below it
+bool train_tc_supported(const Layout& lo) { return lo.Ip <= 64 && lo.NH <= 32; }
+
+static long long* g_chain_trace = nullptr;
+void set_chain_trace(long long* p) { g_chain_trace = p; }
 
 TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
   TrainTcPlan p;
@@ -1062,6 +1208,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;
+  a.trace = g_chain_trace;
   cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.chain_smem);
   if (e != cudaSuccess) return e;
   chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(a);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "dmvae_set_decode_impl": (c_int, [c_int]),
     "dmvae_set_train_impl": (c_int, [c_int]),
     "dmvae_debug_decode_trace": (c_int, [_P]),
+    "dmvae_debug_train_trace": (c_int, [_P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),

@@ -106,6 +106,9 @@ int dmvae_set_decode_impl(int impl);
 /* Development aid: device buffer of 128 int64 that CTA 0 of decode_tc_kernel fills with
  * clock64 stamps per layer step (NULL = off, the default). */
 int dmvae_debug_decode_trace(void* device_int64x128);
+/* Same for chain_kernel (first tile of CTA 0): 256 int64; [4 o + 0 / 1] = MMA warp starts / has issued
+ * op o, [128 + 2 e + 0 / 1] = epilogue e starts (accumulator complete) / has released the A operand. */
+int dmvae_debug_train_trace(void* device_int64x256);
 
 /* model.condition_encoder(c) on its own (Training_VAE.py:132-137; called directly
  * at Tools.py:55, :898): start (B,2) -> h_c (B,128). */

@@ -1,0 +1,46 @@
+"""Development aid: per-op clock64 timeline of chain_kernel (CTA 0, first tile)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "defensive-model-vae_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+from dmvae import ConditionalTrajectoryVAE, _lib  # noqa: E402
+from dmvae.train import FusedTrainer  # noqa: E402
+
+OPS = ["cond0", "cond1", "heads_c", "enc0", "enc1", "enc2", "enc3", "heads_e", "dec0", "dec1", "dec2", "dec3",
+       "b_dec3", "b_dec2", "b_dec1", "b_dec0_c", "b_dec0_z", "b_heads_c", "b_cond1", "b_heads_e", "b_enc3", "b_enc2", "b_enc1"]
+EPI_OF_OP = {}
+e = 0
+for i, n in enumerate(OPS):
+    if n != "b_dec0_c":
+        EPI_OF_OP[i] = e
+        e += 1
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+lib = _lib.lib()
+torch.manual_seed(0)
+model = ConditionalTrajectoryVAE(10, 3, 8).to("cuda")
+tr = FusedTrainer(model, lr=1e-4)
+x = torch.randn(B, 10, 3, device="cuda").cumsum(1)
+for _ in range(3):
+    tr.step(x)
+buf = torch.zeros(256, dtype=torch.int64, device="cuda")
+lib.dmvae_debug_train_trace(_lib.ptr(buf))
+tr.step(x)
+torch.cuda.synchronize()
+lib.dmvae_debug_train_trace(None)
+t = buf.cpu().tolist()
+t0 = t[0]
+print(f"B={B}: per op [mma start -> issued] | [epilogue start -> released]  (cycles from first MMA start)")
+for i, n in enumerate(OPS):
+    ms, mi = t[4 * i] - t0, t[4 * i + 1] - t0
+    line = f"{n:10s} mma {ms:7d} -> {mi:7d} (+{mi - ms:5d})"
+    if i in EPI_OF_OP:
+        e = EPI_OF_OP[i]
+        es, er = t[128 + 2 * e] - t0, t[128 + 2 * e + 1] - t0
+        line += f" | epi {es:7d} (+{es - mi:5d} after issue) -> {er:7d} (+{er - es:5d})"
+    print(line)

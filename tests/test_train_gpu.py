@@ -1,11 +1,21 @@
 """GPU parity of the fused training kernels (through the C ABI) against the oracle
 and the reference-generated goldens.
 
+Every fused-pass test runs twice: with the tensor-core kernels (tcgen05, 3xTF32: chain_kernel +
+wgrad_kernel + reduce_tc_kernel; the default wherever 3*seq_len <= 64 and latent_dim <= 16) and with
+the FP32 FFMA kernels (train_kernel + reduce_kernel).
+
 Tolerances (fp32, summation order differs from ATen's):
-  per-step gradients   ||g - g_ref||_inf / ||g_ref||_inf <= 2e-5
-  loss terms           relative <= 2e-6 (+ tiny absolute for terms near zero)
-  Adam update          <= 2 ulp-ish: relative 1e-6 on the parameters
-  loss curve, 50 steps first 10 steps <= 1e-4 relative, all 50 <= 2e-2 (chaotic drift)
+                         FFMA kernels                     tensor cores (3xTF32)
+  per-step gradients     ||g - g_ref||_inf / ||g_ref||_inf <= 2e-5     <= 2e-4
+  loss terms             relative <= 2e-6                               <= 2e-4
+  loss curve, 50 steps   first 10 <= 1e-4, all 50 <= 2e-2               first 10 <= 1e-3, all 50 <= 2e-2
+  Adam update            relative 1e-6 on the parameters (same kernel arithmetic for both)
+The tensor-core accumulators round toward zero on every accumulate (measured on B200,
+scripts/umma_accuracy.cu): a 128-deep 3xTF32 product lands at 1.3e-6 of the row maximum against
+4.7e-7 for an fp32 FMA chain, and the bias is systematic, so it compounds through the ten layers of
+the forward / backward chain to ~3e-5 on the gradients in the harshest regime tested here (default
+initialisation on +-100 m start coordinates, KLD ~ 500).
 """
 import os
 
@@ -18,6 +28,18 @@ from oracle import vae_oracle as O
 pytestmark = pytest.mark.gpu
 GRAD_TOL = 2e-5
 LOSS_TOL = 2e-6
+TOL = {"ffma": dict(grad=2e-5, loss=2e-6, tensor=2e-4, curve10=1e-4, shards=5e-6),
+       "tc": dict(grad=2e-4, loss=2e-4, tensor=2e-3, curve10=1e-3, shards=5e-5)}
+
+
+@pytest.fixture(params=["tc", "ffma"])
+def impl(request):
+    """Selects the kernels behind the fused training pass for one test, then restores the default."""
+    from dmvae import _lib
+    lib = _lib.lib()
+    _lib.check(lib.dmvae_set_train_impl(0 if request.param == "tc" else 1), "dmvae_set_train_impl")
+    yield request.param
+    _lib.check(lib.dmvae_set_train_impl(0), "dmvae_set_train_impl")
 
 
 def rel_inf(a, b):
@@ -45,13 +67,13 @@ def synth_batch(B, T, seed, scale=50.0):
     return torch.cat([t[..., None], xy], -1).contiguous()
 
 
-def check_losses(got, ref):
+def check_losses(got, ref, tol=LOSS_TOL):
     got = [float(v) for v in got]
     scale = max(abs(float(r)) for r in ref)
     for g, r in zip(got, ref):
         # a term that is tiny next to the others (start_loss ~1e-3 vs kld ~10) is a sum of
         # squared cancellations: allow 1e-8 of the largest term in absolute
-        assert abs(g - r) <= LOSS_TOL * abs(r) + 1e-8 * scale + 1e-9, (got, ref)
+        assert abs(g - r) <= tol * abs(r) + 1e-8 * scale * (tol / LOSS_TOL) + 1e-9, (got, ref)
 
 
 def per_tensor_err(grads, grads_ref):
@@ -78,8 +100,9 @@ def per_tensor_err(grads, grads_ref):
     (42, 64, 70, O.SCRIPT_WEIGHTS),     # largest envelope: Ip = 128, L2p = 128
     (10, 5, 64, (0.3, 0.2, 0.0, 0.0)),  # odd latent (misaligned offsets), zero-weight terms
 ])
-def test_fused_fwd_bwd_vs_oracle(T, L, B, weights):
+def test_fused_fwd_bwd_vs_oracle(T, L, B, weights, impl):
     from dmvae.train import FusedTrainer
+    tol = TOL[impl]
     p = O.init_params(T, L, seed=7 + T + L)
     model = make_model(p, T, L)
     batch = synth_batch(B, T, seed=B)
@@ -88,16 +111,16 @@ def test_fused_fwd_bwd_vs_oracle(T, L, B, weights):
     losses_ref, grads_ref, _ = O.loss_and_grads(p, batch, eps, weights)
     tr = FusedTrainer(model, weights=weights)
     losses, grads = tr.loss_and_grads(batch.cuda(), eps=eps.cuda())
-    check_losses(losses.cpu(), losses_ref)
+    check_losses(losses.cpu(), losses_ref, tol["loss"])
     gnp = grads.cpu().numpy()
-    assert rel_inf(gnp, flat(grads_ref).numpy()) < GRAD_TOL
-    assert per_tensor_err(gnp, grads_ref) < 2e-4   # every tensor on its own scale
+    assert rel_inf(gnp, flat(grads_ref).numpy()) < tol["grad"]
+    assert per_tensor_err(gnp, grads_ref) < tol["tensor"]   # every tensor on its own scale
     # bit-reproducible: fixed-order reduction, no atomics
     losses2, grads2 = tr.loss_and_grads(batch.cuda(), eps=eps.cuda())
     assert torch.equal(grads2.cpu(), torch.from_numpy(gnp))
 
 
-def test_golden_sce1_first_step_and_curve(golden_dir):
+def test_golden_sce1_first_step_and_curve(golden_dir, impl):
     """Real sce1 data, seed-0 init, injected eps: gradients of step 0 against the
     reference's own, then 50 fused steps against the reference's loss history."""
     from dmvae.train import FusedTrainer
@@ -118,15 +141,15 @@ def test_golden_sce1_first_step_and_curve(golden_dir):
         ref = g[f"grad0/{k}"]
         part = mine[:4] if n >= 128 * 128 else mine
         scale = max(np.abs(ref).max(), 1e-30)
-        assert np.abs(part - ref).max() / scale < 2e-4, k
-        assert abs(mine.astype(np.float64).sum() - g[f"grad0_digest/{k}"][0]) <= 2e-4 * g[f"grad0_digest/{k}"][1] + 1e-12, k
+        assert np.abs(part - ref).max() / scale < TOL[impl]["tensor"], k
+        assert abs(mine.astype(np.float64).sum() - g[f"grad0_digest/{k}"][0]) <= TOL[impl]["tensor"] * g[f"grad0_digest/{k}"][1] + 1e-12, k
         off += n
     hist = np.zeros((50, 5))
     for s in range(50):
         hist[s] = tr.step(batch, eps=eps[s]).cpu().numpy()
     ref_hist = g["loss_hist"]
     rel = np.abs(hist[:, 0] - ref_hist[:, 0]) / np.abs(ref_hist[:, 0])
-    assert rel[:10].max() < 1e-4, rel[:10]
+    assert rel[:10].max() < TOL[impl]["curve10"], rel[:10]
     assert rel.max() < 2e-2, rel
     # parameters after 50 steps stay close to the reference's (digest = sum, abs-sum)
     sd = model.state_dict()
@@ -159,7 +182,7 @@ def test_adam_update_vs_oracle():
     assert rel_inf(model.generate(start, z=z).cpu().numpy(), O.generate(p, z, start).numpy()) < 1e-5
 
 
-def test_data_parallel_shards_sum_to_the_full_batch():
+def test_data_parallel_shards_sum_to_the_full_batch(impl):
     """Two 'ranks' with global-batch scaling: summed gradient buffers (what the SUM
     all-reduce produces) equal the single-rank result."""
     from dmvae.train import FusedTrainer
@@ -176,12 +199,12 @@ def test_data_parallel_shards_sum_to_the_full_batch():
         tr.loss_and_grads(batch[lo:hi].contiguous(), eps=eps[lo:hi].contiguous(), global_batch=B)
         acc += tr.grad_buf
     n = tr.n_params
-    assert rel_inf(acc[:n].cpu().numpy(), full[:n].cpu().numpy()) < 5e-6
+    assert rel_inf(acc[:n].cpu().numpy(), full[:n].cpu().numpy()) < TOL[impl]["shards"]
     # tail: recon/kld/start/time partial means add up; total = weighted sum
-    np.testing.assert_allclose(acc[n + 1:].cpu().numpy(), full[n + 1:].cpu().numpy(), rtol=5e-6)
+    np.testing.assert_allclose(acc[n + 1:].cpu().numpy(), full[n + 1:].cpu().numpy(), rtol=TOL[impl]["shards"])
 
 
-def test_philox_eps_is_shard_invariant_and_steps_differ():
+def test_philox_eps_is_shard_invariant_and_steps_differ(impl):
     from dmvae.train import FusedTrainer
     T, L, B = 10, 8, 512
     p = O.init_params(T, L, seed=3)
@@ -196,7 +219,7 @@ def test_philox_eps_is_shard_invariant_and_steps_differ():
     for lo, hi in ((0, 200), (200, B)):
         tr.loss_and_grads(batch[lo:hi].contiguous(), global_batch=B, sample_offset=lo)
         acc += tr.grad_buf
-    assert rel_inf(acc[: tr.n_params].cpu().numpy(), full[: tr.n_params].cpu().numpy()) < 5e-6
+    assert rel_inf(acc[: tr.n_params].cpu().numpy(), full[: tr.n_params].cpu().numpy()) < TOL[impl]["shards"]
     tr.t += 1                                                # next step -> different noise stream
     other = tr.loss_and_grads(batch)[1]
     assert not torch.equal(other, full[: tr.n_params])
