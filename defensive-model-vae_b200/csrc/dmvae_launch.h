@@ -56,8 +56,10 @@ struct TrainTcPlan {
   long long n_tiles;          // 128-row tiles
   int chain_grid, chain_stages;
   size_t chain_smem;
-  int wgrad_grid;             // = number of partial slabs
-  int role_begin[3], role_count[3];
+  int wgrad_grid;
+  int role_begin[3], role_count[3];    // CTAs of each role
+  int unit_tiles[3], unit_count[3], unit_begin[3];  // tiles per unit, units (= partial slabs) per role, first slab
+  int n_slabs;
   int slab_stride;
   size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials]
 };

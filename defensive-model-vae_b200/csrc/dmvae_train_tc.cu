@@ -837,10 +837,12 @@ __host__ __device__ inline int wgrad_role_cols(const Layout& lo, int role) {
 struct WgradArgs {
   Layout lo;
   const float* stash;
-  float* slabs;        // [grid][slab_stride]
+  float* slabs;        // [units of all roles][slab_stride]
   long long n_tiles;
   int slab_stride;
-  int role_end[WG_ROLES];  // CTA index ranges: role r owns [role_end[r-1], role_end[r])
+  int role_end[WG_ROLES];   // CTA index ranges: role r owns [role_end[r-1], role_end[r])
+  int unit_tiles[WG_ROLES]; // tiles accumulated in tensor memory before the accumulators are written out
+  int unit_begin[WG_ROLES]; // first slab of the role; unit u of role r writes slab unit_begin[r] + u
 };
 
 constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 /* ones (A side) */ + 1024 /* ones (B side) */ +
@@ -851,7 +853,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const Layout& lo = a.lo;
   float *ring, *ones_a, *ones_b;
   WOp* ops;
-  uint64_t *raw_full, *split_full, *empty, *d_done;
+  uint64_t *raw_full, *split_full, *empty, *d_done, *d_free;
   uint32_t* tmem_slot;
   {
     const uint32_t base = smem_u32(smem_dyn);
@@ -864,7 +866,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     split_full = raw_full + 8;
     empty = split_full + 8;
     d_done = empty + 8;
-    tmem_slot = reinterpret_cast<uint32_t*>(d_done + 1);
+    d_free = d_done + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(d_free + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int role = 0;
@@ -872,6 +875,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   const int role_begin = role == 0 ? 0 : a.role_end[role - 1];
   const int role_ctas = a.role_end[role] - role_begin;
   const int my_index = (int)blockIdx.x - role_begin;
+  // A unit = a run of consecutive tiles whose gradients are accumulated in tensor memory and then written to
+  // the unit's own partial slab: bounds the number of (round-toward-zero) accumulations per accumulator.
+  const long long ut = a.unit_tiles[role];
+  const long long n_units = (a.n_tiles + ut - 1) / ut;
 
   if (tid == 0) {
     for (int st = 0; st < WG_STAGES; ++st) {
@@ -880,6 +887,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
       mbar_init(&empty[st], 1);
     }
     mbar_init(d_done, 1);
+    mbar_init(d_free, WG_WORK_WARPS);
     mbar_fence_init();
     wgrad_program(lo, role, ops);
   }
@@ -903,7 +911,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   if (warp == WG_PRODUCER_WARP) {
     if (lane == 0) {
       RingStateRt rs(WG_STAGES);
-      for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas) {
+      for (long long unit = my_index; unit < n_units; unit += role_ctas)
+      for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile) {
         const float* ts = a.stash + (size_t)tile * lo.tile_stash;
         for (int o = 0; o < n_ops; ++o) {
           const WOp op = ops[o];
@@ -924,8 +933,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     }
   } else if (warp == WG_MMA_WARP) {
     RingStateRt rs(WG_STAGES);
-    bool first_tile = true;
-    for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas) {
+    uint32_t free_phase = 0;
+    for (long long unit = my_index; unit < n_units; unit += role_ctas) {
+     if (unit != my_index) {  // the previous unit's accumulators have been read out
+       mbar_wait(d_free, free_phase);
+       free_phase ^= 1u;
+       tc_fence_after();
+     }
+     bool first_tile = true;
+     for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile) {
       for (int o = 0; o < n_ops; ++o) {
         const WOp op = ops[o];
         const uint32_t idesc = umma_idesc_tf32(128, op.FB, UMMA_A_MN | UMMA_B_MN);
@@ -965,13 +981,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         }
       }
       first_tile = false;
+     }
+     if (elect_one()) umma_commit(d_done);
+     __syncwarp();
     }
-    if (elect_one()) umma_commit(d_done);
-    __syncwarp();
   } else {
     // ===================== work warps: TF32 split of the raw stages, then the final write-out ======
     RingStateRt rs(WG_STAGES);
-    for (long long tile = my_index; tile < a.n_tiles; tile += role_ctas)
+    uint32_t done_phase = 0;
+    for (long long unit = my_index; unit < n_units; unit += role_ctas) {
+    for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile)
       for (int o = 0; o < n_ops; ++o) {
         const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
         for (int c = 0; c < chunks; ++c) {
@@ -992,13 +1011,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         }
       }
 
-    // ---- write-out: accumulators -> this CTA's partial slab (torch layout of each tensor) ----------
-    mbar_wait(d_done, 0);
+    // ---- write-out: accumulators -> the unit's partial slab (torch layout of each tensor) ----------
+    mbar_wait(d_done, done_phase);
+    done_phase ^= 1u;
     tc_fence_after();
     const int q = warp & 3, hh = warp >> 2;
     const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float* slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+    float* slab = a.slabs + (size_t)(a.unit_begin[role] + unit) * a.slab_stride;
     const int L = lo.L, I = lo.I;
     for (int o = 0; o < n_ops; ++o) {
       const WOp op = ops[o];
@@ -1095,6 +1115,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         }
       }
     }
+    // accumulators read: the MMA warp may start the next unit
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(d_free);
+    }  // units
   }
 
   tc_fence_before();
@@ -1181,10 +1206,12 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
   p.chain_stages = 4;
   while (p.chain_stages > 2 && chain_smem_bytes(lo, p.chain_stages) > 232448) --p.chain_stages;
   p.chain_smem = chain_smem_bytes(lo, p.chain_stages);
-  // CTAs per role in proportion to the accumulator columns (= MMA time per tile), at most one per tile
+  // CTAs per role in proportion to the accumulator columns (= MMA time per tile), at most one per tile.
+  // Tiles are grouped into units of at most 4 (64 K steps: bounds the tensor-memory accumulation depth);
+  // every unit writes its own partial slab.
   int cols[WG_ROLES], total = 0;
   for (int r = 0; r < WG_ROLES; ++r) { cols[r] = wgrad_role_cols(lo, r); total += cols[r]; }
-  int used = 0;
+  int used = 0, slabs = 0;
   for (int r = 0; r < WG_ROLES; ++r) {
     long long n = (long long)sm_count * cols[r] / total;
     if (n < 1) n = 1;
@@ -1192,11 +1219,24 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
     p.role_count[r] = (int)n;
     p.role_begin[r] = used;
     used += (int)n;
+    // unit size 1..4 that minimises the busiest CTA: units go round-robin, a write-out costs ~0.4 tiles
+    int best_u = 1;
+    double best_cost = 1e30;
+    for (int u = 1; u <= 4; ++u) {
+      const long long units = (p.n_tiles + u - 1) / u;
+      const double cost = (double)((units + n - 1) / n) * (u + 0.4);
+      if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && u > best_u)) { best_cost = cost; best_u = u; }
+    }
+    p.unit_tiles[r] = best_u;
+    p.unit_count[r] = (int)((p.n_tiles + p.unit_tiles[r] - 1) / p.unit_tiles[r]);
+    p.unit_begin[r] = slabs;
+    slabs += p.unit_count[r];
   }
   p.wgrad_grid = used;
+  p.n_slabs = slabs;
   p.slab_stride = round_up(lo.n_params, 4);
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
-  p.slab_floats = (size_t)p.wgrad_grid * p.slab_stride;
+  p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
   p.loss_floats = (size_t)p.chain_grid * 16;
   return p;
 }
@@ -1209,8 +1249,12 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;
   a.trace = g_chain_trace;
-  cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.chain_smem);
-  if (e != cudaSuccess) return e;
+  static size_t attr_set = 0;   // the opt-in limit only ever needs to grow
+  if (plan.chain_smem > attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.chain_smem);
+    if (e != cudaSuccess) return e;
+    attr_set = plan.chain_smem;
+  }
   chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(a);
   return cudaGetLastError();
 }
@@ -1218,9 +1262,17 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream) {
   WgradArgs a;
   a.lo = lo; a.stash = stash; a.slabs = slabs; a.n_tiles = plan.n_tiles; a.slab_stride = plan.slab_stride;
-  for (int r = 0; r < WG_ROLES; ++r) a.role_end[r] = plan.role_begin[r] + plan.role_count[r];
-  cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
+  for (int r = 0; r < WG_ROLES; ++r) {
+    a.role_end[r] = plan.role_begin[r] + plan.role_count[r];
+    a.unit_tiles[r] = plan.unit_tiles[r];
+    a.unit_begin[r] = plan.unit_begin[r];
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
   return cudaGetLastError();
 }
@@ -1240,7 +1292,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
     r.tensor_end[2 * i + 1] = i < 11 ? w_off[i + 1] : lo.n_params;      // the bias ends where the next weight starts
     r.tensor_role[2 * i] = r.tensor_role[2 * i + 1] = role_of_pair[i];
   }
-  for (int k = 0; k < WG_ROLES; ++k) { r.role_begin[k] = plan.role_begin[k]; r.role_count[k] = plan.role_count[k]; }
+  for (int k = 0; k < WG_ROLES; ++k) { r.role_begin[k] = plan.unit_begin[k]; r.role_count[k] = plan.unit_count[k]; }
   r.n_params = lo.n_params; r.slab_stride = plan.slab_stride; r.chain_grid = plan.chain_grid;
   r.w_recon = w[0]; r.w_kld = w[1]; r.w_start = w[2]; r.w_time = w[3];
   r.adam = adam != nullptr ? 1 : 0;
