@@ -304,6 +304,8 @@ def run_cuda(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"    # the version banner would land on stdout next to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
@@ -344,10 +346,17 @@ def run_cuda(args):
     from dmvae.parallel import DataParallelTrainer
     dp = DataParallelTrainer(trainer)    # N > 1: fwd+bwd, ONE NCCL all-reduce of [grads | 5 losses], replicated Adam
 
+    # single GPU: the whole step is one CUDA graph (dmvae_train_step_dev: Adam step index in device memory);
+    # the batch of the step is copied device-to-device into the graph's input buffer
+    gstep = trainer.capture(B) if (world == 1 and not args.no_graph) else None
+
     def train_step(i):
         b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
-        if world == 1:
-            trainer.step(b, sample_offset=0)             # 3 launches: train_kernel, reduce+Adam, pack
+        if gstep is not None:
+            gstep.batch.copy_(b, non_blocking=True)
+            gstep.replay()                               # 4 kernels: chain, wgrad, reduce+Adam, pack
+        elif world == 1:
+            trainer.step(b, sample_offset=0)
         else:
             dp.step(b)
 
@@ -366,12 +375,21 @@ def run_cuda(args):
     barrier()
     t_mark1 = time.perf_counter()
     launches = lib.dmvae_launch_count(-1) - launches0
+    if gstep is not None:
+        launches += K * gstep.kernels        # kernels inside the replayed graphs (counted once, at capture)
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = K * Bg / (ms_total * 1e-3)
     losses_end = [float(v) for v in trainer.losses.cpu()]
 
     # ---------------------------------------------------------------- per-kernel live timing (separate pass)
-    prof = profile(lib, lambda i: train_step(W + K + i), min(K, 200))
+    def train_step_host(i):      # host-driven launches: the library brackets each kernel with an event pair
+        b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
+        if world == 1:
+            trainer.step(b, sample_offset=0)
+        else:
+            dp.step(b)
+
+    prof = profile(lib, lambda i: train_step_host(W + K + i), min(K, 200))
     n_steps_prof = max(max(v[1] for v in prof.values()), 1) if prof else 1
     step_kernel_ms = sum(v[0] for v in prof.values()) / n_steps_prof
     shares = {k: round(v[0] / max(sum(x[0] for x in prof.values()), 1e-12), 4) for k, v in prof.items()}
@@ -384,13 +402,13 @@ def run_cuda(args):
     # the FFMA kernels on the same workload, for the comparison north_star asks for
     _lib.check(lib.dmvae_set_train_impl(1), "dmvae_set_train_impl")
     for i in range(5):
-        train_step(i)
+        train_step_host(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Kf = max(10, min(K, 200))
     f0.record()
     for i in range(Kf):
-        train_step(i)
+        train_step_host(i)
     f1.record()
     barrier()
     ffma_value = Kf * Bg / (max_over_ranks(f0.elapsed_time(f1)) * 1e-3)
@@ -431,10 +449,16 @@ def run_cuda(args):
     host_losses = torch.empty(5, dtype=torch.float32).pin_memory()
     dbuf = torch.empty(B, T, 3, dtype=torch.float32, device=dev)
 
+    # single GPU: one graph per pinned host buffer = [H2D of the batch, fused step, D2H of the 5 loss terms]
+    e2e_graphs = [trainer.capture(B, host_batch=hb, host_losses=host_losses) for hb in host_batches] if gstep is not None else None
+
     def e2e_step(i, blocking=True):
-        dbuf.copy_(host_batches[i % 8], non_blocking=True)
-        losses = trainer.step(dbuf) if world == 1 else dp.step(dbuf)
-        host_losses.copy_(losses, non_blocking=True)
+        if e2e_graphs is not None:
+            e2e_graphs[i % 8].replay()
+        else:
+            dbuf.copy_(host_batches[i % 8], non_blocking=True)
+            losses = trainer.step(dbuf) if world == 1 else dp.step(dbuf)
+            host_losses.copy_(losses, non_blocking=True)
         if blocking:
             torch.cuda.current_stream().synchronize()
             return float(host_losses[0])
@@ -538,6 +562,7 @@ def run_cuda(args):
                                "transform + forward + 5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128",
                    "batch_per_gpu": B, "global_batch": Bg, "parallelism": f"dp{world}",
                    "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows,
+                   "launch": "one CUDA graph per step (device-side Adam step counter)" if gstep is not None else "host-driven launches",
                    "l2": f"each step reads a different batch of a {rows * T * 3 * 4 / 1e6:.0f} MB resident set (> 126 MB L2); "
                          "weights and the per-step stash / slabs are L2-resident by design",
                    "collective": "none" if world == 1 else "NCCL all-reduce SUM of 128947 fp32 per step"},
@@ -600,6 +625,7 @@ def main():
     ap.add_argument("--big-batch", type=int, default=1 << 16, help="rows per GPU of the large-batch throughput leg")
     ap.add_argument("--decode-rows", type=int, default=1 << 20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="host-driven steps instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

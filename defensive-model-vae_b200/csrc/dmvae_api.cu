@@ -241,7 +241,7 @@ int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B) {
 static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
                         uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
                         void* workspace, float* grads, const DmvaeAdam* adam, float* params, float* m, float* v,
-                        float* packed_rw, void* stream, const char* what) {
+                        float* packed_rw, void* stream, const char* what, long long* step_dev = nullptr) {
   dmvae::Layout lo;
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
@@ -255,11 +255,13 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   dmvae::TrainIO io;
   io.packed = packed; io.x = x; io.eps = eps;
-  io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.B = B;
+  io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.step_dev = step_dev; io.B = B;
   io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
   cudaError_t e;
-  if (g_train_impl.load() == 0 && dmvae::train_tc_supported(lo)) {
+  if (step_dev != nullptr && !dmvae::train_tc_supported(lo))
+    return fail(DMVAE_ERR_SHAPE, "%s: the device-side step counter needs the tensor-core path (3*seq_len <= 64, latent_dim <= 16)", what);
+  if ((g_train_impl.load() == 0 || step_dev != nullptr) && dmvae::train_tc_supported(lo)) {
     // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)
     const dmvae::TrainTcPlan tp = dmvae::plan_train_tc(lo, B, sms);
     float* stash = static_cast<float*>(workspace);
@@ -269,7 +271,7 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     if (e != cudaSuccess) return cuda_fail(e, what);
     e = PROF(dmvae::K_WGRAD, st, dmvae::launch_wgrad(lo, tp, stash, slabs, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
-    e = PROF(dmvae::K_REDUCE_TC, st, dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, st));
+    e = PROF(dmvae::K_REDUCE_TC, st, dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
   } else {
     const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, false);
@@ -282,10 +284,20 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     if (e != cudaSuccess) return cuda_fail(e, what);
   }
   if (adam && packed_rw) {
-    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed_rw, st));
+    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed_rw, st, step_dev));
     if (e != cudaSuccess) return cuda_fail(e, what);
   }
   return DMVAE_OK;
+}
+
+int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
+                         const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
+                         float inv_batch, int64_t B, const DmvaeAdam* adam, int64_t* step_dev, void* workspace,
+                         float* grads, void* stream) {
+  if (!adam || !step_dev) return fail(DMVAE_ERR_ARG, "train_step_dev: adam or step_dev is null");
+  if (!packed) return fail(DMVAE_ERR_ARG, "train_step_dev: packed is null");
+  return train_common(cfg, packed, x, eps, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, adam, params, m, v,
+                      packed, stream, "train_step_dev", reinterpret_cast<long long*>(step_dev));
 }
 
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,

@@ -7,7 +7,9 @@
 
 namespace dmvae {
 
-cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cudaStream_t stream);
+// step_inc: optional device counter incremented by the kernel (graph-capturable training step)
+cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cudaStream_t stream,
+                        long long* step_inc = nullptr);
 
 // mode: 0 per-row start, 1 shared start, 2 decode from a supplied h_c, 3 condition encoder only
 cudaError_t launch_decode(const Layout& lo, int mode, const float* packed, const float* z, uint64_t seed,
@@ -45,6 +47,7 @@ struct TrainIO {
   float* recon = nullptr; float* mu = nullptr; float* logvar = nullptr; float* hc = nullptr;
   const float* g_recon = nullptr; const float* g_mu = nullptr; const float* g_logvar = nullptr; const float* g_hc = nullptr;
   unsigned long long seed = 0, sample_offset = 0, step = 0;
+  const long long* step_dev = nullptr;  // tensor-core path: step index in device memory (graph-capturable)
   long long B = 0;
   float w_recon = 0.f, w_kld = 0.f, w_start = 0.f, w_time = 0.f, inv_batch = 0.f;
 };
@@ -71,7 +74,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream);
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
-                             cudaStream_t stream);
+                             const long long* step_dev, cudaStream_t stream);
 
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],

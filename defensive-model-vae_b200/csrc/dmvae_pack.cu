@@ -78,7 +78,9 @@ struct PackPlan {
 constexpr int PACK_THREADS = 256;
 
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(const __grid_constant__ Layout lo, const __grid_constant__ PackPlan plan,
-                                                            const float* __restrict__ p, float* __restrict__ q) {
+                                                            const float* __restrict__ p, float* __restrict__ q,
+                                                            long long* step_inc) {
+  if (step_inc != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_inc += 1;   // this launch completes update t + 1
   int sgm = 0;
   while (sgm + 1 < plan.n && (int)blockIdx.x >= plan.block0[sgm + 1]) ++sgm;
   const int idx = ((int)blockIdx.x - plan.block0[sgm]) * PACK_THREADS + (int)threadIdx.x;
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(const __grid_constan
   }
 }
 
-cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cudaStream_t stream) {
+cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cudaStream_t stream, long long* step_inc) {
   PackPlan plan;
   plan.n = 0;
   int blocks = 0;
@@ -161,7 +163,7 @@ cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cu
     if (lo.tc[t].off_thi >= 0) add(PS_TT, t, lo.tc[t].Kt * lo.tc[t].N);
   }
   plan.block0[plan.n] = blocks;
-  pack_kernel<<<blocks, PACK_THREADS, 0, stream>>>(lo, plan, params, packed);
+  pack_kernel<<<blocks, PACK_THREADS, 0, stream>>>(lo, plan, params, packed, step_inc);
   return cudaGetLastError();
 }
 

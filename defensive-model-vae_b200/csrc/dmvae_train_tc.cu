@@ -85,6 +85,7 @@ struct ChainArgs {
   float* stash;       // [n_tiles][tile_stash]
   float* loss_part;   // [grid][4 warps][4 terms]
   unsigned long long seed, sample_offset, step;
+  const long long* step_dev;   // when set: the step index is *step_dev + 1 (graph-capturable launches)
   long long B;
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
@@ -553,8 +554,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
               for (int i = 0; i < 4; ++i)
                 if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
             } else {
+              const unsigned long long step = a.step_dev != nullptr ? (unsigned long long)(*a.step_dev + 1) : a.step;
               const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
-                                              (uint32_t)(a.step + 1));
+                                              (uint32_t)(step + 1));
               e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
             }
           }
@@ -1141,12 +1143,26 @@ struct ReduceTcArgs {
   float w_recon, w_kld, w_start, w_time;
   AdamScalarsTc h;
   int adam;
+  // graph-capturable launches: the scalars that depend on the step index are derived in the kernel from
+  // *step_dev + 1 (double arithmetic, as the host path and torch's Python floats)
+  const long long* step_dev;
+  double lr, beta1, beta2;
 };
 
 __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* __restrict__ loss_part,
                                  const __grid_constant__ ReduceTcArgs r, float* __restrict__ grads, float* __restrict__ p,
                                  float* __restrict__ m, float* __restrict__ v) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ AdamScalarsTc hs;
+  if (threadIdx.x == 0) {
+    hs = r.h;
+    if (r.adam && r.step_dev != nullptr) {
+      const double step = (double)(*r.step_dev + 1);
+      hs.step_size = (float)(r.lr / (1.0 - pow(r.beta1, step)));
+      hs.bc2_sqrt = (float)sqrt(1.0 - pow(r.beta2, step));
+    }
+  }
+  __syncthreads();
   if (e < r.n_params) {
     int t = 0;
     while (t < 23 && e >= r.tensor_end[t]) ++t;
@@ -1160,10 +1176,10 @@ __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* _
     if (r.adam) {
       // torch optim/adam.py::_single_tensor_adam (see dmvae_adam.cu)
       float pp = p[e], mm = m[e], vv = v[e];
-      mm = r.h.w1 < 0.5f ? fmaf(r.h.w1, s - mm, mm) : s - (s - mm) * (1.f - r.h.w1);
-      vv = fmaf(r.h.w2 * s, s, vv * r.h.b2);
-      const float denom = sqrtf(vv) / r.h.bc2_sqrt + r.h.eps;
-      pp = pp - r.h.step_size * (mm / denom);
+      mm = hs.w1 < 0.5f ? fmaf(hs.w1, s - mm, mm) : s - (s - mm) * (1.f - hs.w1);
+      vv = fmaf(hs.w2 * s, s, vv * hs.b2);
+      const float denom = sqrtf(vv) / hs.bc2_sqrt + hs.eps;
+      pp = pp - hs.step_size * (mm / denom);
       p[e] = pp; m[e] = mm; v[e] = vv;
     }
   }
@@ -1248,6 +1264,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;
+  a.step_dev = io.step_dev;
   a.trace = g_chain_trace;
   static size_t attr_set = 0;   // the opt-in limit only ever needs to grow
   if (plan.chain_smem > attr_set) {
@@ -1279,7 +1296,7 @@ cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float*
 
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
-                             cudaStream_t stream) {
+                             const long long* step_dev, cudaStream_t stream) {
   ReduceTcArgs r;
   // state_dict order: cond0 (w,b) cond1 enc0 enc1 enc2 enc3 fc_mu fc_logvar dec0 dec1 dec2 dec3
   static const int role_of_pair[12] = {0, 0, 1, 0, 0, 1, 2, 2, 2, 1, 1, 2};
@@ -1297,6 +1314,8 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
   r.w_recon = w[0]; r.w_kld = w[1]; r.w_start = w[2]; r.w_time = w[3];
   r.adam = adam != nullptr ? 1 : 0;
   r.h = AdamScalarsTc{};
+  r.step_dev = step_dev;
+  r.lr = adam != nullptr ? adam->lr : 0.0; r.beta1 = adam != nullptr ? adam->beta1 : 0.0; r.beta2 = adam != nullptr ? adam->beta2 : 0.0;
   if (adam != nullptr) {
     const double b1 = adam->beta1, b2 = adam->beta2;
     const double bc1 = 1.0 - pow(b1, (double)adam->step), bc2 = 1.0 - pow(b2, (double)adam->step);

@@ -25,9 +25,10 @@ class FusedTrainer:
     """Owns the Adam state (flat m, v, step), the gradient buffer and the kernel
     workspace for a ``ConditionalTrajectoryVAE``.
 
-    ``step(batch)``              single-GPU fused step (3 launches)
+    ``step(batch)``              single-GPU fused step (4 launches)
     ``loss_and_grads(batch)``    fused forward+loss+backward only -> (losses, grads)
     ``apply(grads)``             Adam + repack from an (all-reduced) gradient buffer
+    ``capture(B, ...)``          the whole step as one CUDA graph (``GraphStep``): no per-step host work
     """
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
@@ -47,6 +48,8 @@ class FusedTrainer:
         self.m = torch.zeros_like(arena)
         self.v = torch.zeros_like(arena)
         self.grad_buf = torch.zeros(n, dtype=torch.float32, device=self.device)   # grads + 5 loss terms
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)     # device copy of ``t`` (GraphStep)
+        self._dev_t = 0                                                            # what step_dev is known to hold
         self._ws = {}
         self._cfg_ref = byref(self.cfg)
         self._w_ref = byref(self.weights)
@@ -84,6 +87,18 @@ class FusedTrainer:
         if tuple(eps.shape) != (B, self.model.latent_dim):
             raise ValueError(f"eps must be (B, {self.model.latent_dim})")
         return eps
+
+    def sync_step_counter(self) -> None:
+        """Device copy of the Adam step count := the host's (after host-driven steps)."""
+        if self._dev_t != self.t:
+            self.step_dev.fill_(self.t)
+            self._dev_t = self.t
+
+    def capture(self, B: int, host_batch: Optional[torch.Tensor] = None, host_losses: Optional[torch.Tensor] = None,
+                sample_offset: int = 0) -> "GraphStep":
+        """The whole step for batch size ``B`` as one CUDA graph (host-driven ``step()`` / ``apply()`` calls may
+        be mixed in: ``replay()`` re-synchronises the device-side step counter when needed)."""
+        return GraphStep(self, B, host_batch, host_losses, sample_offset)
 
     # ------------------------------------------------------------------ passes
     def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
@@ -137,6 +152,72 @@ class FusedTrainer:
                                             byref(h), ptr(ws), ptr(self.grad_buf), stream_ptr()), "dmvae_train_step")
         self.model.mark_packed_current()
         return self.losses
+
+
+class GraphStep:
+    """One training step captured as a CUDA graph: optional H2D copy of the batch from a pinned host
+    buffer, the fused step (``dmvae_train_step_dev``: chain, weight gradients, reduction + Adam, repack;
+    the Adam step index lives in device memory so that nothing in the graph depends on the step), optional
+    D2H copy of the five loss terms into a pinned host buffer.  ``replay()`` is one graph launch."""
+
+    def __init__(self, trainer: "FusedTrainer", B: int, host_batch: Optional[torch.Tensor] = None,
+                 host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0):
+        model = trainer.model
+        self.trainer = trainer
+        self.B = int(B)
+        dev = trainer.device
+        self.batch = torch.empty(B, model.seq_len, 3, dtype=torch.float32, device=dev)   # static input buffer
+        self.host_batch, self.host_losses = host_batch, host_losses
+        if host_batch is not None and (not host_batch.is_pinned() or tuple(host_batch.shape) != tuple(self.batch.shape)):
+            raise ValueError("host_batch must be a pinned (B, T, 3) fp32 tensor")
+        arena = model.flat_parameters()
+        packed = model.packed_weights()
+        ws = trainer._workspace(B)
+        self._keep = (arena, packed, ws)
+        hyper = DmvaeAdam(trainer.lr, trainer.betas[0], trainer.betas[1], trainer.eps, 0)
+        self._hyper = hyper
+        lib = trainer.lib
+
+        def launch():
+            if host_batch is not None:
+                self.batch.copy_(host_batch, non_blocking=True)
+            check(lib.dmvae_train_step_dev(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
+                                           ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
+                                           ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(1.0 / B), B,
+                                           byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
+                                           stream_ptr()), "dmvae_train_step_dev")
+            if host_losses is not None:
+                host_losses.copy_(trainer.losses, non_blocking=True)
+
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(dev):
+            trainer.sync_step_counter()
+            torch.cuda.current_stream().synchronize()
+            saved = (arena.clone(), trainer.m.clone(), trainer.v.clone(), trainer.step_dev.clone())
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):        # warm-up launch outside the capture (lazy module loading, attributes)
+                launch()
+            torch.cuda.current_stream().wait_stream(s)
+            n0 = lib.dmvae_launch_count(-1)
+            with torch.cuda.graph(self.graph):
+                launch()
+            self.kernels = int(lib.dmvae_launch_count(-1) - n0)   # libdmvae kernels launched by one replay
+            # the warm-up applied one update: restore the state it changed
+            arena.copy_(saved[0]); trainer.m.copy_(saved[1]); trainer.v.copy_(saved[2]); trainer.step_dev.copy_(saved[3])
+            check(lib.dmvae_pack_weights(trainer._cfg_ref, ptr(arena), ptr(packed), stream_ptr()), "dmvae_pack_weights")
+            model.mark_packed_current()
+
+    def replay(self) -> torch.Tensor:
+        """Runs the captured step on the current contents of ``batch`` (or ``host_batch``); returns the five
+        loss terms (device view, no sync)."""
+        tr = self.trainer
+        tr.sync_step_counter()
+        self.graph.replay()
+        tr.t += 1
+        tr._dev_t = tr.t
+        tr.model.mark_packed_current()
+        return tr.losses
 
 
 class LossMeter:

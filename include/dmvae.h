@@ -152,6 +152,16 @@ int dmvae_train_step(const DmvaeCfg* cfg, float* params, float* packed, float* m
                      const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                      const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
                      void* workspace, float* grads, void* stream);
+/* dmvae_train_step with the Adam step index in device memory, so that every launch parameter is
+ * step-independent and the whole call can be captured in a CUDA graph and replayed (no per-step host
+ * work: Training_VAE.py:351-363 as one graph launch).  *step_dev = number of updates applied so far;
+ * the call applies update *step_dev + 1 (adam->step is ignored; the bias corrections are derived on the
+ * device in double) and its last kernel increments the counter.  The Philox stream of the step is
+ * *step_dev + 2, as in dmvae_train_step.  Tensor-core path only: DMVAE_ERR_SHAPE outside its envelope. */
+int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
+                         const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
+                         const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
+                         int64_t* step_dev, void* workspace, float* grads, void* stream);
 /* optimizer.step() of torch.optim.Adam (Training_VAE.py:363; torch
  * optim/adam.py::_single_tensor_adam): updates params, m, v in place from
  * grads (dmvae_param_count floats each) and refreshes `packed` (may be NULL).

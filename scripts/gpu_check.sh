@@ -10,13 +10,15 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "bench ref rc=$?"
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 tail -c 3000 gpurun_out/${tag}_bench.json
-SMALL="python bench.py --steps 6 --warmup 3 --no-cpu --dataset-rows 65536 --decode-rows 262144"
+SMALL="python bench.py --steps 6 --warmup 3 --no-cpu --dataset-rows 131072 --big-batch 65536 --decode-rows 262144"
 $SMALL > gpurun_out/${tag}_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu list rc=$?"
 $SMALL > gpurun_out/${tag}_small2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:train_kernel -s 5 -c 2 -f -o gpurun_out/${tag}_prof_train $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
-echo "ncu full train rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 4 -c 2 -f -o gpurun_out/${tag}_prof_decode $SMALL > gpurun_out/${tag}_ncu3.log 2>&1
-echo "ncu full decode rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_prof_chain $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
+echo "ncu full chain rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_prof_wgrad $SMALL > gpurun_out/${tag}_ncu3.log 2>&1
+echo "ncu full wgrad rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:decode_tc_kernel -s 4 -c 1 -f -o gpurun_out/${tag}_prof_decode_tc $SMALL > gpurun_out/${tag}_ncu4.log 2>&1
+echo "ncu full decode_tc rc=$?"
 ls -la gpurun_out

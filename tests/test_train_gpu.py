@@ -308,3 +308,34 @@ def test_zero_weight_terms_are_python_zero():
                                start_weight=0.0, time_weight=0.0)
     assert out[3] == 0 and out[4] == 0 and isinstance(out[3], int)   # Training_VAE.py:246,:255
     assert abs(out[0].item() - 0.1) < 1e-6                            # 0.1 * mse(=1) + 0.1 * kld(=0)
+
+
+def test_graph_step_matches_host_driven_steps():
+    """The CUDA-graph step (device-side Adam step counter, dmvae_train_step_dev) against the host-driven
+    dmvae_train_step on the same batches and Philox streams: same kernels, the bias corrections computed
+    on the device in double instead of on the host."""
+    from dmvae.train import FusedTrainer
+    T, L, B = 10, 8, 700
+    p = O.init_params(T, L, seed=11)
+    batches = [synth_batch(B, T, seed=40 + i).cuda() for i in range(4)]
+    ma, mb = make_model(p, T, L), make_model(p, T, L)
+    ta, tb = FusedTrainer(ma, lr=1e-3, seed=5), FusedTrainer(mb, lr=1e-3, seed=5)
+    host_losses = torch.zeros(5).pin_memory()
+    gs = tb.capture(B, host_losses=host_losses)
+    assert rel_inf(mb.flat_parameters().cpu().numpy(), flat(p).numpy()) == 0.0   # capture leaves the state untouched
+    for i, b in enumerate(batches):
+        la = ta.step(b).clone()
+        if i == 2:                       # a host-driven step in between: the counter is re-synchronised
+            lb = tb.step(b).clone()
+        else:
+            gs.batch.copy_(b)
+            lb = gs.replay().clone()
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(host_losses.numpy(), lb.cpu().numpy(), rtol=0, atol=0)
+        np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-6)
+        assert rel_inf(mb.flat_parameters().cpu().numpy(), ma.flat_parameters().cpu().numpy()) < 1e-6, i
+    assert ta.t == tb.t == 4 and int(tb.step_dev.item()) == 4
+    # generation sees the weights the graph updated
+    z = torch.randn(32, L, generator=torch.Generator().manual_seed(1))
+    st = torch.rand(32, 2) * 10
+    assert rel_inf(mb.generate(st, z=z).cpu().numpy(), ma.generate(st, z=z).cpu().numpy()) < 1e-5
