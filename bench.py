@@ -348,7 +348,12 @@ def run_cuda(args):
 
     # single GPU: the whole step is one CUDA graph (dmvae_train_step_dev: Adam step index in device memory);
     # the batch of the step is copied device-to-device into the graph's input buffer
-    gstep = trainer.capture(B) if (world == 1 and not args.no_graph) else None
+    if args.no_graph:
+        gstep = None
+    elif world == 1:
+        gstep = trainer.capture(B)
+    else:
+        gstep = dp.capture(B)     # + the NCCL all-reduce of [grads | losses], captured in the same graph
 
     def train_step(i):
         b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
@@ -450,7 +455,10 @@ def run_cuda(args):
     dbuf = torch.empty(B, T, 3, dtype=torch.float32, device=dev)
 
     # single GPU: one graph per pinned host buffer = [H2D of the batch, fused step, D2H of the 5 loss terms]
-    e2e_graphs = [trainer.capture(B, host_batch=hb, host_losses=host_losses) for hb in host_batches] if gstep is not None else None
+    e2e_graphs = None
+    if gstep is not None:
+        e2e_graphs = [(trainer.capture(B, host_batch=hb, host_losses=host_losses) if world == 1 else
+                       dp.capture(B, host_batch=hb, host_losses=host_losses)) for hb in host_batches]
 
     def e2e_step(i, blocking=True):
         if e2e_graphs is not None:
@@ -533,9 +541,17 @@ def run_cuda(args):
     peak_ffma = ffma_peak_tflops(lib)
     clk = clocks.stop(t_mark0, time.perf_counter()) if clocks is not None else None
 
-    if rank != 0:
+    def leave():
+        """Exit of a multi-rank job: the step graphs hold captured NCCL work and tearing the communicator
+        down under them can block, so the ranks meet once more and leave without destroying the group."""
         if world > 1:
-            dist.destroy_process_group()
+            barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     # ---------------------------------------------------------------- CPU baseline beside it (rank 0, N = 1 only)
@@ -562,7 +578,8 @@ def run_cuda(args):
                                "transform + forward + 5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128",
                    "batch_per_gpu": B, "global_batch": Bg, "parallelism": f"dp{world}",
                    "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows,
-                   "launch": "one CUDA graph per step (device-side Adam step counter)" if gstep is not None else "host-driven launches",
+                   "launch": ("one CUDA graph per step (device-side Adam step counter" +
+                              ("; the NCCL all-reduce is captured in it)" if world > 1 else ")")) if gstep is not None else "host-driven launches",
                    "l2": f"each step reads a different batch of a {rows * T * 3 * 4 / 1e6:.0f} MB resident set (> 126 MB L2); "
                          "weights and the per-step stash / slabs are L2-resident by design",
                    "collective": "none" if world == 1 else "NCCL all-reduce SUM of 128947 fp32 per step"},
@@ -610,8 +627,7 @@ def run_cuda(args):
         },
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():

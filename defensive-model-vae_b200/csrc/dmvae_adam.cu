@@ -93,8 +93,22 @@ __global__ void reduce_kernel(const float* __restrict__ slabs, int n_slabs, int 
   }
 }
 
+// step_dev != null: the step-dependent scalars are derived from *step_dev + 1 on the device (double
+// arithmetic), so that the launch can be captured in a CUDA graph (dmvae_adam_step_dev).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int n, AdamScalars h) {
+                            float* __restrict__ v, int n, AdamScalars h0, const long long* __restrict__ step_dev, double lr,
+                            double beta1, double beta2) {
+  __shared__ AdamScalars hs;
+  if (threadIdx.x == 0) {
+    hs = h0;
+    if (step_dev != nullptr) {
+      const double step = (double)(*step_dev + 1);
+      hs.step_size = (float)(lr / (1.0 - pow(beta1, step)));
+      hs.bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+    }
+  }
+  __syncthreads();
+  const AdamScalars h = hs;
   const int n4 = n >> 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
@@ -144,11 +158,14 @@ cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int
 }
 
 cudaError_t launch_adam(const Layout& lo, float* p, const float* g, float* m, float* v, const DmvaeAdam& a,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const long long* step_dev) {
   const int n = lo.n_params;
   const int threads = 256;
   const int work = (n >> 2) + (n & 3);
-  adam_kernel<<<(work + threads - 1) / threads, threads, 0, stream>>>(p, g, m, v, n, make_scalars(a));
+  DmvaeAdam a1 = a;
+  if (step_dev != nullptr) a1.step = 1;   // placeholder: the kernel derives the real scalars from the device counter
+  adam_kernel<<<(work + threads - 1) / threads, threads, 0, stream>>>(p, g, m, v, n, make_scalars(a1), step_dev, a.lr,
+                                                                      a.beta1, a.beta2);
   return cudaGetLastError();
 }
 

@@ -315,23 +315,43 @@ int dmvae_train_step(const DmvaeCfg* cfg, float* params, float* packed, float* m
                       adam, params, m, v, packed, stream, "train_step");
 }
 
-int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v, const DmvaeAdam* adam,
-                    float* packed, void* stream) {
+static int adam_common(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v, const DmvaeAdam* adam,
+                       long long* step_dev, float* packed, void* stream, const char* what) {
   dmvae::Layout lo;
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
   if (!params || !grads || !m || !v || !adam || !aligned16(params) || !aligned16(grads) || !aligned16(m) || !aligned16(v))
-    return fail(DMVAE_ERR_ARG, "adam_step: null or misaligned pointer");
-  if (adam->step < 1) return fail(DMVAE_ERR_ARG, "adam_step: step must be >= 1");
+    return fail(DMVAE_ERR_ARG, "%s: null or misaligned pointer", what);
+  if (!step_dev && adam->step < 1) return fail(DMVAE_ERR_ARG, "%s: step must be >= 1", what);
   if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = PROF(dmvae::K_ADAM, st, dmvae::launch_adam(lo, params, grads, m, v, *adam, st));
-  if (e != cudaSuccess) return cuda_fail(e, "adam_step");
+  cudaError_t e = PROF(dmvae::K_ADAM, st, dmvae::launch_adam(lo, params, grads, m, v, *adam, st, step_dev));
+  if (e != cudaSuccess) return cuda_fail(e, what);
   if (packed) {
-    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed, st));
-    if (e != cudaSuccess) return cuda_fail(e, "adam_step(pack)");
+    e = PROF(dmvae::K_PACK, st, dmvae::launch_pack(lo, params, packed, st, step_dev));
+    if (e != cudaSuccess) return cuda_fail(e, what);
   }
   return DMVAE_OK;
+}
+
+int dmvae_adam_step(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v, const DmvaeAdam* adam,
+                    float* packed, void* stream) {
+  return adam_common(cfg, params, grads, m, v, adam, nullptr, packed, stream, "adam_step");
+}
+
+int dmvae_adam_step_dev(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v, const DmvaeAdam* adam,
+                        int64_t* step_dev, float* packed, void* stream) {
+  if (!step_dev || !packed) return fail(DMVAE_ERR_ARG, "adam_step_dev: step_dev and packed are required");
+  return adam_common(cfg, params, grads, m, v, adam, reinterpret_cast<long long*>(step_dev), packed, stream, "adam_step_dev");
+}
+
+int dmvae_train_fwd_bwd_dev(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
+                            uint64_t sample_offset, const int64_t* step_dev, const DmvaeLossWeights* w, float inv_batch,
+                            int64_t B, void* workspace, float* grads, void* stream) {
+  if (!step_dev) return fail(DMVAE_ERR_ARG, "train_fwd_bwd_dev: step_dev is null");
+  return train_common(cfg, packed, x, eps, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, stream, "train_fwd_bwd_dev",
+                      const_cast<long long*>(reinterpret_cast<const long long*>(step_dev)));
 }
 
 int dmvae_forward(const DmvaeCfg* cfg, const float* packed, const float* x_rel, const float* start, const float* eps,

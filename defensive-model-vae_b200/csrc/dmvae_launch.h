@@ -80,7 +80,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],
                           float* grads, const DmvaeAdam* adam, float* p, float* m, float* v, cudaStream_t stream);
 cudaError_t launch_adam(const Layout& lo, float* p, const float* g, float* m, float* v, const DmvaeAdam& a,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const long long* step_dev = nullptr);
 
 cudaError_t launch_loss(const Layout& lo, long long B, const float* recon, const float* x, const float* mu,
                         const float* logvar, const float w[4], float* losses, cudaStream_t stream);

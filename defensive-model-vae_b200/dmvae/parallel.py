@@ -99,6 +99,21 @@ class DataParallelTrainer:
         self.engine.apply()
         return self.engine.grad_buf[self.engine.n_params:]
 
+    def capture(self, local_rows: int, host_batch=None, host_losses=None):
+        """The whole data-parallel step for ``local_rows`` rows per rank as one CUDA graph on every rank:
+        fused forward+loss+backward, the SUM all-reduce of [gradients | losses] (NCCL, captured), Adam,
+        repack (engine = ``FusedTrainer``; equal shards).  Returns the engine's ``GraphStep``."""
+        B, offset = self.global_batch_layout(int(local_rows), True)
+        reduce_fn = None
+        if self.world > 1:
+            def reduce_fn(t):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            def reduce_fn(t):
+                return None
+        return self.engine.capture(int(local_rows), host_batch=host_batch, host_losses=host_losses, sample_offset=offset,
+                                   all_reduce=reduce_fn, global_batch=B)
+
     def parameter_checksum(self, flat_params: torch.Tensor) -> bool:
         """True when every rank holds bit-identical parameters (compares the exact
         int64 sum of the raw fp32 bit patterns, a checksum of the replicas)."""

@@ -95,10 +95,10 @@ class FusedTrainer:
             self._dev_t = self.t
 
     def capture(self, B: int, host_batch: Optional[torch.Tensor] = None, host_losses: Optional[torch.Tensor] = None,
-                sample_offset: int = 0) -> "GraphStep":
+                sample_offset: int = 0, all_reduce=None, global_batch: Optional[int] = None) -> "GraphStep":
         """The whole step for batch size ``B`` as one CUDA graph (host-driven ``step()`` / ``apply()`` calls may
         be mixed in: ``replay()`` re-synchronises the device-side step counter when needed)."""
-        return GraphStep(self, B, host_batch, host_losses, sample_offset)
+        return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch)
 
     # ------------------------------------------------------------------ passes
     def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
@@ -161,7 +161,11 @@ class GraphStep:
     D2H copy of the five loss terms into a pinned host buffer.  ``replay()`` is one graph launch."""
 
     def __init__(self, trainer: "FusedTrainer", B: int, host_batch: Optional[torch.Tensor] = None,
-                 host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0):
+                 host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0,
+                 all_reduce=None, global_batch: Optional[int] = None):
+        """``all_reduce``: data-parallel ranks pass a callable that SUM-all-reduces a tensor in place (captured
+        in the graph between the fused pass and the Adam update) and ``global_batch`` / ``sample_offset`` =
+        the global batch size and this rank's row offset."""
         model = trainer.model
         self.trainer = trainer
         self.B = int(B)
@@ -177,15 +181,26 @@ class GraphStep:
         hyper = DmvaeAdam(trainer.lr, trainer.betas[0], trainer.betas[1], trainer.eps, 0)
         self._hyper = hyper
         lib = trainer.lib
+        inv = 1.0 / float(global_batch if global_batch is not None else B)
 
         def launch():
             if host_batch is not None:
                 self.batch.copy_(host_batch, non_blocking=True)
-            check(lib.dmvae_train_step_dev(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
-                                           ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
-                                           ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(1.0 / B), B,
-                                           byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
-                                           stream_ptr()), "dmvae_train_step_dev")
+            if all_reduce is None:
+                check(lib.dmvae_train_step_dev(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
+                                               ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
+                                               ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,
+                                               byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
+                                               stream_ptr()), "dmvae_train_step_dev")
+            else:
+                check(lib.dmvae_train_fwd_bwd_dev(trainer._cfg_ref, ptr(packed), ptr(self.batch), None,
+                                                  ctypes.c_uint64(trainer.seed), ctypes.c_uint64(sample_offset),
+                                                  ptr(trainer.step_dev), trainer._w_ref, ctypes.c_float(inv), B, ptr(ws),
+                                                  ptr(trainer.grad_buf), stream_ptr()), "dmvae_train_fwd_bwd_dev")
+                all_reduce(trainer.grad_buf)
+                check(lib.dmvae_adam_step_dev(trainer._cfg_ref, ptr(arena), ptr(trainer.grad_buf), ptr(trainer.m),
+                                              ptr(trainer.v), byref(hyper), ptr(trainer.step_dev), ptr(packed),
+                                              stream_ptr()), "dmvae_adam_step_dev")
             if host_losses is not None:
                 host_losses.copy_(trainer.losses, non_blocking=True)
 

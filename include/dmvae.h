@@ -162,6 +162,16 @@ int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, floa
                          const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                          const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
                          int64_t* step_dev, void* workspace, float* grads, void* stream);
+/* The two halves of the data-parallel step in the same graph-capturable form: forward + loss + backward
+ * with the Philox stream taken from *step_dev + 2 (the counter is only read), and the Adam update for
+ * step *step_dev + 1 followed by the repack, whose kernel increments the counter.  Between them the
+ * caller all-reduces `grads` (NCCL collectives can be captured in the same graph). */
+int dmvae_train_fwd_bwd_dev(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps,
+                            uint64_t seed, uint64_t sample_offset, const int64_t* step_dev,
+                            const DmvaeLossWeights* w, float inv_batch, int64_t B, void* workspace,
+                            float* grads, void* stream);
+int dmvae_adam_step_dev(const DmvaeCfg* cfg, float* params, const float* grads, float* m, float* v,
+                        const DmvaeAdam* adam, int64_t* step_dev, float* packed, void* stream);
 /* optimizer.step() of torch.optim.Adam (Training_VAE.py:363; torch
  * optim/adam.py::_single_tensor_adam): updates params, m, v in place from
  * grads (dmvae_param_count floats each) and refreshes `packed` (may be NULL).

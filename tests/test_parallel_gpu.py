@@ -116,3 +116,46 @@ def test_nccl_data_parallel_matches_single_gpu(tmp_path):
     model.flat_parameters().copy_(got["params"].cuda())
     _, _, whole = generate_shard(model, [[11.0, 0.0]], 50_001, seed=3, rank=0, world=1)
     assert np.array_equal(np.load(os.path.join(tmp_path, "gen.npy")), whole.cpu().numpy())
+
+
+def _nccl_graph_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from dmvae.parallel import DataParallelTrainer, init_distributed, shard_range
+    from dmvae.train import FusedTrainer
+    init_distributed("nccl")
+    B, steps = 2048, 4
+    batches = [_batch(B, 20 + s) for s in range(steps)]
+    lo, hi = shard_range(B, rank, world)
+    # host-driven data-parallel steps (Philox noise, keyed by the global row index) ...
+    model_a, _ = _model(seed=6)
+    dpa = DataParallelTrainer(FusedTrainer(model_a, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77))
+    ha = [dpa.step(b[lo:hi].cuda()).cpu().clone() for b in batches]
+    # ... against the same steps replayed from one CUDA graph (all-reduce captured inside)
+    model_b, _ = _model(seed=6)
+    dpb = DataParallelTrainer(FusedTrainer(model_b, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77))
+    gs = dpb.capture(hi - lo)
+    hb = []
+    for b in batches:
+        gs.batch.copy_(b[lo:hi])
+        hb.append(gs.replay().cpu().clone())
+    assert dpb.parameter_checksum(model_b.flat_parameters())
+    np.testing.assert_allclose(torch.stack(hb).numpy(), torch.stack(ha).numpy(), rtol=1e-6)
+    pa, pb = model_a.flat_parameters().cpu(), model_b.flat_parameters().cpu()
+    assert (pa - pb).abs().max().item() <= 1e-6 * pa.abs().max().item()
+    if rank == 0:
+        open(os.path.join(tmp, "ok"), "w").write("ok")
+    # the graph holds captured NCCL work: release it before the communicator goes away
+    gs.graph.reset()
+    del gs
+    torch.cuda.synchronize()
+    dist.barrier()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_nccl_graph_step_matches_host_driven_step(tmp_path):
+    port = _free_port()
+    mp.spawn(_nccl_graph_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.isfile(os.path.join(tmp_path, "ok"))
