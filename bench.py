@@ -64,6 +64,25 @@ SCENARIOS = (
 SCENARIO_DEFAULT_START = ((-193.3, 50.0), (-155.0, -5.0), (155.0, -15.0), (11.0, 0.0))  # Tools.py:101-108
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line (driver contract): everything else that native libraries print
+    there (NCCL's version banner, for one) is sent to stderr for the life of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def flops_per_unit():
     I = 3 * T
     cond = 2 * H + H * H
@@ -254,7 +273,7 @@ def run_reference(args):
                    "sample": f"{dec_n} x {1 << 18} rows, shared start, host randn + cond-encoder + decoder + offset add"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------- CUDA arm
@@ -626,7 +645,7 @@ def run_cuda(args):
             "cpu_baseline": dec_cpu_obj,
         },
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     leave()
 
 
@@ -643,6 +662,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="host-driven steps instead of the CUDA-graph step")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -71,7 +71,7 @@ int layout_or_fail(const DmvaeCfg* cfg, dmvae::Layout* lo) {
     if (!cfg) return fail(DMVAE_ERR_ARG, "cfg is null");
     return fail(DMVAE_ERR_SHAPE,
                 "unsupported configuration seq_len=%d dim=%d latent_dim=%d hidden_dim=%d "
-                "(need dim=3, hidden_dim=128, 1<=latent_dim<=64, 2<=seq_len, 3*seq_len<=128)",
+                "(need dim=3, hidden_dim=128, 1<=latent_dim<=64, 2<=seq_len<=400)",
                 cfg->seq_len, cfg->dim, cfg->latent_dim, cfg->hidden_dim);
   }
   return DMVAE_OK;

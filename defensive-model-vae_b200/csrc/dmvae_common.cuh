@@ -79,7 +79,9 @@ __host__ __device__ constexpr int round_up(int a, int b) { return (a + b - 1) / 
 // (Training_VAE.py:193).  dec0 rows [0,L) multiply z, [L,L+128) h_c (:214).
 struct Layout {
   int T, L, I;      // seq_len, latent_dim, 3*seq_len
-  int Ip;           // I padded: 32, 64 or 128
+  int Ip;           // I padded: 32, 64 or 128; for I > 128 the width of one chunk of the flattened trajectory (128)
+  int NC;           // chunks of 128 features the first encoder / last decoder layer is cut into (1 unless I > 128)
+  int Ipt;          // NC * Ip: padded total width of the flattened trajectory
   int L2p;          // 2L padded: 32, 64 or 128
   int n_params;
   int n_packed;
@@ -116,10 +118,12 @@ __host__ __device__ inline int pad_width(int n) { return n <= 32 ? 32 : (n <= 64
 inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   if (!c || c->dim != 3 || c->hidden_dim != H) return DMVAE_ERR_SHAPE;
   if (c->latent_dim < 1 || c->latent_dim > 64) return DMVAE_ERR_SHAPE;
-  if (c->seq_len < 2 || c->seq_len * 3 > 128) return DMVAE_ERR_SHAPE;
+  if (c->seq_len < 2 || c->seq_len > 400) return DMVAE_ERR_SHAPE;
   Layout& l = *lo;
   l.T = c->seq_len; l.L = c->latent_dim; l.I = 3 * l.T;
-  l.Ip = pad_width(l.I); l.L2p = pad_width(2 * l.L);
+  l.Ip = pad_width(l.I < 128 ? l.I : 128); l.L2p = pad_width(2 * l.L);
+  l.NC = (l.I + 127) / 128;
+  l.Ipt = l.NC * l.Ip;
   const int Ks[NUM_LAYERS] = {2, H, l.I, H, H, H, 2 * H, l.L + H, H, H, H};
   const int Ns[NUM_LAYERS] = {H, H, H, H, H, H, 2 * l.L, H, H, H, l.I};
   int p = 0, q = 0;
@@ -135,8 +139,10 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
       l.p_w[i] = p; p += Ns[i] * Ks[i];
       l.p_b[i] = p; p += Ns[i];
     }
-    l.q_w[i] = q; q += round_up(Ks[i] * l.Np[i], 4);
-    l.q_b[i] = q; q += l.Np[i];
+    // dec3 with I > 128: one [k][128] image per chunk of 128 outputs, then the bias of all chunks
+    const int np_total = (i == L_DEC3) ? l.Ipt : l.Np[i];
+    l.q_w[i] = q; q += round_up(Ks[i] * np_total, 4);
+    l.q_b[i] = q; q += np_total;
   }
   l.n_params = p;
   q = round_up(q, 4);
@@ -164,6 +170,10 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   for (int t = 0; t < NUM_TC; ++t) {
     TcLayer& c = l.tc[t];
     c.K = H; c.N = H;
+    if (l.NC > 1) {  // the tensor-core kernels cover I <= 128 only: no images
+      c.K = 0; c.Kb = 0; c.N = 16; c.kps = 32; c.off_hi = c.off_lo = q; c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
+      continue;
+    }
     if (t == TC_COND0) c.K = 8;
     else if (t == TC_ENC0) c.K = l.Ip;
     else if (t == TC_HEADS) { c.K = 2 * H; c.N = l.NH; }

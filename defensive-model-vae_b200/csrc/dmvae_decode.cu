@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_c
         if (!shared_start) produce(pk + lo.q_w[L_DEC0] + L * H, H, H, ring, full, empty, rs);
         produce(pk + lo.q_w[L_DEC1], H, H, ring, full, empty, rs);
         produce(pk + lo.q_w[L_DEC2], H, H, ring, full, empty, rs);
-        produce(pk + lo.q_w[L_DEC3], H, NP3, ring, full, empty, rs);
+        for (int c = 0; c < lo.NC; ++c)   // trajectories longer than 128 floats: one image per chunk of 128 outputs
+          produce(pk + lo.q_w[L_DEC3] + (size_t)c * H * NP3, H, NP3, ring, full, empty, rs);
       }
     }
     return;
@@ -237,14 +238,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_c
       store_relu<CM>(acc, act, DEC_LD, pk + lo.q_b[l], warp, lane);
       consumer_sync();
     }
-    // dec3: 128 -> 3T, no activation, + start on the x / y columns, straight to HBM
-    {
+    // dec3: 128 -> 3T, no activation, + start on the x / y columns, straight to HBM; 128 output
+    // columns per pass (one pass unless 3T > 128)
+    for (int c = 0; c < lo.NC; ++c) {
       float o[C3::TI][C3::TJ];
       zero_acc<C3>(o);
       consume<C3>(o, act, DEC_LD, H, NP3, ring, full, empty, rs, warp, lane);
       if (C3::active(warp)) {
         const int i0 = C3::i0(warp, lane), j0 = C3::j0(warp, lane);
-        const float* __restrict__ b3 = pk + lo.q_b[L_DEC3];
+        const float* __restrict__ b3 = pk + lo.q_b[L_DEC3] + c * NP3;
 #pragma unroll
         for (int gi = 0; gi < C3::GI; ++gi)
 #pragma unroll
@@ -258,9 +260,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_c
             for (int gj = 0; gj < C3::GJ; ++gj)
 #pragma unroll
               for (int v = 0; v < C3::VJ; ++v) {
-                const int n = j0 + gj * C3::SJ + v;
+                const int nl = j0 + gj * C3::SJ + v;
+                const int n = c * NP3 + nl;
                 if (n >= I) continue;
-                float val = o[4 * gi + r][gj * C3::VJ + v] + b3[n];
+                float val = o[4 * gi + r][gj * C3::VJ + v] + b3[nl];
                 if (a.add_start) {
                   const int d = n % 3;
                   if (d == 1) val = sx + val;
@@ -270,6 +273,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) decode_kernel(const __grid_c
               }
           }
       }
+    }
+    {
       consumer_sync();  // act / zt / st are rewritten by the next tile
     }
   }

@@ -450,6 +450,7 @@ void set_decode_tc_trace(long long* p) { g_tc_trace = p; }
 
 // false when the configuration needs more spare A columns than tensor memory has
 bool decode_tc_supported(const Layout& lo, bool shared_start) {
+  if (lo.NC > 1) return false;   // trajectories longer than 128 floats decode on the FFMA kernel
   return shared_start ? lo.Lp8 <= 64 : lo.Lp8 + 8 <= 64;
 }
 

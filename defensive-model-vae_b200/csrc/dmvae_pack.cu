@@ -88,6 +88,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(const __grid_constan
   const int l = plan.id[sgm];
   switch (plan.type[sgm]) {
     case PS_FW: {
+      if (l == L_DEC3 && lo.NC > 1) {  // [chunk of 128 outputs][k][128]
+        const int c = idx / (H * 128), r = idx - c * (H * 128);
+        q[lo.q_w[l] + idx] = fwd_weight(lo, p, l, r / 128, c * 128 + (r % 128));
+        break;
+      }
       const int Np = lo.Np[l];
       q[lo.q_w[l] + idx] = fwd_weight(lo, p, l, idx / Np, idx % Np);
       break;
@@ -151,14 +156,14 @@ cudaError_t launch_pack(const Layout& lo, const float* params, float* packed, cu
     ++plan.n;
   };
   for (int l = 0; l < NUM_LAYERS; ++l) {
-    add(PS_FW, l, lo.K[l] * lo.Np[l]);
-    add(PS_FB, l, lo.Np[l]);
+    add(PS_FW, l, lo.K[l] * (l == L_DEC3 ? lo.Ipt : lo.Np[l]));
+    add(PS_FB, l, l == L_DEC3 ? lo.Ipt : lo.Np[l]);
     if (lo.r_w[l] < 0) continue;
     if (l == L_HEADS) add(PS_RW_HEADS, l, 2 * lo.L * 2 * H);
     else if (l == L_DEC0) { add(PS_RW_DEC0C, l, H * H); add(PS_RW_DEC0Z, l, H * lo.Lzp); }
     else add(PS_RW, l, lo.N[l] * lo.K[l]);
   }
-  for (int t = 0; t < NUM_TC; ++t) {
+  for (int t = 0; t < NUM_TC && lo.NC == 1; ++t) {
     add(PS_TC, t, lo.tc[t].Kb * lo.tc[t].N);
     if (lo.tc[t].off_thi >= 0) add(PS_TT, t, lo.tc[t].Kt * lo.tc[t].N);
   }

@@ -17,6 +17,13 @@
 //             result is masked by relu' and written over the layer input in place.
 // The slabs are summed in a fixed order by reduce_kernel (dmvae_adam.cu), so a step is
 // bit-reproducible run to run.
+//
+// Trajectories longer than 128 floats (3 * seq_len > 128, up to seq_len = 400): the first encoder layer
+// contracts over the flattened trajectory and the last decoder layer produces it, 128 features at a time.
+// x_rel and recon / d(total)/d(recon) then live feature-major in the CTA's stash (L2) instead of shared
+// memory: the encoder accumulates over chunks of x_rel, the decoder writes recon chunk by chunk, the loss
+// walks the stash (one thread per row, coalesced across rows), and the backward pass of those two layers
+// loops over the same chunks.
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
 
@@ -57,6 +64,9 @@ __host__ __device__ inline SmallRows small_rows(const Layout& lo) {
   r.total = o;
   return r;
 }
+
+// floats of the long-trajectory areas of a stash unit: x_rel [Ipt][M], then recon / gradient [Ipt][M]
+__host__ __device__ inline size_t long_floats(const Layout& lo, int M) { return lo.NC > 1 ? (size_t)lo.Ipt * M : 0; }
 
 template <int M>
 __host__ __device__ inline size_t train_smem_bytes(const Layout& lo, int stages) {
@@ -362,16 +372,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
     if (lane == 0) {
       RingStateRt rs(a.stages);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (do_fwd)
-          for (int id = 0; id < N_FWD_OPS; ++id) {
-            const Op op = op_desc(lo, id);
+        // long trajectories: enc0 / dec3 are walked in chunks of 128 features (consumer side: same order)
+        for (int id = do_fwd ? 0 : N_FWD_OPS; id < (do_bwd ? N_OPS : N_FWD_OPS); ++id) {
+          const Op op = op_desc(lo, id);
+          if (lo.NC > 1 && (id == OP_F_ENC0 || id == OP_F_DEC3 || id == OP_B_DEC3)) {
+            for (int c = 0; c < lo.NC; ++c) {
+              const int kc = min(128, lo.I - c * 128);
+              if (id == OP_F_DEC3) produce(pk + op.off + (size_t)c * H * 128, H, 128, s.ring, s.full, s.empty, rs);
+              else produce(pk + op.off + (size_t)c * 128 * H, kc, H, s.ring, s.full, s.empty, rs);
+            }
+          } else {
             produce(pk + op.off, op.rows, op.width, s.ring, s.full, s.empty, rs);
           }
-        if (do_bwd)
-          for (int id = N_FWD_OPS; id < N_OPS; ++id) {
-            const Op op = op_desc(lo, id);
-            produce(pk + op.off, op.rows, op.width, s.ring, s.full, s.empty, rs);
-          }
+        }
       }
     }
     return;
@@ -394,6 +407,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
     const int valid = (int)min((long long)M, a.B - m0);
     float* stash = a.stash + (size_t)(a.mode == TM_FUSED ? (long long)blockIdx.x : tile) * a.stash_stride;
     float* stash_small = stash + (size_t)N_STASH * H * M;
+    const bool chunked = lo.NC > 1;
+    float* XR = stash_small + (size_t)sr.total * LD;      // long trajectories: x_rel [Ipt][M]
+    float* RG = XR + long_floats(lo, M);                   //                    recon, then its gradient [Ipt][M]
+    // chunk c of a feature-major stash area -> shared tile [128][LD] (rows past the chunk are zero)
+    auto load_chunk = [&](float* tile, const float* area, int c) {
+      const int kc = min(128, I - c * 128);
+      for (int idx = tid; idx < 128 * M; idx += CONSUMER_THREADS) {
+        const int n = idx / M, m = idx - n * M;
+        tile[n * LD + m] = n < kc ? area[(size_t)(c * 128 + n) * M + m] : 0.f;
+      }
+    };
 
     if (do_fwd) {
       // ---- stage x (relative), start, eps ------------------------------------------------
@@ -409,7 +433,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
             else if (d == 2) v = v - __ldg(row + 2);
           }
         }
-        s.XT[n * LD + m] = v;
+        if (chunked) XR[(size_t)n * M + m] = v;
+        else s.XT[n * LD + m] = v;
       }
       for (int idx = tid; idx < 2 * M; idx += CONSUMER_THREADS) {
         const int d = idx / M, m = idx - d * M;
@@ -451,7 +476,16 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
       consumer_sync();
       // enc0: XT -> R0 (e1)
       zero_acc<CM>(acc);
-      DMVAE_CONSUME(CM, acc, s.XT, OP_F_ENC0);
+      if (!chunked) {
+        DMVAE_CONSUME(CM, acc, s.XT, OP_F_ENC0);
+      } else {
+        for (int c = 0; c < lo.NC; ++c) {
+          load_chunk(s.XT, XR, c);
+          consumer_sync();
+          consume<CM>(acc, s.XT, LD, min(128, I - c * 128), H, s.ring, s.full, s.empty, rs, warp, lane);
+          consumer_sync();  // XT is restaged by the next chunk
+        }
+      }
       store_fwd<CM, M, true>(acc, s.R0, pk + lo.q_b[L_ENC0], stash + S_E1 * H * M, H, warp, lane);
       consumer_sync();
       // enc1: R0 -> R1 (e2)
@@ -498,6 +532,21 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
       store_fwd<CM, M, true>(acc, s.R0, pk + lo.q_b[L_DEC2], stash + S_D3 * H * M, H, warp, lane);
       consumer_sync();
       // dec3: R0 -> GT (recon), no activation; padding rows come out as exact zeros
+      if (chunked) {
+        for (int c = 0; c < lo.NC; ++c) {
+          const int kc = min(128, I - c * 128);
+          float o3[CM::TI][CM::TJ];
+          zero_acc<CM>(o3);
+          consume<CM>(o3, s.R0, LD, H, 128, s.ring, s.full, s.empty, rs, warp, lane);
+          store_fwd<CM, M, false>(o3, s.GT, pk + lo.q_b[L_DEC3] + c * 128, nullptr, 128, warp, lane);
+          consumer_sync();
+          for (int idx = tid; idx < kc * M; idx += CONSUMER_THREADS) {
+            const int n = idx / M, m = idx - n * M;
+            RG[(size_t)(c * 128 + n) * M + m] = s.GT[n * LD + m];
+          }
+          consumer_sync();  // GT is rewritten by the next chunk
+        }
+      } else
       if (lo.Ip == 32) fwd_small_layer<M, 32>(lo, s, rs, s.R0, OP_F_DEC3, nullptr, 0, s.GT, pk + lo.q_b[L_DEC3], lo.Ip, warp, lane);
       else if (lo.Ip == 64) fwd_small_layer<M, 64>(lo, s, rs, s.R0, OP_F_DEC3, nullptr, 0, s.GT, pk + lo.q_b[L_DEC3], lo.Ip, warp, lane);
       else fwd_small_layer<M, 128>(lo, s, rs, s.R0, OP_F_DEC3, nullptr, 0, s.GT, pk + lo.q_b[L_DEC3], lo.Ip, warp, lane);
@@ -507,7 +556,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
         // outputs of model.forward (Training_VAE.py:226), row-major, + the small tiles for backward
         for (int idx = tid; idx < M * I; idx += CONSUMER_THREADS) {
           const int m = idx / I, n = idx - m * I;
-          if (m < valid) a.recon[(m0 + m) * I + n] = s.GT[n * LD + m];
+          if (m < valid) a.recon[(m0 + m) * I + n] = chunked ? RG[(size_t)n * M + m] : s.GT[n * LD + m];
         }
         for (int idx = tid; idx < M * L; idx += CONSUMER_THREADS) {
           const int m = idx / L, j = idx - m * L;
@@ -528,6 +577,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
       // ---- loss (Training_VAE.py:229-268) and d(total)/d(recon), one thread per row -----------
       {
         float p_rec = 0.f, p_kld = 0.f, p_start = 0.f, p_time = 0.f;
+        // recon (then its gradient) and x_rel, feature-major: shared tiles, or the stash areas for long trajectories
+        float* Gp = chunked ? RG : s.GT;
+        const float* Xp = chunked ? XR : s.XT;
+        const int gld = chunked ? M : LD;
         if (tid < M && tid < valid) {
           const int m = tid;
           const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
@@ -538,7 +591,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
           float g_prev = 0.f, r_prev = 0.f;
           for (int t = 0; t < T; ++t) {
             {
-              const float r = s.GT[(3 * t) * LD + m], x = s.XT[(3 * t) * LD + m];
+              const float r = Gp[(size_t)(3 * t) * gld + m], x = Xp[(size_t)(3 * t) * gld + m];
               const float diff = r - x;
               s_rec = fmaf(diff, diff, s_rec);
               float g = c_rec * diff;
@@ -552,7 +605,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
                   g -= c_mono;
                   g_prev += c_mono;
                 }
-                s.GT[(3 * (t - 1)) * LD + m] = g_prev;
+                Gp[(size_t)(3 * (t - 1)) * gld + m] = g_prev;
               }
               g_prev = g;
               r_prev = r;
@@ -560,7 +613,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
 #pragma unroll
             for (int d = 1; d < 3; ++d) {
               const int n = 3 * t + d;
-              const float r = s.GT[n * LD + m], x = s.XT[n * LD + m];
+              const float r = Gp[(size_t)n * gld + m], x = Xp[(size_t)n * gld + m];
               const float diff = r - x;
               s_rec = fmaf(diff, diff, s_rec);
               float g = c_rec * diff;
@@ -568,10 +621,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
                 s_start = fmaf(diff, diff, s_start);
                 g = fmaf(c_start, diff, g);
               }
-              s.GT[n * LD + m] = g;
+              Gp[(size_t)n * gld + m] = g;
             }
           }
-          s.GT[(3 * (T - 1)) * LD + m] = g_prev;
+          Gp[(size_t)(3 * (T - 1)) * gld + m] = g_prev;
           float s_k = 0.f;
           for (int j = 0; j < L; ++j) {
             const float mu = s.ML[j * LD + m], lv = s.ML[(L + j) * LD + m];
@@ -582,7 +635,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
           p_start = s_start * (a.inv_batch * 0.5f);
           p_time = s_t0 * a.inv_batch + (T > 1 ? s_mono * (a.inv_batch / (float)(T - 1)) : 0.f);
         } else if (tid < M) {
-          for (int n = 0; n < I; ++n) s.GT[n * LD + tid] = 0.f;  // rows past the batch end carry no gradient
+          for (int n = 0; n < I; ++n) Gp[(size_t)n * gld + tid] = 0.f;  // rows past the batch end carry no gradient
         }
         if (warp < (M + 31) / 32) {
 #pragma unroll
@@ -612,9 +665,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
       consumer_sync();
       for (int idx = tid; idx < M * I; idx += CONSUMER_THREADS) {
         const int m = idx / I, n = idx - m * I;
-        s.GT[n * LD + m] = (a.g_recon != nullptr && m < valid) ? __ldg(a.g_recon + (m0 + m) * I + n) : 0.f;
+        const float g = (a.g_recon != nullptr && m < valid) ? __ldg(a.g_recon + (m0 + m) * I + n) : 0.f;
+        if (chunked) RG[(size_t)n * M + m] = g;
+        else s.GT[n * LD + m] = g;
       }
-      for (int idx = tid; idx < (lo.Ip - I) * LD; idx += CONSUMER_THREADS) s.GT[I * LD + idx] = 0.f;
+      if (!chunked)
+        for (int idx = tid; idx < (lo.Ip - I) * LD; idx += CONSUMER_THREADS) s.GT[I * LD + idx] = 0.f;
       load_tile_async<M>(s.R0, stash + S_D3 * H * M, tid);
       load_tile_async<M>(s.R1, stash + S_D2 * H * M, tid);
       cp_async_wait<0>();
@@ -624,10 +680,24 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
     float acc[CM::TI][CM::TJ];
     // ---- dec3: delta = GT (I rows), input d3 = R0 ------------------------------------------------
     load_tile_async<M>(s.R2, stash + S_D1 * H * M, tid);  // prefetch d1 (R2 = hc is reloaded later)
-    wgrad_any<M>(s.R0, H, H, 128, s.GT, I, lo.Ip, lo.Ip, plain_dst(slab + lo.p_w[L_DEC3], H), first, warp, lane);
-    bias_grad<M>(s.GT, I, plain_dst(slab + lo.p_b[L_DEC3], 1), first, warp, lane);
     zero_acc<CM>(acc);
-    DMVAE_CONSUME(CM, acc, s.GT, OP_B_DEC3);
+    if (!chunked) {
+      wgrad_any<M>(s.R0, H, H, 128, s.GT, I, lo.Ip, lo.Ip, plain_dst(slab + lo.p_w[L_DEC3], H), first, warp, lane);
+      bias_grad<M>(s.GT, I, plain_dst(slab + lo.p_b[L_DEC3], 1), first, warp, lane);
+      DMVAE_CONSUME(CM, acc, s.GT, OP_B_DEC3);
+    } else {
+      consumer_sync();  // the loss pass (or the upstream-gradient copy) has finished writing the stash area
+      for (int c = 0; c < lo.NC; ++c) {
+        const int kc = min(128, I - c * 128);
+        load_chunk(s.GT, RG, c);
+        consumer_sync();
+        wgrad_any<M>(s.R0, H, H, 128, s.GT, kc, 128, 128, plain_dst(slab + lo.p_w[L_DEC3] + (size_t)c * 128 * H, H), first,
+                     warp, lane);
+        bias_grad<M>(s.GT, kc, plain_dst(slab + lo.p_b[L_DEC3] + c * 128, 1), first, warp, lane);
+        consume<CM>(acc, s.GT, LD, kc, H, s.ring, s.full, s.empty, rs, warp, lane);
+        consumer_sync();  // GT is reloaded by the next chunk
+      }
+    }
     consumer_sync();
     store_dgrad<CM, M, EPI_MASK>(acc, s.R0, H, warp, lane);
     consumer_sync();
@@ -772,7 +842,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1) train_kernel(const __grid_co
     store_dgrad<CM, M, EPI_MASK>(acc, s.R2, H, warp, lane);
     consumer_sync();
     // ---- enc0: delta = R2, input x_rel = XT (no data gradient) ------------------------------------
-    wgrad_any<M>(s.XT, I, lo.Ip, lo.Ip, s.R2, H, H, 128, plain_dst(slab + lo.p_w[L_ENC0], I), first, warp, lane);
+    if (!chunked) {
+      wgrad_any<M>(s.XT, I, lo.Ip, lo.Ip, s.R2, H, H, 128, plain_dst(slab + lo.p_w[L_ENC0], I), first, warp, lane);
+    } else {
+      for (int c = 0; c < lo.NC; ++c) {
+        load_chunk(s.XT, XR, c);
+        consumer_sync();
+        wgrad_any<M>(s.XT, min(128, I - c * 128), 128, 128, s.R2, H, H, 128, plain_dst(slab + lo.p_w[L_ENC0] + c * 128, I),
+                     first, warp, lane);
+        consumer_sync();  // XT is reloaded by the next chunk
+      }
+    }
     bias_grad<M>(s.R2, H, plain_dst(slab + lo.p_b[L_ENC0], 1), first, warp, lane);
     consumer_sync();  // the next tile restages XT / ST / EP and rewrites R0..R2
     first = false;
@@ -812,7 +892,7 @@ TrainPlan plan_train(const Layout& lo, long long B, int sm_count, bool per_tile_
   p.grid = (int)(p.n_tiles < sm_count ? p.n_tiles : sm_count);
   if (p.grid < 1) p.grid = 1;
   const SmallRows sr = small_rows(lo);
-  p.stash_stride = round_up(N_STASH * H * p.M + sr.total * (p.M + 4), 4);
+  p.stash_stride = round_up(N_STASH * H * p.M + sr.total * (p.M + 4) + 2 * (int)long_floats(lo, p.M), 4);
   p.stash_units = per_tile_stash ? p.n_tiles : p.grid;
   p.slab_stride = round_up(lo.n_params + 4, 4);
   p.smem = p.M == 64 ? train_smem_bytes<64>(lo, p.stages) : train_smem_bytes<32>(lo, p.stages);

@@ -1210,7 +1210,7 @@ __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* _
 // host side
 // =========================================================================================
 // the ones column sits in the last 8 extra columns: the widest small operand (NH) must stay below it
-bool train_tc_supported(const Layout& lo) { return lo.Ip <= 64 && lo.NH <= 32; }
+bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && lo.NH <= 32; }
 
 static long long* g_chain_trace = nullptr;
 void set_chain_trace(long long* p) { g_chain_trace = p; }

@@ -30,7 +30,7 @@ from ._lib import byref, check, ptr, stream_ptr
 
 HIDDEN = 128
 MAX_LATENT = 64
-MAX_FLAT = 128  # 3 * seq_len, this ABI version
+MAX_SEQ = 400   # seq_len; beyond 3 * seq_len = 128 the first / last layers run in chunks on the FFMA kernels
 
 
 def _envelope(seq_len: int, dim: int, latent_dim: int, hidden_dim: int) -> None:
@@ -42,8 +42,8 @@ def _envelope(seq_len: int, dim: int, latent_dim: int, hidden_dim: int) -> None:
         raise NotImplementedError(f"hidden_dim={hidden_dim}: kernels are specialised for hidden_dim=128")
     if not (1 <= latent_dim <= MAX_LATENT):
         raise NotImplementedError(f"latent_dim={latent_dim}: supported range is 1..{MAX_LATENT}")
-    if seq_len < 2 or seq_len * dim > MAX_FLAT:
-        raise NotImplementedError(f"seq_len={seq_len}: supported range is 2..{MAX_FLAT // 3} in this version")
+    if seq_len < 2 or seq_len > MAX_SEQ:
+        raise NotImplementedError(f"seq_len={seq_len}: supported range is 2..{MAX_SEQ}")
 
 
 class _KernelBackedSequential(nn.Sequential):

@@ -21,7 +21,9 @@
  *     DMVAE_ERR_DEVICE.  There is no CPU path.
  *
  * Shape envelope: dim == 3, hidden_dim == 128,
- * 1 <= latent_dim <= 64, 2 <= seq_len with 3*seq_len <= 128 in this ABI version.
+ * 1 <= latent_dim <= 64, 2 <= seq_len <= 400.  Inside it the tensor-core kernels cover
+ * 3*seq_len <= 128 (generation) and 3*seq_len <= 64, latent_dim <= 16 (training); the rest runs on the
+ * FP32 FFMA kernels behind the same entry points.
  */
 #ifndef DMVAE_H_
 #define DMVAE_H_
@@ -141,7 +143,7 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
 int64_t dmvae_grad_count(const DmvaeCfg* cfg);
 int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
 /* Which kernels the fused training pass launches: 0 (default) = tensor cores (tcgen05, 3xTF32:
- * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 32,
+ * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 16,
  * the FFMA kernels otherwise; 1 = always the FP32 FFMA kernels (train_kernel + reduce_kernel).
  * Both hold the tolerances of tests/test_train_gpu.py; dmvae_train_workspace_bytes covers both. */
 int dmvae_set_train_impl(int impl);

@@ -69,7 +69,8 @@ def test_condition_encoder_and_decode_submodule_api(golden_dir):
 
 @pytest.mark.parametrize("T,L,B", [(10, 8, 1), (10, 8, 127), (10, 8, 128), (10, 8, 129), (10, 8, 5000),
                                    (12, 8, 300), (2, 1, 77), (21, 16, 513), (32, 32, 260), (42, 64, 1000),
-                                   (10, 5, 333), (7, 3, 64)])
+                                   (10, 5, 333), (7, 3, 64),
+                                   (43, 8, 100), (50, 8, 300), (100, 16, 257), (400, 64, 130)])
 def test_decode_vs_oracle_seeded_weights(T, L, B):
     p = O.init_params(T, L, seed=100 + T + L)
     m = model_from_params(p, T, L)

@@ -99,6 +99,10 @@ def per_tensor_err(grads, grads_ref):
     (30, 24, 100, O.SCRIPT_WEIGHTS),    # Ip = 128 (90), L2p = 64
     (42, 64, 70, O.SCRIPT_WEIGHTS),     # largest envelope: Ip = 128, L2p = 128
     (10, 5, 64, (0.3, 0.2, 0.0, 0.0)),  # odd latent (misaligned offsets), zero-weight terms
+    (43, 8, 70, O.SCRIPT_WEIGHTS),      # 3T = 129: first trajectory longer than one 128-feature chunk
+    (50, 8, 200, O.SCRIPT_WEIGHTS),     # BASELINE configs[4] lower end of the length sweep
+    (100, 16, 150, O.DEFAULT_WEIGHTS),  # three chunks, ragged last chunk (300 = 2*128 + 44)
+    (400, 64, 40, O.SCRIPT_WEIGHTS),    # top of the envelope: ten chunks, latent 64
 ])
 def test_fused_fwd_bwd_vs_oracle(T, L, B, weights, impl):
     from dmvae.train import FusedTrainer
