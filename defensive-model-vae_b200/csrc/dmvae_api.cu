@@ -220,9 +220,11 @@ int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B) {
   const dmvae::TrainPlan p = dmvae::plan_train(lo, B > 0 ? B : 1, sms, false);
   size_t floats = workspace_floats(p);
   if (dmvae::train_tc_supported(lo)) {  // covers both implementations (dmvae_set_train_impl)
-    const dmvae::TrainTcPlan t = dmvae::plan_train_tc(lo, B > 0 ? B : 1, sms);
-    const size_t tc = t.stash_floats + t.slab_floats + t.loss_floats;
-    if (tc > floats) floats = tc;
+    for (int overlap = 0; overlap < 2; ++overlap) {   // either launch scheme (dmvae_set_train_impl 0 / 2)
+      const dmvae::TrainTcPlan t = dmvae::plan_train_tc(lo, B > 0 ? B : 1, sms, overlap);
+      const size_t tc = t.stash_floats + t.slab_floats + t.loss_floats + t.flag_floats;
+      if (tc > floats) floats = tc;
+    }
   }
   return (int64_t)(floats * sizeof(float));
 }
@@ -267,10 +269,16 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     float* stash = static_cast<float*>(workspace);
     float* slabs = stash + tp.stash_floats;
     float* loss_part = slabs + tp.slab_floats;
-    e = PROF(dmvae::K_CHAIN, st, dmvae::launch_chain(lo, tp, io, stash, loss_part, st));
-    if (e != cudaSuccess) return cuda_fail(e, what);
-    e = PROF(dmvae::K_WGRAD, st, dmvae::launch_wgrad(lo, tp, stash, slabs, st));
-    if (e != cudaSuccess) return cuda_fail(e, what);
+    if (tp.overlap) {
+      int* flags = reinterpret_cast<int*>(loss_part + tp.loss_floats);
+      e = PROF(dmvae::K_TRAIN_TC_FUSED, st, dmvae::launch_chain_wgrad_fused(lo, tp, io, stash, slabs, loss_part, flags, st));
+      if (e != cudaSuccess) return cuda_fail(e, what);
+    } else {
+      e = PROF(dmvae::K_CHAIN, st, dmvae::launch_chain(lo, tp, io, stash, loss_part, st));
+      if (e != cudaSuccess) return cuda_fail(e, what);
+      e = PROF(dmvae::K_WGRAD, st, dmvae::launch_wgrad(lo, tp, stash, slabs, st));
+      if (e != cudaSuccess) return cuda_fail(e, what);
+    }
     e = PROF(dmvae::K_REDUCE_TC, st, dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
   } else {
@@ -439,8 +447,10 @@ int dmvae_set_decode_impl(int impl) {
 }
 
 int dmvae_set_train_impl(int impl) {
-  if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (tensor cores) or 1 (FFMA)");
-  g_train_impl.store(impl);
+  if (impl < 0 || impl > 2)
+    return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (tensor cores), 1 (FFMA) or 2 (tensor cores, always two launches)");
+  g_train_impl.store(impl == 1 ? 1 : 0);
+  if (impl != 1) dmvae::set_train_tc_overlap(impl == 0);
   return DMVAE_OK;
 }
 
@@ -465,6 +475,7 @@ int dmvae_profile_begin(void) {
   return DMVAE_OK;
 }
 
+static_assert(DMVAE_KERNEL_COUNT == dmvae::K_COUNT, "include/dmvae.h and dmvae_prof.h disagree on the kernel count");
 int dmvae_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n) {
   if (!ms_by_kernel || !launches_by_kernel || n < 1 || n > DMVAE_KERNEL_COUNT)
     return fail(DMVAE_ERR_ARG, "profile_end: need two arrays of 1..%d entries", DMVAE_KERNEL_COUNT);

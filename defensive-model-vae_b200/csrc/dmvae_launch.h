@@ -64,14 +64,19 @@ struct TrainTcPlan {
   int unit_tiles[3], unit_count[3], unit_begin[3];  // tiles per unit, units (= partial slabs) per role, first slab
   int n_slabs;
   int slab_stride;
-  size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials]
+  size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials][tile flags]
+  bool overlap;               // small batch: chain and weight-gradient CTAs side by side in one launch
+  size_t flag_floats;         // per-tile epilogue counters of that launch (ints)
 };
 bool train_tc_supported(const Layout& lo);
 void set_chain_trace(long long* device_buffer);  // development aid (256 int64), null = off
-TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count);
+TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overlap = -1);  // -1: the current setting
 cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
                          cudaStream_t stream);
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream);
+cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* slabs,
+                                     float* loss_part, int* flags, cudaStream_t stream);
+void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (measurement / debugging)
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, cudaStream_t stream);

@@ -47,6 +47,12 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // =========================================================================================
 // chain kernel
 // =========================================================================================
@@ -78,7 +84,6 @@ struct COp {
 };
 
 struct ChainArgs {
-  Layout lo;
   const float* packed;
   const float* x;     // (B, T, 3) absolute
   const float* eps;   // (B, L) or null (Philox)
@@ -90,6 +95,12 @@ struct ChainArgs {
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
   long long* trace;   // development aid: clock64 stamps of CTA 0, first tile (null in production)
+  int* ready;         // when set: per-tile counter, +1 per epilogue warp and epilogue, once the stash images of that
+                      // epilogue are written (the weight-gradient CTAs of train_tc_fused_kernel wait on it)
+};
+struct ChainKArgs {
+  Layout lo;
+  ChainArgs c;
 };
 
 __device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
@@ -142,13 +153,13 @@ enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_
 enum EpiType { EP_HIDDEN = 0, EP_XREL, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
 constexpr int CH_EPIS = 22;
 __constant__ int c_epi[CH_EPIS][4] = {
-    // type, mask slot, stash slot, write the A operand
-    {EP_HIDDEN, MK_HC1, SX_HC1, 1}, {EP_HIDDEN, MK_HC, SX_HC, 1},  {EP_XREL, 0, 0, 0},
+    // type, mask slot, stash slot (the image the epilogue completes), write the A operand
+    {EP_HIDDEN, MK_HC1, SX_HC1, 1}, {EP_HIDDEN, MK_HC, SX_HC, 1},  {EP_XREL, 0, SX_X, 0},
     {EP_HIDDEN, MK_E1, SX_E1, 1},   {EP_HIDDEN, MK_E2, SX_E2, 1},  {EP_HIDDEN, MK_E3, SX_E3, 1},
-    {EP_HIDDEN, MK_E4, SX_E4, 1},   {EP_HEADS, 0, 0, 0},           {EP_HIDDEN, MK_D1, SX_D1, 1},
-    {EP_HIDDEN, MK_D2, SX_D2, 1},   {EP_HIDDEN, MK_D3, SX_D3, 1},  {EP_LOSS, 0, 0, 0},
+    {EP_HIDDEN, MK_E4, SX_E4, 1},   {EP_HEADS, 0, SX_Z, 0},        {EP_HIDDEN, MK_D1, SX_D1, 1},
+    {EP_HIDDEN, MK_D2, SX_D2, 1},   {EP_HIDDEN, MK_D3, SX_D3, 1},  {EP_LOSS, 0, SG_REC, 0},
     {EP_DGRAD, MK_D3, SG_D3, 1},    {EP_DGRAD, MK_D2, SG_D2, 1},   {EP_DGRAD, MK_D1, SG_D1, 1},
-    {EP_BDEC0, 0, 0, 0},            {EP_DGRAD, MK_HC, SG_HC, 1},   {EP_DGRAD, MK_HC1, SG_HC1, 0},
+    {EP_BDEC0, 0, SG_ML, 0},        {EP_DGRAD, MK_HC, SG_HC, 1},   {EP_DGRAD, MK_HC1, SG_HC1, 0},
     {EP_DGRAD, MK_E4, SG_E4, 1},    {EP_DGRAD, MK_E3, SG_E3, 1},   {EP_DGRAD, MK_E2, SG_E2, 1},
     {EP_DGRAD, MK_E1, SG_E1, 0},
 };
@@ -161,9 +172,9 @@ __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages)
   return chain_smem_floats(lo, stages) * 4 + CH_MAX_OPS * sizeof(COp) + 24 * 8 + 16 + 1024;
 }
 
-__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  const Layout& lo = a.lo;
+// cta / ncta: index of this CTA among the chain CTAs and their number (the whole grid for chain_kernel)
+__device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a, const int cta, const int ncta,
+                                           unsigned char* smem_dyn) {
   const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
   float *ring, *scratch, *xbuf, *mlb, *epb;
   uint32_t* masks;
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   const long long n_tiles = (a.B + CH_M - 1) / CH_M;
 
   if (tid == 0) {
+    if (a.trace != nullptr && cta == 0) a.trace[176] = global_ns();
     for (int st = 0; st < a.stages; ++st) {
       mbar_init(&full[st], 1);
       mbar_init(&empty[st], 1);
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     // ===================== producer warp: weight planes L2 -> smem ring =======================
     if (lane == 0) {
       RingStateRt rs(a.stages);
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (long long tile = cta; tile < n_tiles; tile += ncta)
         for (int o = 0; o < n_ops; ++o) {
           const COp op = ops[o];
           if (!op.dgrad) {
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
     // ===================== MMA warp (warp-uniform walk, one elected lane issues) ===============
     RingStateRt rs(a.stages);
     uint32_t a_phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (long long tile = cta; tile < n_tiles; tile += ncta)
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
         if (op.wait_a) {
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
           a_phase ^= 1u;
         }
         tc_fence_after();
-        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tile == blockIdx.x && lane == 0;
+        const bool tr = a.trace != nullptr && cta == 0 && tile == cta && lane == 0;
         if (tr) a.trace[o * 4 + 0] = clock64();
         if (!op.dgrad) {
           const uint32_t unit_bytes = (uint32_t)op.N * 32u;  // one K step of a plane
@@ -366,11 +378,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       tc_fence_after();
       if (tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
     };
+    long long flag_tile = -1;   // tile whose counter the next release bumps (none before the first epilogue)
     auto release_a = [&]() {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) {
+        mbar_arrive(a_ready);
+        if (a.ready != nullptr && flag_tile >= 0) {
+          // the warp's stash stores (ordered before this lane by the __syncwarp) -> visible device-wide, also to
+          // the bulk copies (async proxy) of the weight-gradient CTAs, before the counter moves
+          fence_proxy_async_global();
+          __threadfence();
+          atomicAdd(a.ready + flag_tile, 1);
+        }
+      }
       if (tr_tile && tid == 0) a.trace[128 + epi_no * 2 + 1] = clock64();
       ++epi_no;
     };
@@ -403,21 +425,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
       for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(a.x + base + i) : 0.f;
     };
-    load_x(blockIdx.x);
+    load_x(cta);
     if (h == 0) {  // the constant ones column (never overwritten)
       tmem_st4(lane_base + CT_ONES, __float_as_uint(1.0f), 0u, 0u, 0u);
       tmem_st4(lane_base + CT_ONES + 4, 0u, 0u, 0u, 0u);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
-    stage_start(blockIdx.x);
+    stage_start(cta);
     release_a();
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = cta; tile < n_tiles; tile += ncta) {
       const long long row = tile * CH_M + m;
       const bool row_ok = row < a.B;
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
-      tr_tile = a.trace != nullptr && blockIdx.x == 0 && tile == blockIdx.x;
+      tr_tile = a.trace != nullptr && cta == 0 && tile == cta;
       epi_no = 0;
+      flag_tile = tile;
 
       // this thread's 64 features of a 128-wide stash image: base of its row, then per 4-feature chunk
       // (mn_image_index with the row part hoisted; f = h*64 + c*16 + j4*4)
@@ -724,7 +747,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
       release_a();
       };
 
-      const long long next = tile + gridDim.x;
+      const long long next = tile + ncta;
 #pragma unroll 1
       for (int e = 0; e < CH_EPIS; ++e) {
         const int ty = c_epi[e][0];
@@ -760,7 +783,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
 #pragma unroll
         for (int t4 = 0; t4 < 4; ++t4) loss_acc[t4] += __shfl_xor_sync(0xffffffffu, loss_acc[t4], o);
       if (lane == 0) {
-        float* dst = a.loss_part + ((size_t)blockIdx.x * 4 + q) * 4;
+        float* dst = a.loss_part + ((size_t)cta * 4 + q) * 4;
         dst[0] = loss_acc[0]; dst[1] = loss_acc[1]; dst[2] = loss_acc[2]; dst[3] = loss_acc[3];
       }
     }
@@ -769,6 +792,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == CH_PRODUCER_WARP) tmem_dealloc(tmem, CT_COLS);
+  if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[177] = global_ns();
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainKArgs k) {
+  extern __shared__ unsigned char smem_dyn[];
+  chain_body(k.lo, k.c, (int)blockIdx.x, (int)gridDim.x, smem_dyn);
 }
 
 // =========================================================================================
@@ -810,34 +839,35 @@ __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* op
     else if (bias == 2) col += FB;
     ops[n++] = w;
   };
+  // within a role the ops follow the order in which the chain kernel completes their gradient images
+  // (epilogue numbers in c_epi), so that a CTA running next to the chain can start each one early
   if (role == 0) {
-    add(WK_COND1, SG_HC, SX_HC1, H, 1);
-    add(WK_ENC1, SG_E2, SX_E1, H, 1);
-    add(WK_ENC2, SG_E3, SX_E2, H, 1);
-    add(WK_COND0, SG_HC1, SX_START, 16, 0);   // columns 0, 1 = dW, column 2 = db (the ones column of the start image)
+    add(WK_COND1, SG_HC, SX_HC1, H, 1);       // 16
+    add(WK_COND0, SG_HC1, SX_START, 16, 0);   // 17; columns 0, 1 = dW, column 2 = db (the ones column of the start image)
+    add(WK_ENC2, SG_E3, SX_E2, H, 1);         // 19
+    add(WK_ENC1, SG_E2, SX_E1, H, 1);         // 20
   } else if (role == 1) {
-    add(WK_ENC3, SG_E4, SX_E3, H, 1);
-    add(WK_DEC1, SG_D2, SX_D1, H, 1);
-    add(WK_DEC2, SG_D3, SX_D2, H, 1);
-    add(WK_ENC0, SG_E1, SX_X, lo.Ip, 1);
+    add(WK_DEC2, SG_D3, SX_D2, H, 1);         // 12
+    add(WK_DEC1, SG_D2, SX_D1, H, 1);         // 13
+    add(WK_ENC3, SG_E4, SX_E3, H, 1);         // 18
+    add(WK_ENC0, SG_E1, SX_X, lo.Ip, 1);      // 21
   } else {
-    add(WK_DEC0_C, SG_D1, SX_HC, H, 1);
+    add(WK_DEC3, SX_D3, SG_REC, lo.Ip, 2);    // 11; transposed: lanes = input features, columns = output index
+    add(WK_DEC0_C, SG_D1, SX_HC, H, 1);       // 14
     add(WK_DEC0_Z, SG_D1, SX_Z, lo.Lp16, 0);
-    add(WK_HEADS_E, SX_E4, SG_ML, lo.NH, 2);  // transposed: lanes = input features, columns = (mu, logvar) index
+    add(WK_HEADS_E, SX_E4, SG_ML, lo.NH, 2);  // 15; transposed: lanes = input features, columns = (mu, logvar) index
     add(WK_HEADS_C, SX_HC, SG_ML, lo.NH, 0);
-    add(WK_DEC3, SX_D3, SG_REC, lo.Ip, 2);    // transposed: lanes = input features, columns = output index
   }
   return n;
 }
 __host__ __device__ inline int wgrad_role_cols(const Layout& lo, int role) {
   WOp ops[WG_MAX_OPS];
   const int n = wgrad_program(lo, role, ops);
-  const WOp& w = ops[n - 1];
+  const WOp& w = ops[n - 1];   // columns are handed out in op order
   return w.bias == 0 ? w.d_col + w.FB : (w.bias == 1 ? w.d_col_b + 16 : w.d_col_b + w.FB);
 }
 
 struct WgradArgs {
-  Layout lo;
   const float* stash;
   float* slabs;        // [units of all roles][slab_stride]
   long long n_tiles;
@@ -845,15 +875,41 @@ struct WgradArgs {
   int role_end[WG_ROLES];   // CTA index ranges: role r owns [role_end[r-1], role_end[r])
   int unit_tiles[WG_ROLES]; // tiles accumulated in tensor memory before the accumulators are written out
   int unit_begin[WG_ROLES]; // first slab of the role; unit u of role r writes slab unit_begin[r] + u
+  const int* ready;         // when set: per-tile epilogue counters of the chain CTAs running beside this kernel's
+  long long* trace;         // development aid: %globaltimer stamps of the CTAs of tile 0 (null in production)
+};
+struct WgradKArgs {
+  Layout lo;
+  WgradArgs w;
 };
 
-constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 /* ones (A side) */ + 1024 /* ones (B side) */ +
-                                 WG_MAX_OPS * sizeof(WOp) + 32 * 8 + 16 + 1024;
+// number of the chain epilogue (c_epi) that completes a stash image
+__device__ inline int slot_epilogue(int slot) {
+  if (slot == SX_START) return 0;   // staged before the tile's first epilogue
+  for (int e = 0; e < CH_EPIS; ++e)
+    if (c_epi[e][2] == slot) return e;
+  return CH_EPIS - 1;
+}
+// spin (one lane) until the chain has completed epilogue `epi` of a tile, then order the bulk copies behind it
+__device__ __forceinline__ void wait_tile_ready(const int* flag, int epi) {
+  const int need = (epi + 1) * CH_EPI_WARPS;
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= need) break;
+    __nanosleep(100);
+  }
+  fence_proxy_async_global();
+}
 
-__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradArgs a) {
-  extern __shared__ unsigned char smem_dyn[];
-  const Layout& lo = a.lo;
-  float *ring, *ones_a, *ones_b;
+constexpr int WG_WO_FLOATS = WG_WORK_WARPS * 32 * 20;   // write-out staging: per work warp 32 rows x 16 columns, row stride 20
+constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 /* ones (A side) */ + 1024 /* ones (B side) */ +
+                                 WG_WO_FLOATS * 4 + WG_MAX_OPS * sizeof(WOp) + 32 * 8 + 16 + 1024;
+static_assert(WG_SMEM_BYTES <= 232448, "weight-gradient kernel: shared memory");
+
+// cta: index of this CTA among the weight-gradient CTAs
+__device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a, const int cta, unsigned char* smem_dyn) {
+  float *ring, *ones_a, *ones_b, *wo_stage;
   WOp* ops;
   uint64_t *raw_full, *split_full, *empty, *d_done, *d_free;
   uint32_t* tmem_slot;
@@ -863,7 +919,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     ring = reinterpret_cast<float*>(p);
     ones_a = ring + (size_t)WG_STAGES * WG_STAGE_FLOATS;
     ones_b = ones_a + 1024;
-    ops = reinterpret_cast<WOp*>(ones_b + 256);
+    wo_stage = ones_b + 256;
+    ops = reinterpret_cast<WOp*>(wo_stage + WG_WO_FLOATS);
     raw_full = reinterpret_cast<uint64_t*>(ops + WG_MAX_OPS);
     split_full = raw_full + 8;
     empty = split_full + 8;
@@ -873,16 +930,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int role = 0;
-  while (role < WG_ROLES - 1 && (int)blockIdx.x >= a.role_end[role]) ++role;
+  while (role < WG_ROLES - 1 && cta >= a.role_end[role]) ++role;
   const int role_begin = role == 0 ? 0 : a.role_end[role - 1];
   const int role_ctas = a.role_end[role] - role_begin;
-  const int my_index = (int)blockIdx.x - role_begin;
+  const int my_index = cta - role_begin;
   // A unit = a run of consecutive tiles whose gradients are accumulated in tensor memory and then written to
   // the unit's own partial slab: bounds the number of (round-toward-zero) accumulations per accumulator.
   const long long ut = a.unit_tiles[role];
   const long long n_units = (a.n_tiles + ut - 1) / ut;
 
   if (tid == 0) {
+    if (a.trace != nullptr && my_index == 0) a.trace[180 + role * 16] = global_ns();
     for (int st = 0; st < WG_STAGES; ++st) {
       mbar_init(&raw_full[st], 1);
       mbar_init(&split_full[st], WG_WORK_WARPS);
@@ -922,6 +980,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
           const float* srcB = ts + lo.slot_off[op.slotB];
           const int FBm = lo.slot_w[op.slotB];  // width of the B image in memory
           const uint32_t bytesA = WG_ROWS * H * 4, bytesB = (uint32_t)(WG_ROWS * FBm * 4);
+          if (a.ready != nullptr) wait_tile_ready(a.ready + tile, max(slot_epilogue(op.slotA), slot_epilogue(op.slotB)));
+          if (a.trace != nullptr && tile == 0) a.trace[180 + role * 16 + 1 + o] = global_ns();
           for (int c = 0; c < chunks; ++c) {
             float* dst = ring + rs.stage * WG_STAGE_FLOATS;
             mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
@@ -1017,10 +1077,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     mbar_wait(d_done, done_phase);
     done_phase ^= 1u;
     tc_fence_after();
+    if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
     const int q = warp & 3, hh = warp >> 2;
     const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     float* slab = a.slabs + (size_t)(a.unit_begin[role] + unit) * a.slab_stride;
+    float* stg = wo_stage + warp * (32 * 20);   // this warp's staging tile of the write-out
     const int L = lo.L, I = lo.I;
     for (int o = 0; o < n_ops; ++o) {
       const WOp op = ops[o];
@@ -1029,32 +1091,49 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
         uint32_t v[16];
         tmem_ld16(lane_base + (uint32_t)(op.d_col + c * 16), v);
         tmem_ld_wait();
-        // layers stored [lane = output feature][column = input feature]: 16 consecutive floats of one row
-        float* rowp = nullptr;
-        int ncols = 16;
+        // layers stored [lane = output feature][column = input feature]: row stride and first float of the
+        // chunk in the row of tensor-memory lane 0
+        float* row0 = nullptr;
+        int rstride = H, ncols = 16;
         switch (op.kind) {
-          case WK_COND1: rowp = slab + lo.p_w[L_COND1] + ln * H + c * 16; break;
-          case WK_ENC0: rowp = slab + lo.p_w[L_ENC0] + ln * I + c * 16; ncols = min(16, I - c * 16); break;
-          case WK_ENC1: rowp = slab + lo.p_w[L_ENC1] + ln * H + c * 16; break;
-          case WK_ENC2: rowp = slab + lo.p_w[L_ENC2] + ln * H + c * 16; break;
-          case WK_ENC3: rowp = slab + lo.p_w[L_ENC3] + ln * H + c * 16; break;
-          case WK_DEC0_C: rowp = slab + lo.p_w[L_DEC0] + ln * (L + H) + L + c * 16; break;
-          case WK_DEC0_Z: rowp = slab + lo.p_w[L_DEC0] + ln * (L + H) + c * 16; ncols = min(16, L - c * 16); break;
-          case WK_DEC1: rowp = slab + lo.p_w[L_DEC1] + ln * H + c * 16; break;
-          case WK_DEC2: rowp = slab + lo.p_w[L_DEC2] + ln * H + c * 16; break;
+          case WK_COND1: row0 = slab + lo.p_w[L_COND1] + c * 16; break;
+          case WK_ENC0: row0 = slab + lo.p_w[L_ENC0] + c * 16; rstride = I; ncols = min(16, I - c * 16); break;
+          case WK_ENC1: row0 = slab + lo.p_w[L_ENC1] + c * 16; break;
+          case WK_ENC2: row0 = slab + lo.p_w[L_ENC2] + c * 16; break;
+          case WK_ENC3: row0 = slab + lo.p_w[L_ENC3] + c * 16; break;
+          case WK_DEC0_C: row0 = slab + lo.p_w[L_DEC0] + L + c * 16; rstride = L + H; break;
+          case WK_DEC0_Z: row0 = slab + lo.p_w[L_DEC0] + c * 16; rstride = L + H; ncols = min(16, L - c * 16); break;
+          case WK_DEC1: row0 = slab + lo.p_w[L_DEC1] + c * 16; break;
+          case WK_DEC2: row0 = slab + lo.p_w[L_DEC2] + c * 16; break;
           default: break;
         }
-        if (rowp != nullptr) {
-          if (ncols == 16 && (reinterpret_cast<uintptr_t>(rowp) & 15u) == 0) {
+        if (row0 != nullptr) {
+          // A lane holds 16 floats of its own row: stored directly, every instruction would touch 32 different
+          // lines.  Through the warp's staging tile (row stride 20 floats: conflict-free 128-bit accesses both
+          // ways) an instruction instead writes 8 rows x 64 contiguous bytes.
+          float4* mine = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4)
-              reinterpret_cast<float4*>(rowp)[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
-                                                                __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
-          } else {
+          for (int j4 = 0; j4 < 4; ++j4)
+            mine[j4] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]),
+                                   __uint_as_float(v[4 * j4 + 3]));
+          __syncwarp();
+          const int c4 = lane & 3;
+          const bool vec = ncols == 16 && (rstride & 3) == 0 && (reinterpret_cast<uintptr_t>(row0) & 15u) == 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < ncols) rowp[j] = __uint_as_float(v[j]);
+          for (int i = 0; i < 4; ++i) {
+            const int r = (lane >> 2) + 8 * i;
+            const float4 val = *reinterpret_cast<const float4*>(stg + r * 20 + c4 * 4);
+            float* dst = row0 + (size_t)(q * 32 + r) * rstride + c4 * 4;
+            if (vec) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              if (c4 * 4 + 0 < ncols) dst[0] = val.x;
+              if (c4 * 4 + 1 < ncols) dst[1] = val.y;
+              if (c4 * 4 + 2 < ncols) dst[2] = val.z;
+              if (c4 * 4 + 3 < ncols) dst[3] = val.w;
+            }
           }
+          __syncwarp();   // the tile is rewritten by the next chunk
           continue;
         }
 #pragma unroll
@@ -1121,12 +1200,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(d_free);
+    if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 9] = global_ns();
     }  // units
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == WG_PRODUCER_WARP) tmem_dealloc(tmem, 512);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradKArgs k) {
+  extern __shared__ unsigned char smem_dyn[];
+  wgrad_body(k.lo, k.w, (int)blockIdx.x, smem_dyn);
+}
+
+// Small batches leave most SMs without a chain tile: one launch runs the chain CTAs (the first chain_grid blocks)
+// and the weight-gradient CTAs side by side, and a weight-gradient CTA picks up each stash image of its tile as
+// soon as the tile's counter says the chain has completed it.  The chain never waits for the other side, and
+// its blocks come first in the grid, so the wait cannot deadlock.
+struct FusedTcArgs {
+  Layout lo;
+  ChainArgs c;
+  WgradArgs w;
+  int chain_grid;
+};
+static_assert(CH_THREADS == WG_THREADS, "the fused launch runs both bodies with one block size");
+__global__ void __launch_bounds__(CH_THREADS, 1) train_tc_fused_kernel(const __grid_constant__ FusedTcArgs k) {
+  extern __shared__ unsigned char smem_dyn[];
+  if ((int)blockIdx.x < k.chain_grid) chain_body(k.lo, k.c, (int)blockIdx.x, k.chain_grid, smem_dyn);
+  else wgrad_body(k.lo, k.w, (int)blockIdx.x - k.chain_grid, smem_dyn);
 }
 
 // =========================================================================================
@@ -1214,14 +1316,19 @@ bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && 
 
 static long long* g_chain_trace = nullptr;
 void set_chain_trace(long long* p) { g_chain_trace = p; }
+static bool g_tc_overlap = true;
+void set_train_tc_overlap(bool on) { g_tc_overlap = on; }
 
-TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
+TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overlap) {
   TrainTcPlan p;
   p.n_tiles = (B + CH_M - 1) / CH_M;
   p.chain_grid = (int)(p.n_tiles < sm_count ? p.n_tiles : sm_count);
   p.chain_stages = 4;
   while (p.chain_stages > 2 && chain_smem_bytes(lo, p.chain_stages) > 232448) --p.chain_stages;
   p.chain_smem = chain_smem_bytes(lo, p.chain_stages);
+  // Small batch: every tile gets a chain CTA and one weight-gradient CTA per role, all on their own SM in ONE launch
+  // (train_tc_fused_kernel); the weight gradients then overlap the second half of the chain.
+  p.overlap = (overlap < 0 ? g_tc_overlap : overlap != 0) && (long long)(1 + WG_ROLES) * p.n_tiles <= sm_count;
   // CTAs per role in proportion to the accumulator columns (= MMA time per tile), at most one per tile.
   // Tiles are grouped into units of at most 4 (64 K steps: bounds the tensor-memory accumulation depth);
   // every unit writes its own partial slab.
@@ -1231,7 +1338,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
   for (int r = 0; r < WG_ROLES; ++r) {
     long long n = (long long)sm_count * cols[r] / total;
     if (n < 1) n = 1;
-    if (n > p.n_tiles) n = p.n_tiles;
+    if (n > p.n_tiles || p.overlap) n = p.n_tiles;
     p.role_count[r] = (int)n;
     p.role_begin[r] = used;
     used += (int)n;
@@ -1254,43 +1361,82 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count) {
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
   p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
   p.loss_floats = (size_t)p.chain_grid * 16;
+  p.flag_floats = p.overlap ? (size_t)round_up((int)p.n_tiles, 4) : 0;
   return p;
 }
 
-cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
-                         cudaStream_t stream) {
+static ChainArgs chain_args(const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part) {
   ChainArgs a;
-  a.lo = lo; a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
+  a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;
   a.step_dev = io.step_dev;
   a.trace = g_chain_trace;
-  static size_t attr_set = 0;   // the opt-in limit only ever needs to grow
-  if (plan.chain_smem > attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.chain_smem);
-    if (e != cudaSuccess) return e;
-    attr_set = plan.chain_smem;
-  }
-  chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(a);
-  return cudaGetLastError();
+  a.ready = nullptr;
+  return a;
 }
-
-cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream) {
+static WgradArgs wgrad_args(const TrainTcPlan& plan, const float* stash, float* slabs) {
   WgradArgs a;
-  a.lo = lo; a.stash = stash; a.slabs = slabs; a.n_tiles = plan.n_tiles; a.slab_stride = plan.slab_stride;
+  a.stash = stash; a.slabs = slabs; a.n_tiles = plan.n_tiles; a.slab_stride = plan.slab_stride;
   for (int r = 0; r < WG_ROLES; ++r) {
     a.role_end[r] = plan.role_begin[r] + plan.role_count[r];
     a.unit_tiles[r] = plan.unit_tiles[r];
     a.unit_begin[r] = plan.unit_begin[r];
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(a);
+  a.ready = nullptr;
+  a.trace = g_chain_trace;
+  return a;
+}
+// the opt-in shared-memory limit of a kernel only ever needs to grow
+template <typename Kernel>
+static cudaError_t grow_smem_limit(Kernel kernel, size_t bytes, size_t* current) {
+  if (bytes <= *current) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) *current = bytes;
+  return e;
+}
+
+cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
+                         cudaStream_t stream) {
+  ChainKArgs k;
+  k.lo = lo;
+  k.c = chain_args(plan, io, stash, loss_part);
+  static size_t limit = 0;
+  const cudaError_t e = grow_smem_limit(chain_kernel, plan.chain_smem, &limit);
+  if (e != cudaSuccess) return e;
+  chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream) {
+  WgradKArgs k;
+  k.lo = lo;
+  k.w = wgrad_args(plan, stash, slabs);
+  static size_t limit = 0;
+  const cudaError_t e = grow_smem_limit(wgrad_kernel, WG_SMEM_BYTES, &limit);
+  if (e != cudaSuccess) return e;
+  wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(k);
+  return cudaGetLastError();
+}
+
+// plan.overlap: chain and weight-gradient CTAs in one launch; `flags` = plan.flag_floats ints of the workspace
+cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* slabs,
+                                     float* loss_part, int* flags, cudaStream_t stream) {
+  FusedTcArgs k;
+  k.lo = lo;
+  k.c = chain_args(plan, io, stash, loss_part);
+  k.w = wgrad_args(plan, stash, slabs);
+  k.c.ready = flags;
+  k.w.ready = flags;
+  k.chain_grid = plan.chain_grid;
+  const size_t smem = plan.chain_smem > WG_SMEM_BYTES ? plan.chain_smem : WG_SMEM_BYTES;
+  static size_t limit = 0;
+  cudaError_t e = grow_smem_limit(train_tc_fused_kernel, smem, &limit);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(flags, 0, plan.flag_floats * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  train_tc_fused_kernel<<<plan.chain_grid + plan.wgrad_grid, CH_THREADS, smem, stream>>>(k);
   return cudaGetLastError();
 }
 

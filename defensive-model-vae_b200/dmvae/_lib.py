@@ -73,7 +73,7 @@ SIGNATURES = {
     "dmvae_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 15
+KERNEL_COUNT = 16
 
 _lib = None
 

@@ -144,8 +144,12 @@ int64_t dmvae_grad_count(const DmvaeCfg* cfg);
 int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
 /* Which kernels the fused training pass launches: 0 (default) = tensor cores (tcgen05, 3xTF32:
  * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 16,
- * the FFMA kernels otherwise; 1 = always the FP32 FFMA kernels (train_kernel + reduce_kernel).
- * Both hold the tolerances of tests/test_train_gpu.py; dmvae_train_workspace_bytes covers both. */
+ * the FFMA kernels otherwise; 1 = always the FP32 FFMA kernels (train_kernel + reduce_kernel);
+ * 2 = tensor cores, always as two launches.  With 0, batches of at most (SMs / 4) * 128 rows run
+ * the chain and the weight-gradient CTAs side by side in ONE launch (train_tc_fused_kernel): a
+ * weight-gradient CTA starts on an image of its tile as soon as the chain has written it.  The
+ * results of 0 and 2 are bit-identical.  All hold the tolerances of tests/test_train_gpu.py;
+ * dmvae_train_workspace_bytes covers all three. */
 int dmvae_set_train_impl(int impl);
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps,
                         uint64_t seed, uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w,
@@ -214,8 +218,9 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
  * Kernel ids: 0 pack, 1 decode, 2 train (fused), 3 train (forward), 4 train
  * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe,
  * 11 decode (tensor cores), 12 train chain (tensor cores), 13 weight gradients (tensor
- * cores), 14 partial-slab reduction (+ Adam). */
-#define DMVAE_KERNEL_COUNT 15
+ * cores), 14 partial-slab reduction (+ Adam), 15 chain + weight gradients in one launch
+ * (small batches). */
+#define DMVAE_KERNEL_COUNT 16
 const char* dmvae_kernel_name(int kernel);
 /* Kernels launched by this process since the library was loaded (kernel < 0: all). */
 int64_t dmvae_launch_count(int kernel);

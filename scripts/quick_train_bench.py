@@ -39,7 +39,7 @@ def main():
     model = ConditionalTrajectoryVAE(T, 3, L).to("cuda")
     for B in sizes:
         x = torch.randn(B, T, 3, device="cuda").cumsum(1)
-        for impl, name in ((1, "FFMA"), (0, "TC  ")):
+        for impl, name in ((1, "FFMA     "), (2, "TC 2-launch"), (0, "TC       ")):
             lib.dmvae_set_train_impl(impl)
             tr = FusedTrainer(model, lr=1e-4)
             for _ in range(5):

@@ -44,3 +44,12 @@ for i, n in enumerate(OPS):
         es, er = t[128 + 2 * e] - t0, t[128 + 2 * e + 1] - t0
         line += f" | epi {es:7d} (+{es - mi:5d} after issue) -> {er:7d} (+{er - es:5d})"
     print(line)
+
+# train_tc_fused_kernel (small batch): %globaltimer stamps of chain CTA 0 and the weight-gradient CTAs of tile 0
+if t[176] and t[180]:
+    g0 = t[176]
+    print(f"fused launch: chain CTA 0 start 0 ns -> end {t[177] - g0} ns")
+    for r in range(3):
+        b = 180 + 16 * r
+        ops = [t[b + 1 + o] - g0 for o in range(5) if t[b + 1 + o]]
+        print(f"  wgrad role {r}: start {t[b] - g0}  ops ready at {ops}  accumulators done {t[b + 8] - g0}  written {t[b + 9] - g0}")
