@@ -269,8 +269,10 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     float* stash = static_cast<float*>(workspace);
     float* slabs = stash + tp.stash_floats;
     float* loss_part = slabs + tp.slab_floats;
+    int* flags = reinterpret_cast<int*>(loss_part + tp.loss_floats);
+    e = cudaMemsetAsync(flags, 0, tp.flag_floats * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail(e, what);
     if (tp.overlap) {
-      int* flags = reinterpret_cast<int*>(loss_part + tp.loss_floats);
       e = PROF(dmvae::K_TRAIN_TC_FUSED, st, dmvae::launch_chain_wgrad_fused(lo, tp, io, stash, slabs, loss_part, flags, st));
       if (e != cudaSuccess) return cuda_fail(e, what);
     } else {
@@ -279,8 +281,12 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
       e = PROF(dmvae::K_WGRAD, st, dmvae::launch_wgrad(lo, tp, stash, slabs, st));
       if (e != cudaSuccess) return cuda_fail(e, what);
     }
-    e = PROF(dmvae::K_REDUCE_TC, st, dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, st));
+    // with the update, the reduction kernel also refreshes `packed` and advances the device-side step counter
+    unsigned int* done = reinterpret_cast<unsigned int*>(flags + tp.flag_floats - 4);
+    e = PROF(dmvae::K_REDUCE_TC, st,
+             dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, packed_rw, step_dev, done, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
+    return DMVAE_OK;
   } else {
     const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, false);
     const Workspace ws = carve(workspace, plan);

@@ -66,7 +66,8 @@ struct TrainTcPlan {
   int slab_stride;
   size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials][tile flags]
   bool overlap;               // small batch: chain and weight-gradient CTAs side by side in one launch
-  size_t flag_floats;         // per-tile epilogue counters of that launch (ints)
+  size_t flag_floats;         // ints, zeroed before every pass: per-tile epilogue counters of that launch, then 4 for the
+                              // finished-block counter of the reduction
 };
 bool train_tc_supported(const Layout& lo);
 void set_chain_trace(long long* device_buffer);  // development aid (256 int64), null = off
@@ -79,7 +80,8 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
 void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (measurement / debugging)
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
-                             const long long* step_dev, cudaStream_t stream);
+                             const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
+                             cudaStream_t stream);
 
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],

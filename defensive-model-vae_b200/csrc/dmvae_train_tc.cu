@@ -28,6 +28,7 @@
 // anything else inside the ABI envelope runs the FFMA kernel of dmvae_train.cu.
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
+#include "dmvae_pack.cuh"
 #include "dmvae_tc.cuh"
 
 #include <type_traits>
@@ -1249,11 +1250,17 @@ struct ReduceTcArgs {
   // *step_dev + 1 (double arithmetic, as the host path and torch's Python floats)
   const long long* step_dev;
   double lr, beta1, beta2;
+  // with the update: the kernel-layout weight arena is refreshed in the same thread (scatter_param), and the
+  // last block to finish advances the device-side step counter (`done` counts finished blocks, self-resetting)
+  float* packed;
+  long long* step_inc;
+  unsigned int* done;
 };
 
-__global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* __restrict__ loss_part,
-                                 const __grid_constant__ ReduceTcArgs r, float* __restrict__ grads, float* __restrict__ p,
-                                 float* __restrict__ m, float* __restrict__ v) {
+__global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float* __restrict__ slabs,
+                                 const float* __restrict__ loss_part, const __grid_constant__ ReduceTcArgs r,
+                                 float* __restrict__ grads, float* __restrict__ p, float* __restrict__ m,
+                                 float* __restrict__ v) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ AdamScalarsTc hs;
   if (threadIdx.x == 0) {
@@ -1283,6 +1290,17 @@ __global__ void reduce_tc_kernel(const float* __restrict__ slabs, const float* _
       const float denom = sqrtf(vv) / hs.bc2_sqrt + hs.eps;
       pp = pp - hs.step_size * (mm / denom);
       p[e] = pp; m[e] = mm; v[e] = vv;
+      if (r.packed != nullptr) scatter_param(lo, e, pp, r.packed);
+    }
+  }
+  if (r.step_inc != nullptr) {   // every block has read *step_dev (above, before its first barrier) by the time it arrives here
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(r.done, 1u) == gridDim.x - 1) {
+        *r.done = 0u;
+        *r.step_inc += 1;
+      }
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
@@ -1361,7 +1379,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
   p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
   p.loss_floats = (size_t)p.chain_grid * 16;
-  p.flag_floats = p.overlap ? (size_t)round_up((int)p.n_tiles, 4) : 0;
+  p.flag_floats = (p.overlap ? (size_t)round_up((int)p.n_tiles, 4) : 0) + 4;   // + the finished-block counter of the reduction
   return p;
 }
 
@@ -1420,7 +1438,7 @@ cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float*
   return cudaGetLastError();
 }
 
-// plan.overlap: chain and weight-gradient CTAs in one launch; `flags` = plan.flag_floats ints of the workspace
+// plan.overlap: chain and weight-gradient CTAs in one launch; `flags` = the zeroed per-tile counters in the workspace
 cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* slabs,
                                      float* loss_part, int* flags, cudaStream_t stream) {
   FusedTcArgs k;
@@ -1434,16 +1452,18 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
   static size_t limit = 0;
   cudaError_t e = grow_smem_limit(train_tc_fused_kernel, smem, &limit);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(flags, 0, plan.flag_floats * sizeof(int), stream);
-  if (e != cudaSuccess) return e;
   train_tc_fused_kernel<<<plan.chain_grid + plan.wgrad_grid, CH_THREADS, smem, stream>>>(k);
   return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
-                             const long long* step_dev, cudaStream_t stream) {
+                             const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
+                             cudaStream_t stream) {
   ReduceTcArgs r;
+  r.packed = adam != nullptr ? packed : nullptr;
+  r.step_inc = (adam != nullptr && done != nullptr) ? step_inc : nullptr;
+  r.done = done;
   // state_dict order: cond0 (w,b) cond1 enc0 enc1 enc2 enc3 fc_mu fc_logvar dec0 dec1 dec2 dec3
   static const int role_of_pair[12] = {0, 0, 1, 0, 0, 1, 2, 2, 2, 1, 1, 2};
   const int w_off[12] = {lo.p_w[L_COND0], lo.p_w[L_COND1], lo.p_w[L_ENC0], lo.p_w[L_ENC1], lo.p_w[L_ENC2], lo.p_w[L_ENC3],
@@ -1469,7 +1489,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
     r.h.step_size = (float)(adam->lr / bc1); r.h.bc2_sqrt = (float)sqrt(bc2); r.h.eps = (float)adam->eps;
   }
   const int threads = 256;
-  reduce_tc_kernel<<<(lo.n_params + threads - 1) / threads, threads, 0, stream>>>(slabs, loss_part, r, grads, p, m, v);
+  reduce_tc_kernel<<<(lo.n_params + threads - 1) / threads, threads, 0, stream>>>(lo, slabs, loss_part, r, grads, p, m, v);
   return cudaGetLastError();
 }
 
