@@ -95,6 +95,7 @@ struct ChainArgs {
   long long B;
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
+  COp ops[CH_MAX_OPS];   // the per-tile GEMM program (chain_program, built on the host)
   long long* trace;   // development aid: clock64 stamps of CTA 0, first tile (null in production)
   int* ready;         // when set: per-tile counter, +1 per epilogue warp and epilogue, once the stash images of that
                       // epilogue are written (the weight-gradient CTAs of train_tc_fused_kernel wait on it)
@@ -104,7 +105,7 @@ struct ChainKArgs {
   ChainArgs c;
 };
 
-__device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
+__host__ __device__ inline COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
                                     int wait_a = 1, int commit_d = 1) {
   if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_col, d_col, acc, wait_a, commit_d, -1};
   return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_col, d_col, acc, wait_a, commit_d, -1};
@@ -112,7 +113,7 @@ __device__ __forceinline__ COp c_op(const TcLayer& c, int k0, int nk, int dgrad,
 
 // The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
 // commit_d is followed by exactly one epilogue of the tile body below (same order).
-__device__ inline int chain_program(const Layout& lo, COp* ops) {
+__host__ __device__ inline int chain_program(const Layout& lo, COp* ops) {
   const int zs = lo.Lp16 / 8;
   int n = 0;
   auto fwd = [&](int t, int k0, int nk, int d_col, int acc, bool with_bias) {
@@ -170,7 +171,7 @@ __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages
          (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */;
 }
 __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
-  return chain_smem_floats(lo, stages) * 4 + CH_MAX_OPS * sizeof(COp) + 24 * 8 + 16 + 1024;
+  return chain_smem_floats(lo, stages) * 4 + 24 * 8 + 16 + 1024;
 }
 
 // cta / ncta: index of this CTA among the chain CTAs and their number (the whole grid for chain_kernel)
@@ -179,7 +180,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
   float *ring, *scratch, *xbuf, *mlb, *epb;
   uint32_t* masks;
-  COp* ops;
+  const COp* ops = a.ops;   // kernel parameter space: uniform reads by the producer and the MMA warp
   uint64_t *full, *empty, *d_ready, *a_ready;
   uint32_t* tmem_slot;
   {
@@ -191,8 +192,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     mlb = xbuf + round_up(128 * I, 4);
     epb = mlb + (size_t)NH * 128;
     masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
-    ops = reinterpret_cast<COp*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
-    full = reinterpret_cast<uint64_t*>(ops + CH_MAX_OPS);
+    full = reinterpret_cast<uint64_t*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
     empty = full + 8;
     d_ready = empty + 8;
     a_ready = d_ready + 1;
@@ -211,7 +211,6 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     mbar_init(d_ready, 1);
     mbar_init(a_ready, CH_EPI_WARPS);
     mbar_fence_init();
-    chain_program(lo, ops);
   }
   if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
   tc_fence_before();
@@ -278,6 +277,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         tc_fence_after();
         const bool tr = a.trace != nullptr && cta == 0 && tile == cta && lane == 0;
         if (tr) a.trace[o * 4 + 0] = clock64();
+        if (tr && o == 0) a.trace[178] = global_ns();
         if (!op.dgrad) {
           const uint32_t unit_bytes = (uint32_t)op.N * 32u;  // one K step of a plane
           for (int k = 0; k < op.nk; k += op.kps) {
@@ -474,7 +474,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               // positive <=> the negated bit pattern is negative as an integer: shift its sign into the mask
               mw[c >> 1] = __funnelshift_l(0u - bits, mw[c >> 1], 1);
               const float x = fmaxf(__uint_as_float(bits), 0.f);
-              split_tf32_cvt(x, hi[j], lw[j]);
+              split_tf32(x, hi[j], lw[j]);
               xv[i] = x;
             }
             st_global_v8(xs + unit_off(c, up), xv);
@@ -505,7 +505,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             const uint32_t keep = (uint32_t)((int32_t)mw[c >> 1] >> 31);
             mw[c >> 1] <<= 1;
             gv[j] = __uint_as_float(v[c & 1][j] & keep);
-            split_tf32_cvt(gv[j], hi[j], lw[j]);
+            split_tf32(gv[j], hi[j], lw[j]);
           }
 #pragma unroll
           for (int up = 0; up < 2; ++up) {
@@ -609,7 +609,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       for (int c = 0; c < 4; ++c) {
         uint32_t hi[16], lw[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32_cvt(hcv[2 * c + (j >> 3)][j & 7], hi[j], lw[j]);
+        for (int j = 0; j < 16; ++j) split_tf32(hcv[2 * c + (j >> 3)][j & 7], hi[j], lw[j]);
         tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
         tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
       }
@@ -777,6 +777,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     }
 
 
+    if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[179] = global_ns();
     // loss partials: fixed-order tree inside the warp, one slot per (CTA, row quarter)
     if (h == 0) {
 #pragma unroll
@@ -876,6 +877,8 @@ struct WgradArgs {
   int role_end[WG_ROLES];   // CTA index ranges: role r owns [role_end[r-1], role_end[r])
   int unit_tiles[WG_ROLES]; // tiles accumulated in tensor memory before the accumulators are written out
   int unit_begin[WG_ROLES]; // first slab of the role; unit u of role r writes slab unit_begin[r] + u
+  WOp ops[WG_ROLES][WG_MAX_OPS];   // the per-tile program of every role (wgrad_program, built on the host)
+  int n_ops[WG_ROLES];
   const int* ready;         // when set: per-tile epilogue counters of the chain CTAs running beside this kernel's
   long long* trace;         // development aid: %globaltimer stamps of the CTAs of tile 0 (null in production)
 };
@@ -905,13 +908,12 @@ __device__ __forceinline__ void wait_tile_ready(const int* flag, int epi) {
 
 constexpr int WG_WO_FLOATS = WG_WORK_WARPS * 32 * 20;   // write-out staging: per work warp 32 rows x 16 columns, row stride 20
 constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 /* ones (A side) */ + 1024 /* ones (B side) */ +
-                                 WG_WO_FLOATS * 4 + WG_MAX_OPS * sizeof(WOp) + 32 * 8 + 16 + 1024;
+                                 WG_WO_FLOATS * 4 + 32 * 8 + 16 + 1024;
 static_assert(WG_SMEM_BYTES <= 232448, "weight-gradient kernel: shared memory");
 
 // cta: index of this CTA among the weight-gradient CTAs
 __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a, const int cta, unsigned char* smem_dyn) {
   float *ring, *ones_a, *ones_b, *wo_stage;
-  WOp* ops;
   uint64_t *raw_full, *split_full, *empty, *d_done, *d_free;
   uint32_t* tmem_slot;
   {
@@ -921,8 +923,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     ones_a = ring + (size_t)WG_STAGES * WG_STAGE_FLOATS;
     ones_b = ones_a + 1024;
     wo_stage = ones_b + 256;
-    ops = reinterpret_cast<WOp*>(wo_stage + WG_WO_FLOATS);
-    raw_full = reinterpret_cast<uint64_t*>(ops + WG_MAX_OPS);
+    raw_full = reinterpret_cast<uint64_t*>(wo_stage + WG_WO_FLOATS);
     split_full = raw_full + 8;
     empty = split_full + 8;
     d_done = empty + 8;
@@ -950,7 +951,6 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     mbar_init(d_done, 1);
     mbar_init(d_free, WG_WORK_WARPS);
     mbar_fence_init();
-    wgrad_program(lo, role, ops);
   }
   // constant "ones" operands (MN-major images of one 8-row group): feature 0 is 1 in every row
   for (int i = tid; i < 1024 + 256; i += WG_THREADS) ones_a[i] = 0.f;
@@ -965,8 +965,8 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  WOp tmp_ops[WG_MAX_OPS];
-  const int n_ops = wgrad_program(lo, role, tmp_ops);
+  const WOp* ops = a.ops[role];
+  const int n_ops = a.n_ops[role];
   constexpr int chunks = CH_M / WG_ROWS;  // 8 ring stages per (tile, op)
 
   if (warp == WG_PRODUCER_WARP) {
@@ -1383,7 +1383,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   return p;
 }
 
-static ChainArgs chain_args(const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part) {
+static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part) {
   ChainArgs a;
   a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
@@ -1392,15 +1392,19 @@ static ChainArgs chain_args(const TrainTcPlan& plan, const TrainIO& io, float* s
   a.step_dev = io.step_dev;
   a.trace = g_chain_trace;
   a.ready = nullptr;
+  for (int o = 0; o < CH_MAX_OPS; ++o) a.ops[o] = COp{};
+  chain_program(lo, a.ops);
   return a;
 }
-static WgradArgs wgrad_args(const TrainTcPlan& plan, const float* stash, float* slabs) {
+static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs) {
   WgradArgs a;
   a.stash = stash; a.slabs = slabs; a.n_tiles = plan.n_tiles; a.slab_stride = plan.slab_stride;
   for (int r = 0; r < WG_ROLES; ++r) {
     a.role_end[r] = plan.role_begin[r] + plan.role_count[r];
     a.unit_tiles[r] = plan.unit_tiles[r];
     a.unit_begin[r] = plan.unit_begin[r];
+    for (int o = 0; o < WG_MAX_OPS; ++o) a.ops[r][o] = WOp{};
+    a.n_ops[r] = wgrad_program(lo, r, a.ops[r]);
   }
   a.ready = nullptr;
   a.trace = g_chain_trace;
@@ -1419,7 +1423,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
                          cudaStream_t stream) {
   ChainKArgs k;
   k.lo = lo;
-  k.c = chain_args(plan, io, stash, loss_part);
+  k.c = chain_args(lo, plan, io, stash, loss_part);
   static size_t limit = 0;
   const cudaError_t e = grow_smem_limit(chain_kernel, plan.chain_smem, &limit);
   if (e != cudaSuccess) return e;
@@ -1430,7 +1434,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream) {
   WgradKArgs k;
   k.lo = lo;
-  k.w = wgrad_args(plan, stash, slabs);
+  k.w = wgrad_args(lo, plan, stash, slabs);
   static size_t limit = 0;
   const cudaError_t e = grow_smem_limit(wgrad_kernel, WG_SMEM_BYTES, &limit);
   if (e != cudaSuccess) return e;
@@ -1443,8 +1447,8 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
                                      float* loss_part, int* flags, cudaStream_t stream) {
   FusedTcArgs k;
   k.lo = lo;
-  k.c = chain_args(plan, io, stash, loss_part);
-  k.w = wgrad_args(plan, stash, slabs);
+  k.c = chain_args(lo, plan, io, stash, loss_part);
+  k.w = wgrad_args(lo, plan, stash, slabs);
   k.c.ready = flags;
   k.w.ready = flags;
   k.chain_grid = plan.chain_grid;

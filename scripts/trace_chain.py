@@ -48,7 +48,7 @@ for i, n in enumerate(OPS):
 # train_tc_fused_kernel (small batch): %globaltimer stamps of chain CTA 0 and the weight-gradient CTAs of tile 0
 if t[176] and t[180]:
     g0 = t[176]
-    print(f"fused launch: chain CTA 0 start 0 ns -> end {t[177] - g0} ns")
+    print(f"fused launch: chain CTA 0 start 0 ns -> first MMA {t[178] - g0} -> last epilogue done {t[179] - g0} -> end {t[177] - g0} ns")
     for r in range(3):
         b = 180 + 16 * r
         ops = [t[b + 1 + o] - g0 for o in range(5) if t[b + 1 + o]]
