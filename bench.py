@@ -363,7 +363,11 @@ def run_cuda(args):
     Bg = B * world
 
     from dmvae.parallel import DataParallelTrainer
-    dp = DataParallelTrainer(trainer)    # N > 1: fwd+bwd, ONE NCCL all-reduce of [grads | 5 losses], replicated Adam
+    # N > 1: the gradient exchange runs inside the update kernel over peer memory (NVLink) when the ranks can map
+    # each other's buffers, else fwd+bwd, ONE NCCL all-reduce of [grads | 5 losses], replicated Adam
+    dp = DataParallelTrainer(trainer, exchange=args.exchange)
+    if rank == 0 and dp.exchange_note:
+        print("bench.py: " + dp.exchange_note, file=sys.stderr)
 
     # single GPU: the whole step is one CUDA graph (dmvae_train_step_dev: Adam step index in device memory);
     # the batch of the step is copied device-to-device into the graph's input buffer
@@ -372,7 +376,7 @@ def run_cuda(args):
     elif world == 1:
         gstep = trainer.capture(B)
     else:
-        gstep = dp.capture(B)     # + the NCCL all-reduce of [grads | losses], captured in the same graph
+        gstep = dp.capture(B)     # + the exchange of [grads | losses]: inside the update kernel, or NCCL captured in the graph
 
     def train_step(i):
         b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
@@ -423,16 +427,26 @@ def run_cuda(args):
     dom_ms = prof[dominant][0] / max(prof[dominant][1], 1)
     per_kernel_us = {k: round(v[0] / max(v[1], 1) * 1e3, 2) for k, v in prof.items()}
 
-    # the FFMA kernels on the same workload, for the comparison north_star asks for
+    # the FFMA kernels on the same workload, for the comparison north_star asks for (N > 1: with the NCCL
+    # all-reduce - the in-kernel exchange belongs to the tensor-core update kernel)
     _lib.check(lib.dmvae_set_train_impl(1), "dmvae_set_train_impl")
+    dp_ffma = dp if dp.exchange != "peer" else DataParallelTrainer(trainer, exchange="nccl")
+
+    def ffma_step(i):
+        b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
+        if world == 1:
+            trainer.step(b, sample_offset=0)
+        else:
+            dp_ffma.step(b)
+
     for i in range(5):
-        train_step_host(i)
+        ffma_step(i)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     Kf = max(10, min(K, 200))
     f0.record()
     for i in range(Kf):
-        train_step_host(i)
+        ffma_step(i)
     f1.record()
     barrier()
     ffma_value = Kf * Bg / (max_over_ranks(f0.elapsed_time(f1)) * 1e-3)
@@ -598,10 +612,12 @@ def run_cuda(args):
                    "batch_per_gpu": B, "global_batch": Bg, "parallelism": f"dp{world}",
                    "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows,
                    "launch": ("one CUDA graph per step (device-side Adam step counter" +
-                              ("; the NCCL all-reduce is captured in it)" if world > 1 else ")")) if gstep is not None else "host-driven launches",
+                              ("; the NCCL all-reduce is captured in it)" if dp.exchange == "nccl" else ")")) if gstep is not None else "host-driven launches",
                    "l2": f"each step reads a different batch of a {rows * T * 3 * 4 / 1e6:.0f} MB resident set (> 126 MB L2); "
                          "weights and the per-step stash / slabs are L2-resident by design",
-                   "collective": "none" if world == 1 else "NCCL all-reduce SUM of 128947 fp32 per step"},
+                   "collective": {"none": "none", "nccl": "NCCL all-reduce SUM of 128947 fp32 per step",
+                                  "peer": "no library collective: the update kernel exchanges the 128947 fp32 of every rank "
+                                          "over peer memory (NVLink), block by block, and sums them in rank order"}[dp.exchange]},
         "roofline": {"bound": "tensor" if on_tensor else "fp32", "kernel": dominant, "achieved": ach, "peak": peak,
                      "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
                      "peak_source": ("dmvae_ffma_probe measured in this run (FP32 FFMA, all SMs)" if not on_tensor else
@@ -662,6 +678,8 @@ def main():
     ap.add_argument("--decode-rows", type=int, default=1 << 20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="host-driven steps instead of the CUDA-graph step")
+    ap.add_argument("--exchange", choices=("auto", "peer", "nccl"), default="auto",
+                    help="N > 1: gradient exchange inside the update kernel over peer memory, or one NCCL all-reduce")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -243,7 +243,8 @@ int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B) {
 static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
                         uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
                         void* workspace, float* grads, const DmvaeAdam* adam, float* params, float* m, float* v,
-                        float* packed_rw, void* stream, const char* what, long long* step_dev = nullptr) {
+                        float* packed_rw, void* stream, const char* what, long long* step_dev = nullptr,
+                        const DmvaeDpPeers* dp = nullptr) {
   dmvae::Layout lo;
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
@@ -263,7 +264,9 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   cudaError_t e;
   if (step_dev != nullptr && !dmvae::train_tc_supported(lo))
     return fail(DMVAE_ERR_SHAPE, "%s: the device-side step counter needs the tensor-core path (3*seq_len <= 64, latent_dim <= 16)", what);
-  if ((g_train_impl.load() == 0 || step_dev != nullptr) && dmvae::train_tc_supported(lo)) {
+  if (dp != nullptr && !dmvae::train_tc_supported(lo))
+    return fail(DMVAE_ERR_SHAPE, "%s: the peer-memory exchange needs the tensor-core path (3*seq_len <= 64, latent_dim <= 16)", what);
+  if ((g_train_impl.load() == 0 || step_dev != nullptr || dp != nullptr) && dmvae::train_tc_supported(lo)) {
     // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)
     const dmvae::TrainTcPlan tp = dmvae::plan_train_tc(lo, B, sms);
     float* stash = static_cast<float*>(workspace);
@@ -284,7 +287,8 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     // with the update, the reduction kernel also refreshes `packed` and advances the device-side step counter
     unsigned int* done = reinterpret_cast<unsigned int*>(flags + tp.flag_floats - 4);
     e = PROF(dmvae::K_REDUCE_TC, st,
-             dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, packed_rw, step_dev, done, st));
+             dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, packed_rw, step_dev, done,
+                                     dp, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
     return DMVAE_OK;
   } else {
@@ -312,6 +316,32 @@ int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, floa
   if (!packed) return fail(DMVAE_ERR_ARG, "train_step_dev: packed is null");
   return train_common(cfg, packed, x, eps, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, adam, params, m, v,
                       packed, stream, "train_step_dev", reinterpret_cast<long long*>(step_dev));
+}
+
+int64_t dmvae_dp_exchange_floats(const DmvaeCfg* cfg) {
+  dmvae::Layout lo;
+  const int rc = layout_or_fail(cfg, &lo);
+  return rc == DMVAE_OK ? dmvae::dp_exchange_stride(lo) : rc;
+}
+int64_t dmvae_dp_flag_words(const DmvaeCfg* cfg) {
+  dmvae::Layout lo;
+  const int rc = layout_or_fail(cfg, &lo);
+  return rc == DMVAE_OK ? (int64_t)(dmvae::reduce_tc_blocks(lo) + 1) * DMVAE_MAX_PEERS : rc;
+}
+int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
+                        const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
+                        float inv_batch, int64_t B, const DmvaeAdam* adam, int64_t* step_dev, void* workspace,
+                        float* grads, const DmvaeDpPeers* peers, void* stream) {
+  if (!adam || !packed) return fail(DMVAE_ERR_ARG, "train_step_dp: adam or packed is null");
+  if (!peers || peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+    return fail(DMVAE_ERR_ARG, "train_step_dp: peers must name 1..%d ranks and this rank among them", DMVAE_MAX_PEERS);
+  for (int p = 0; p < peers->world; ++p)
+    if (!peers->exchange[p] || !peers->flags[p] || !aligned16(peers->exchange[p]))
+      return fail(DMVAE_ERR_ARG, "train_step_dp: null or misaligned buffer of rank %d", p);
+  if (!step_dev && adam->step < 1) return fail(DMVAE_ERR_ARG, "train_step_dp: step must be >= 1");
+  return train_common(cfg, packed, x, eps, seed, sample_offset, step_dev ? 0 : (uint64_t)adam->step, w, inv_batch, B,
+                      workspace, grads, adam, params, m, v, packed, stream, "train_step_dp",
+                      reinterpret_cast<long long*>(step_dev), peers);
 }
 
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,

@@ -81,7 +81,9 @@ void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (m
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
-                             cudaStream_t stream);
+                             const DmvaeDpPeers* dp, cudaStream_t stream);
+int reduce_tc_blocks(const Layout& lo);   // grid of the reduction kernel = exchange units of a data-parallel step - 1
+inline int dp_exchange_stride(const Layout& lo) { return round_up(lo.n_params + 5, 4); }
 
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],

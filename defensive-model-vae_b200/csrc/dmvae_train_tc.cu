@@ -1235,6 +1235,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) train_tc_fused_kernel(const __g
 // =========================================================================================
 // reduction of the partial slabs (+ Adam)
 // =========================================================================================
+constexpr int REDUCE_TC_THREADS = 256;
 struct AdamScalarsTc {
   float w1, b2, w2, step_size, bc2_sqrt, eps;
 };
@@ -1255,7 +1256,44 @@ struct ReduceTcArgs {
   float* packed;
   long long* step_inc;
   unsigned int* done;
+  // data parallel (dp.world > 1): the gradient exchange over peer memory runs inside this kernel, between the
+  // slab sum and the update.  exchange[p] = rank p's buffer, two parities of dp_stride floats; flags[p] = rank p's
+  // flag words, [block][source rank] (+ one row for the loss terms), holding the last step each source published.
+  DmvaeDpPeers dp;
+  int dp_stride;
+  unsigned int epoch_host;   // the step index when there is no device-side counter
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+// One exchange unit (a block's 256 gradients, or the loss terms): every thread of `n_threads` has stored its own
+// value in this rank's buffer; publish the step to all peers, wait until every peer has published it, after
+// which the peers' values of the unit can be read.  Called by all threads of the unit (barrier = its scope).
+template <bool kBlock>
+__device__ __forceinline__ void dp_publish_and_wait(const DmvaeDpPeers& dp, int unit, unsigned int epoch) {
+  if (kBlock) __syncthreads(); else __syncwarp();
+  const int t = (int)threadIdx.x;
+  if (t < dp.world && t != dp.rank) {
+    // this thread's peer: the fence orders the unit's stores (made visible to it by the barrier) before the flag
+    __threadfence_system();
+    st_release_sys(dp.flags[t] + unit * 8 + dp.rank, epoch);
+    const unsigned int* mine = dp.flags[dp.rank] + unit * 8 + t;
+    while ((int)(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(40);
+  }
+  if (kBlock) __syncthreads(); else __syncwarp();
+}
+
 
 __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float* __restrict__ slabs,
                                  const float* __restrict__ loss_part, const __grid_constant__ ReduceTcArgs r,
@@ -1263,24 +1301,44 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
                                  float* __restrict__ v) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ AdamScalarsTc hs;
+  __shared__ unsigned int epoch_s;
   if (threadIdx.x == 0) {
     hs = r.h;
-    if (r.adam && r.step_dev != nullptr) {
+    epoch_s = r.epoch_host;
+    if (r.step_dev != nullptr) {
       const double step = (double)(*r.step_dev + 1);
-      hs.step_size = (float)(r.lr / (1.0 - pow(r.beta1, step)));
-      hs.bc2_sqrt = (float)sqrt(1.0 - pow(r.beta2, step));
+      epoch_s = (unsigned int)(*r.step_dev + 1);
+      if (r.adam) {
+        hs.step_size = (float)(r.lr / (1.0 - pow(r.beta1, step)));
+        hs.bc2_sqrt = (float)sqrt(1.0 - pow(r.beta2, step));
+      }
     }
   }
   __syncthreads();
+  const bool dp_on = r.dp.world > 1;
+  const int parity_off = dp_on ? (int)(epoch_s & 1u) * r.dp_stride : 0;
+  float s = 0.f;
   if (e < r.n_params) {
     int t = 0;
     while (t < 23 && e >= r.tensor_end[t]) ++t;
     const int role = r.tensor_role[t];
     const float* src = slabs + (size_t)r.role_begin[role] * r.slab_stride + e;
     const int n = r.role_count[role];
-    float s = 0.f;
 #pragma unroll 8
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
+    if (dp_on) r.dp.exchange[r.dp.rank][parity_off + e] = s;
+  }
+  if (dp_on) {
+    // sum over the ranks in rank order: the same values in the same order on every rank, so the replicas
+    // stay bit-identical without a broadcast
+    dp_publish_and_wait<true>(r.dp, (int)blockIdx.x, epoch_s);
+    if (e < r.n_params) {
+      float g = 0.f;
+      for (int p = 0; p < r.dp.world; ++p) g += p == r.dp.rank ? s : ld_relaxed_sys(r.dp.exchange[p] + parity_off + e);
+      s = g;
+    }
+  }
+  if (e < r.n_params) {
     grads[e] = s;
     if (r.adam) {
       // torch optim/adam.py::_single_tensor_adam (see dmvae_adam.cu)
@@ -1314,15 +1372,30 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) t[qd] += __shfl_xor_sync(0xffffffffu, t[qd], o);
-    if (threadIdx.x == 0) {
+    float mine[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    {
       const float start = r.w_start > 0.f ? t[2] : 0.f;
       const float time = r.w_time > 0.f ? t[3] : 0.f;
       float total = r.w_recon * t[0] + r.w_kld * t[1];
       if (r.w_start > 0.f) total += r.w_start * start;
       if (r.w_time > 0.f) total += r.w_time * time;
-      float* out = grads + r.n_params;
-      out[0] = total; out[1] = t[0]; out[2] = t[1]; out[3] = start; out[4] = time;
+      mine[0] = total; mine[1] = t[0]; mine[2] = t[1]; mine[3] = start; mine[4] = time;   // identical in every lane
     }
+    const int lane = (int)threadIdx.x;
+    float val = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) val = lane == i ? mine[i] : val;
+    if (dp_on) {   // the loss terms of the global batch: same exchange, unit = one past the last block
+      if (lane < 5) r.dp.exchange[r.dp.rank][parity_off + r.n_params + lane] = val;
+      dp_publish_and_wait<false>(r.dp, (int)gridDim.x, epoch_s);
+      if (lane < 5) {
+        float g = 0.f;
+        for (int p = 0; p < r.dp.world; ++p)
+          g += p == r.dp.rank ? val : ld_relaxed_sys(r.dp.exchange[p] + parity_off + r.n_params + lane);
+        val = g;
+      }
+    }
+    if (lane < 5) grads[r.n_params + lane] = val;
   }
 }
 
@@ -1463,8 +1536,12 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
-                             cudaStream_t stream) {
+                             const DmvaeDpPeers* dp, cudaStream_t stream) {
   ReduceTcArgs r;
+  if (dp != nullptr) r.dp = *dp;
+  else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
+  r.dp_stride = dp_exchange_stride(lo);
+  r.epoch_host = adam != nullptr ? (unsigned int)adam->step : 0u;
   r.packed = adam != nullptr ? packed : nullptr;
   r.step_inc = (adam != nullptr && done != nullptr) ? step_inc : nullptr;
   r.done = done;
@@ -1492,9 +1569,9 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
     r.h.w1 = (float)(1.0 - b1); r.h.b2 = (float)b2; r.h.w2 = (float)(1.0 - b2);
     r.h.step_size = (float)(adam->lr / bc1); r.h.bc2_sqrt = (float)sqrt(bc2); r.h.eps = (float)adam->eps;
   }
-  const int threads = 256;
-  reduce_tc_kernel<<<(lo.n_params + threads - 1) / threads, threads, 0, stream>>>(lo, slabs, loss_part, r, grads, p, m, v);
+  reduce_tc_kernel<<<reduce_tc_blocks(lo), REDUCE_TC_THREADS, 0, stream>>>(lo, slabs, loss_part, r, grads, p, m, v);
   return cudaGetLastError();
 }
+int reduce_tc_blocks(const Layout& lo) { return (lo.n_params + REDUCE_TC_THREADS - 1) / REDUCE_TC_THREADS; }
 
 }  // namespace dmvae

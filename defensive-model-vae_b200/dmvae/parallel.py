@@ -4,10 +4,18 @@
   global index range ``shard_range(n, r, world)``; the in-kernel Philox counter is the
   GLOBAL row index, so the bytes written are identical for any world size.  No collective.
 * Training is data parallel: every rank runs the fused forward+loss+backward on its slice
-  of the global batch with the loss means scaled by 1/B_global, then ONE ``all_reduce(SUM)``
-  of the flat fp32 buffer [gradients (128 942 at T=10, L=8) | 5 loss terms], then the
-  identical replicated Adam update.  NCCL all-reduce results are bit-identical on every
-  rank, so the replicas stay in lock-step; ``parameter_checksum`` asserts it.
+  of the global batch with the loss means scaled by 1/B_global, then the flat fp32 buffer
+  [gradients (128 942 at T=10, L=8) | 5 loss terms] is summed over the ranks, then the
+  identical replicated Adam update.  Two exchanges:
+    "peer"  (GPUs of one node, the default where it can be set up) the update kernel itself
+            publishes its slab sums in a buffer every peer has mapped (torch symmetric
+            memory = CUDA peer access over NVLink), waits block by block for the peers'
+            flags and adds the ranks in rank order: compute, exchange and update are one
+            kernel, no library collective (``dmvae_train_step_dp``);
+    "nccl"  ONE ``all_reduce(SUM)`` between the fused pass and the Adam kernel (also the
+            path of the CPU tests, with gloo).
+  Either way every rank adds the same numbers in the same order, so the replicas stay
+  bit-identical; ``parameter_checksum`` asserts it.
 
 The reference has no distributed code at all (single process, Training_VAE.py:327); this
 module is the capability the north star adds.  The compute engine is injected (``engine``)
@@ -70,12 +78,83 @@ class DataParallelTrainer:
     the same step; sizes may differ).  Equivalent to one single-process step on the
     concatenated batch: same loss (means over the global batch), same update."""
 
-    def __init__(self, engine: GradEngine, group=None):
+    def __init__(self, engine: GradEngine, group=None, exchange: str = "auto"):
+        """``exchange``: "peer" (gradient exchange inside the update kernel over peer memory; raises where it
+        cannot be set up), "nccl" (one all-reduce per step), or "auto" (peer when possible, else nccl - the
+        reason is kept in ``exchange_note``).  All ranks must pass the same value."""
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(f"exchange={exchange!r}")
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._sizes = torch.zeros(self.world, dtype=torch.int64)
+        self.peers = None
+        self.exchange_note = ""
+        if self.world > 1 and exchange != "nccl":
+            try:
+                self._setup_peers()
+            except Exception as e:  # noqa: BLE001 - any failure of the optional path selects the collective
+                self.peers = None
+                self.exchange_note = f"peer exchange unavailable ({type(e).__name__}: {e}); using all_reduce"
+                ok = torch.zeros(1, device=self._device())
+            else:
+                ok = torch.ones(1, device=self._device())
+            # the choice must be unanimous: a rank that could not map its peers sends everyone to the collective
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if ok.item() < 1:
+                if exchange == "peer":
+                    raise RuntimeError(self.exchange_note or "peer exchange unavailable on another rank")
+                self.peers = None
+        self.exchange = "peer" if self.peers is not None else ("nccl" if self.world > 1 else "none")
+
+    def _device(self):
+        buf = getattr(self.engine, "grad_buf", None)
+        return buf.device if buf is not None else torch.device("cpu")
+
+    def _setup_peers(self) -> None:
+        """Allocates this rank's exchange buffer + flag words in symmetric memory and maps every peer's."""
+        from ._lib import MAX_PEERS, DmvaeDpPeers, check
+        eng = self.engine
+        lib, cfg_ref = getattr(eng, "lib", None), getattr(eng, "_cfg_ref", None)
+        if lib is None or cfg_ref is None or not self._device().type == "cuda":
+            raise RuntimeError("the engine is not a CUDA FusedTrainer")
+        if self.world > MAX_PEERS:
+            raise RuntimeError(f"{self.world} ranks, at most {MAX_PEERS} peers")
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = self._device()
+        with torch.cuda.device(dev):
+            stride = check(lib.dmvae_dp_exchange_floats(cfg_ref), "dmvae_dp_exchange_floats")
+            nflags = check(lib.dmvae_dp_flag_words(cfg_ref), "dmvae_dp_flag_words")
+            group = self.group if self.group is not None else dist.group.WORLD
+            enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
+            if enable is not None:
+                try:
+                    enable(group.group_name)
+                except Exception:  # noqa: BLE001 - newer torch enables every group implicitly
+                    pass
+            buf = symm_mem.empty(2 * stride + nflags, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, group)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or int(hdl.rank) != self.rank:
+            raise RuntimeError("symmetric memory handle does not match the process group")
+        peers = DmvaeDpPeers()
+        peers.world, peers.rank = self.world, self.rank
+        for p in range(self.world):
+            peers.exchange[p] = ptrs[p]
+            peers.flags[p] = ptrs[p] + 2 * stride * 4
+        self._symm = (buf, hdl)
+        self._flag_view = buf[2 * stride:]
+        self.peers = peers
+        self._reset_flags()
+
+    def _reset_flags(self) -> None:
+        """Collective: every rank zeroes its own flag words between two barriers (start of a step sequence)."""
+        torch.cuda.synchronize(self._device())
+        dist.barrier(group=self.group)
+        self._flag_view.zero_()
+        torch.cuda.synchronize(self._device())
+        dist.barrier(group=self.group)
 
     def global_batch_layout(self, local_rows: int, equal: bool = True) -> Tuple[int, int]:
         """(global batch size, this rank's row offset).  With ``equal`` every rank holds
@@ -93,6 +172,8 @@ class DataParallelTrainer:
 
     def step(self, local_batch: torch.Tensor, eps: Optional[torch.Tensor] = None, equal_shards: bool = True):
         B, offset = self.global_batch_layout(int(local_batch.shape[0]), equal_shards)
+        if self.peers is not None:
+            return self.engine.step_dp(local_batch, self.peers, B, eps=eps, sample_offset=offset)
         self.engine.loss_and_grads(local_batch, eps=eps, global_batch=B, sample_offset=offset)
         if self.world > 1:
             dist.all_reduce(self.engine.grad_buf, op=dist.ReduceOp.SUM, group=self.group)
@@ -104,6 +185,9 @@ class DataParallelTrainer:
         fused forward+loss+backward, the SUM all-reduce of [gradients | losses] (NCCL, captured), Adam,
         repack (engine = ``FusedTrainer``; equal shards).  Returns the engine's ``GraphStep``."""
         B, offset = self.global_batch_layout(int(local_rows), True)
+        if self.peers is not None:
+            return self.engine.capture(int(local_rows), host_batch=host_batch, host_losses=host_losses, sample_offset=offset,
+                                       global_batch=B, peers=self.peers, peers_reset=self._reset_flags)
         reduce_fn = None
         if self.world > 1:
             def reduce_fn(t):

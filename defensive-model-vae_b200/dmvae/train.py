@@ -95,10 +95,11 @@ class FusedTrainer:
             self._dev_t = self.t
 
     def capture(self, B: int, host_batch: Optional[torch.Tensor] = None, host_losses: Optional[torch.Tensor] = None,
-                sample_offset: int = 0, all_reduce=None, global_batch: Optional[int] = None) -> "GraphStep":
+                sample_offset: int = 0, all_reduce=None, global_batch: Optional[int] = None, peers=None,
+                peers_reset=None) -> "GraphStep":
         """The whole step for batch size ``B`` as one CUDA graph (host-driven ``step()`` / ``apply()`` calls may
         be mixed in: ``replay()`` re-synchronises the device-side step counter when needed)."""
-        return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch)
+        return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch, peers, peers_reset)
 
     # ------------------------------------------------------------------ passes
     def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
@@ -154,6 +155,29 @@ class FusedTrainer:
         return self.losses
 
 
+    def step_dp(self, batch: torch.Tensor, peers, global_batch: int, eps: Optional[torch.Tensor] = None,
+                sample_offset: int = 0) -> torch.Tensor:
+        """One data-parallel step with the gradient exchange inside the update kernel (``dmvae_train_step_dp``:
+        peer-memory reads over NVLink, no library collective).  ``peers``: a ``DmvaeDpPeers`` naming every rank's
+        exchange / flag buffer; all ranks call with the same step.  Returns the loss terms of the GLOBAL batch."""
+        batch = self._check_batch(batch)
+        B = batch.shape[0]
+        eps = self._check_eps(eps, B)
+        arena = self.model.flat_parameters()
+        packed = self.model.packed_weights()
+        ws = self._workspace(B)
+        self.t += 1
+        h = self._adam()
+        with torch.cuda.device(self.device):
+            check(self.lib.dmvae_train_step_dp(self._cfg_ref, ptr(arena), ptr(packed), ptr(self.m), ptr(self.v),
+                                               ptr(batch), ptr(eps), ctypes.c_uint64(self.seed),
+                                               ctypes.c_uint64(sample_offset), self._w_ref,
+                                               ctypes.c_float(1.0 / float(global_batch)), B, byref(h), None, ptr(ws),
+                                               ptr(self.grad_buf), byref(peers), stream_ptr()), "dmvae_train_step_dp")
+        self.model.mark_packed_current()
+        return self.losses
+
+
 class GraphStep:
     """One training step captured as a CUDA graph: optional H2D copy of the batch from a pinned host
     buffer, the fused step (``dmvae_train_step_dev``: chain, weight gradients, reduction + Adam, repack;
@@ -162,10 +186,11 @@ class GraphStep:
 
     def __init__(self, trainer: "FusedTrainer", B: int, host_batch: Optional[torch.Tensor] = None,
                  host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0,
-                 all_reduce=None, global_batch: Optional[int] = None):
+                 all_reduce=None, global_batch: Optional[int] = None, peers=None, peers_reset=None):
         """``all_reduce``: data-parallel ranks pass a callable that SUM-all-reduces a tensor in place (captured
         in the graph between the fused pass and the Adam update) and ``global_batch`` / ``sample_offset`` =
-        the global batch size and this rank's row offset."""
+        the global batch size and this rank's row offset.  ``peers`` (a ``DmvaeDpPeers``) instead selects the
+        step whose update kernel exchanges the gradients over peer memory itself (``dmvae_train_step_dp``)."""
         model = trainer.model
         self.trainer = trainer
         self.B = int(B)
@@ -186,7 +211,13 @@ class GraphStep:
         def launch():
             if host_batch is not None:
                 self.batch.copy_(host_batch, non_blocking=True)
-            if all_reduce is None:
+            if peers is not None:
+                check(lib.dmvae_train_step_dp(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
+                                              ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
+                                              ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,
+                                              byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
+                                              byref(peers), stream_ptr()), "dmvae_train_step_dp")
+            elif all_reduce is None:
                 check(lib.dmvae_train_step_dev(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
                                                ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
                                                ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,
@@ -222,6 +253,10 @@ class GraphStep:
             arena.copy_(saved[0]); trainer.m.copy_(saved[1]); trainer.v.copy_(saved[2]); trainer.step_dev.copy_(saved[3])
             check(lib.dmvae_pack_weights(trainer._cfg_ref, ptr(arena), ptr(packed), stream_ptr()), "dmvae_pack_weights")
             model.mark_packed_current()
+            if peers is not None and peers_reset is not None:
+                # the warm-up published its step index in the peers' flags and the counter was just rewound:
+                # the flags start over (collective: every rank resets its own between two barriers)
+                peers_reset()
 
     def replay(self) -> torch.Tensor:
         """Runs the captured step on the current contents of ``batch`` (or ``host_batch``); returns the five

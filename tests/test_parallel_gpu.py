@@ -71,7 +71,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, tmp):
+def _nccl_worker(rank, world, port, tmp, exchange):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch.distributed as dist
@@ -83,7 +83,8 @@ def _nccl_worker(rank, world, port, tmp):
     batch = _batch(B, 9)
     eps = torch.randn(steps, B, L, generator=torch.Generator().manual_seed(10))
     lo, hi = shard_range(B, rank, world)
-    dp = DataParallelTrainer(FusedTrainer(model, lr=1e-3, weights=O.SCRIPT_WEIGHTS))
+    dp = DataParallelTrainer(FusedTrainer(model, lr=1e-3, weights=O.SCRIPT_WEIGHTS), exchange=exchange)
+    assert dp.exchange == exchange, dp.exchange_note
     hist = []
     for s in range(steps):
         hist.append(dp.step(batch[lo:hi].cuda(), eps=eps[s, lo:hi].cuda()).cpu().clone())
@@ -96,11 +97,14 @@ def _nccl_worker(rank, world, port, tmp):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_nccl_data_parallel_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_nccl_data_parallel_matches_single_gpu(tmp_path, exchange):
+    """exchange = "peer": the gradient exchange runs inside the update kernel over peer memory
+    (dmvae_train_step_dp); "nccl": one all-reduce between the fused pass and the Adam kernel."""
     from dmvae.parallel import generate_shard
     from dmvae.train import FusedTrainer
     port = _free_port()
-    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     got = torch.load(os.path.join(tmp_path, "dp.pt"), weights_only=False)
     model, _ = _model(seed=5)
     B, steps = 4096, 4
@@ -118,7 +122,7 @@ def test_nccl_data_parallel_matches_single_gpu(tmp_path):
     assert np.array_equal(np.load(os.path.join(tmp_path, "gen.npy")), whole.cpu().numpy())
 
 
-def _nccl_graph_worker(rank, world, port, tmp):
+def _nccl_graph_worker(rank, world, port, tmp, exchange):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch.distributed as dist
@@ -130,18 +134,26 @@ def _nccl_graph_worker(rank, world, port, tmp):
     lo, hi = shard_range(B, rank, world)
     # host-driven data-parallel steps (Philox noise, keyed by the global row index) ...
     model_a, _ = _model(seed=6)
-    dpa = DataParallelTrainer(FusedTrainer(model_a, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77))
+    dpa = DataParallelTrainer(FusedTrainer(model_a, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77), exchange=exchange)
+    assert dpa.exchange == exchange, dpa.exchange_note
     ha = [dpa.step(b[lo:hi].cuda()).cpu().clone() for b in batches]
     # ... against the same steps replayed from one CUDA graph (all-reduce captured inside)
     model_b, _ = _model(seed=6)
-    dpb = DataParallelTrainer(FusedTrainer(model_b, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77))
+    dpb = DataParallelTrainer(FusedTrainer(model_b, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77), exchange=exchange)
     gs = dpb.capture(hi - lo)
     hb = []
-    for b in batches:
-        gs.batch.copy_(b[lo:hi])
-        hb.append(gs.replay().cpu().clone())
+    for rep in range(6):      # the same batches again and again: many back-to-back replays exercise the flags
+        for b in batches:
+            gs.batch.copy_(b[lo:hi])
+            out = gs.replay()
+            if rep == 0:
+                hb.append(out.cpu().clone())
     assert dpb.parameter_checksum(model_b.flat_parameters())
     np.testing.assert_allclose(torch.stack(hb).numpy(), torch.stack(ha).numpy(), rtol=1e-6)
+    for rep in range(5):
+        for b in batches:
+            dpa.step(b[lo:hi].cuda())
+    assert dpa.parameter_checksum(model_a.flat_parameters())
     pa, pb = model_a.flat_parameters().cpu(), model_b.flat_parameters().cpu()
     assert (pa - pb).abs().max().item() <= 1e-6 * pa.abs().max().item()
     if rank == 0:
@@ -155,7 +167,8 @@ def _nccl_graph_worker(rank, world, port, tmp):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_nccl_graph_step_matches_host_driven_step(tmp_path):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_nccl_graph_step_matches_host_driven_step(tmp_path, exchange):
     port = _free_port()
-    mp.spawn(_nccl_graph_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_graph_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     assert os.path.isfile(os.path.join(tmp_path, "ok"))
