@@ -318,15 +318,12 @@ int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, floa
                       packed, stream, "train_step_dev", reinterpret_cast<long long*>(step_dev));
 }
 
-int64_t dmvae_dp_exchange_floats(const DmvaeCfg* cfg) {
+int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world) {
   dmvae::Layout lo;
   const int rc = layout_or_fail(cfg, &lo);
-  return rc == DMVAE_OK ? dmvae::dp_exchange_stride(lo) : rc;
-}
-int64_t dmvae_dp_flag_words(const DmvaeCfg* cfg) {
-  dmvae::Layout lo;
-  const int rc = layout_or_fail(cfg, &lo);
-  return rc == DMVAE_OK ? (int64_t)(dmvae::reduce_tc_blocks(lo) + 1) * DMVAE_MAX_PEERS : rc;
+  if (rc != DMVAE_OK) return rc;
+  if (world < 1 || world > DMVAE_MAX_PEERS) return fail(DMVAE_ERR_ARG, "dp_inbox_bytes: 1..%d ranks", DMVAE_MAX_PEERS);
+  return (int64_t)world * 2 * dmvae::dp_exchange_stride(lo) * 8;   // [source][parity][stride] x {value, step}
 }
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
                         const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
@@ -336,8 +333,8 @@ int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float
   if (!peers || peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
     return fail(DMVAE_ERR_ARG, "train_step_dp: peers must name 1..%d ranks and this rank among them", DMVAE_MAX_PEERS);
   for (int p = 0; p < peers->world; ++p)
-    if (!peers->exchange[p] || !peers->flags[p] || !aligned16(peers->exchange[p]))
-      return fail(DMVAE_ERR_ARG, "train_step_dp: null or misaligned buffer of rank %d", p);
+    if (!peers->inbox[p] || !aligned16(peers->inbox[p]))
+      return fail(DMVAE_ERR_ARG, "train_step_dp: null or misaligned inbox of rank %d", p);
   if (!step_dev && adam->step < 1) return fail(DMVAE_ERR_ARG, "train_step_dp: step must be >= 1");
   return train_common(cfg, packed, x, eps, seed, sample_offset, step_dev ? 0 : (uint64_t)adam->step, w, inv_batch, B,
                       workspace, grads, adam, params, m, v, packed, stream, "train_step_dp",

@@ -82,7 +82,6 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
                              const DmvaeDpPeers* dp, cudaStream_t stream);
-int reduce_tc_blocks(const Layout& lo);   // grid of the reduction kernel = exchange units of a data-parallel step - 1
 inline int dp_exchange_stride(const Layout& lo) { return round_up(lo.n_params + 5, 4); }
 
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.

@@ -1257,43 +1257,37 @@ struct ReduceTcArgs {
   long long* step_inc;
   unsigned int* done;
   // data parallel (dp.world > 1): the gradient exchange over peer memory runs inside this kernel, between the
-  // slab sum and the update.  exchange[p] = rank p's buffer, two parities of dp_stride floats; flags[p] = rank p's
-  // flag words, [block][source rank] (+ one row for the loss terms), holding the last step each source published.
+  // slab sum and the update (dp_all_sum)
   DmvaeDpPeers dp;
   int dp_stride;
   unsigned int epoch_host;   // the step index when there is no device-side counter
+  long long* trace;          // development aid: %globaltimer stamps of block 0 (slots 230..)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// Data-parallel exchange, "low-latency" style: a gradient travels as one 8-byte word {value bits, step index}
+// written straight into the peer's inbox (a single NVLink store, atomic at that size), so the receiver polls the
+// word itself and no fence or separate flag is needed.  Inbox of a rank: [source rank][step parity][dp_stride] words.
+__device__ __forceinline__ void dp_push(uint2* dst, float v, unsigned int epoch) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ float dp_pull(const uint2* src, unsigned int epoch) {
+  unsigned int x, y;
+  do {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(src) : "memory");
+  } while (y != epoch);
+  return __uint_as_float(x);
 }
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
+// sum of `mine` over the ranks, in rank order (the same values in the same order on every rank: the replicas stay
+// bit-identical without a broadcast); idx = element index inside the exchange
+__device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, int idx, float mine, unsigned int epoch) {
+  const size_t par = (size_t)(epoch & 1u) * stride + idx;
+  for (int p = 0; p < dp.world; ++p)
+    if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+  float g = 0.f;
+  for (int p = 0; p < dp.world; ++p)
+    g += p == dp.rank ? mine : dp_pull(reinterpret_cast<const uint2*>(dp.inbox[dp.rank]) + (size_t)p * 2 * stride + par, epoch);
+  return g;
 }
-// One exchange unit (a block's 256 gradients, or the loss terms): every thread of `n_threads` has stored its own
-// value in this rank's buffer; publish the step to all peers, wait until every peer has published it, after
-// which the peers' values of the unit can be read.  Called by all threads of the unit (barrier = its scope).
-template <bool kBlock>
-__device__ __forceinline__ void dp_publish_and_wait(const DmvaeDpPeers& dp, int unit, unsigned int epoch) {
-  if (kBlock) __syncthreads(); else __syncwarp();
-  const int t = (int)threadIdx.x;
-  if (t < dp.world && t != dp.rank) {
-    // this thread's peer: the fence orders the unit's stores (made visible to it by the barrier) before the flag
-    __threadfence_system();
-    st_release_sys(dp.flags[t] + unit * 8 + dp.rank, epoch);
-    const unsigned int* mine = dp.flags[dp.rank] + unit * 8 + t;
-    while ((int)(ld_acquire_sys(mine) - epoch) < 0) __nanosleep(40);
-  }
-  if (kBlock) __syncthreads(); else __syncwarp();
-}
-
 
 __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float* __restrict__ slabs,
                                  const float* __restrict__ loss_part, const __grid_constant__ ReduceTcArgs r,
@@ -1302,6 +1296,8 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ AdamScalarsTc hs;
   __shared__ unsigned int epoch_s;
+  const bool tr = r.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (tr) r.trace[230] = global_ns();
   if (threadIdx.x == 0) {
     hs = r.h;
     epoch_s = r.epoch_host;
@@ -1316,7 +1312,6 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
   }
   __syncthreads();
   const bool dp_on = r.dp.world > 1;
-  const int parity_off = dp_on ? (int)(epoch_s & 1u) * r.dp_stride : 0;
   float s = 0.f;
   if (e < r.n_params) {
     int t = 0;
@@ -1326,17 +1321,9 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     const int n = r.role_count[role];
 #pragma unroll 8
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
-    if (dp_on) r.dp.exchange[r.dp.rank][parity_off + e] = s;
-  }
-  if (dp_on) {
-    // sum over the ranks in rank order: the same values in the same order on every rank, so the replicas
-    // stay bit-identical without a broadcast
-    dp_publish_and_wait<true>(r.dp, (int)blockIdx.x, epoch_s);
-    if (e < r.n_params) {
-      float g = 0.f;
-      for (int p = 0; p < r.dp.world; ++p) g += p == r.dp.rank ? s : ld_relaxed_sys(r.dp.exchange[p] + parity_off + e);
-      s = g;
-    }
+    if (tr) r.trace[231] = global_ns();
+    if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s);
+    if (tr) r.trace[233] = global_ns() + (long long)(s == 123.456f);
   }
   if (e < r.n_params) {
     grads[e] = s;
@@ -1351,6 +1338,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
       if (r.packed != nullptr) scatter_param(lo, e, pp, r.packed);
     }
   }
+  if (tr) r.trace[234] = global_ns();
   if (r.step_inc != nullptr) {   // every block has read *step_dev (above, before its first barrier) by the time it arrives here
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1385,16 +1373,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     float val = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) val = lane == i ? mine[i] : val;
-    if (dp_on) {   // the loss terms of the global batch: same exchange, unit = one past the last block
-      if (lane < 5) r.dp.exchange[r.dp.rank][parity_off + r.n_params + lane] = val;
-      dp_publish_and_wait<false>(r.dp, (int)gridDim.x, epoch_s);
-      if (lane < 5) {
-        float g = 0.f;
-        for (int p = 0; p < r.dp.world; ++p)
-          g += p == r.dp.rank ? val : ld_relaxed_sys(r.dp.exchange[p] + parity_off + r.n_params + lane);
-        val = g;
-      }
-    }
+    if (dp_on && lane < 5) val = dp_all_sum(r.dp, r.dp_stride, r.n_params + lane, val, epoch_s);   // the global batch's
     if (lane < 5) grads[r.n_params + lane] = val;
   }
 }
@@ -1542,6 +1521,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
   else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
   r.dp_stride = dp_exchange_stride(lo);
   r.epoch_host = adam != nullptr ? (unsigned int)adam->step : 0u;
+  r.trace = g_chain_trace;
   r.packed = adam != nullptr ? packed : nullptr;
   r.step_inc = (adam != nullptr && done != nullptr) ? step_inc : nullptr;
   r.done = done;
@@ -1569,9 +1549,8 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
     r.h.w1 = (float)(1.0 - b1); r.h.b2 = (float)b2; r.h.w2 = (float)(1.0 - b2);
     r.h.step_size = (float)(adam->lr / bc1); r.h.bc2_sqrt = (float)sqrt(bc2); r.h.eps = (float)adam->eps;
   }
-  reduce_tc_kernel<<<reduce_tc_blocks(lo), REDUCE_TC_THREADS, 0, stream>>>(lo, slabs, loss_part, r, grads, p, m, v);
+  reduce_tc_kernel<<<(lo.n_params + REDUCE_TC_THREADS - 1) / REDUCE_TC_THREADS, REDUCE_TC_THREADS, 0, stream>>>(lo, slabs, loss_part, r, grads, p, m, v);
   return cudaGetLastError();
 }
-int reduce_tc_blocks(const Layout& lo) { return (lo.n_params + REDUCE_TC_THREADS - 1) / REDUCE_TC_THREADS; }
 
 }  // namespace dmvae

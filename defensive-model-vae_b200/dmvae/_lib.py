@@ -36,7 +36,7 @@ MAX_PEERS = 8
 
 
 class DmvaeDpPeers(ctypes.Structure):
-    _fields_ = [("world", c_int32), ("rank", c_int32), ("exchange", c_void_p * MAX_PEERS), ("flags", c_void_p * MAX_PEERS)]
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("inbox", c_void_p * MAX_PEERS)]
 
 
 # name -> (restype, argtypes); mirrors include/dmvae.h one to one
@@ -62,8 +62,7 @@ SIGNATURES = {
     "dmvae_train_fwd_bwd_dev": (c_int, [_CFG, _P, _P, _P, c_uint64, c_uint64, _P, POINTER(DmvaeLossWeights),
                                         c_float, c_int64, _P, _P, _P]),
     "dmvae_adam_step_dev": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P, _P]),
-    "dmvae_dp_exchange_floats": (c_int64, [_CFG]),
-    "dmvae_dp_flag_words": (c_int64, [_CFG]),
+    "dmvae_dp_inbox_bytes": (c_int64, [_CFG, c_int]),
     "dmvae_train_step_dp": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                     c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, POINTER(DmvaeDpPeers), _P]),
     "dmvae_adam_step": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P]),

@@ -7,11 +7,11 @@
   of the global batch with the loss means scaled by 1/B_global, then the flat fp32 buffer
   [gradients (128 942 at T=10, L=8) | 5 loss terms] is summed over the ranks, then the
   identical replicated Adam update.  Two exchanges:
-    "peer"  (GPUs of one node, the default where it can be set up) the update kernel itself
-            publishes its slab sums in a buffer every peer has mapped (torch symmetric
-            memory = CUDA peer access over NVLink), waits block by block for the peers'
-            flags and adds the ranks in rank order: compute, exchange and update are one
-            kernel, no library collective (``dmvae_train_step_dp``);
+    "peer"  (GPUs of one node, the default where it can be set up) every thread of the update
+            kernel writes its slab sum, tagged with the step, straight into the peers' inboxes
+            (torch symmetric memory = CUDA peer access over NVLink), polls its own inbox for
+            theirs and adds the ranks in rank order: sum, exchange and update are one kernel,
+            no library collective, no fence (``dmvae_train_step_dp``);
     "nccl"  ONE ``all_reduce(SUM)`` between the fused pass and the Adam kernel (also the
             path of the CPU tests, with gloo).
   Either way every rank adds the same numbers in the same order, so the replicas stay
@@ -113,7 +113,7 @@ class DataParallelTrainer:
         return buf.device if buf is not None else torch.device("cpu")
 
     def _setup_peers(self) -> None:
-        """Allocates this rank's exchange buffer + flag words in symmetric memory and maps every peer's."""
+        """Allocates this rank's inbox in symmetric memory and maps every peer's."""
         from ._lib import MAX_PEERS, DmvaeDpPeers, check
         eng = self.engine
         lib, cfg_ref = getattr(eng, "lib", None), getattr(eng, "_cfg_ref", None)
@@ -124,16 +124,9 @@ class DataParallelTrainer:
         import torch.distributed._symmetric_memory as symm_mem
         dev = self._device()
         with torch.cuda.device(dev):
-            stride = check(lib.dmvae_dp_exchange_floats(cfg_ref), "dmvae_dp_exchange_floats")
-            nflags = check(lib.dmvae_dp_flag_words(cfg_ref), "dmvae_dp_flag_words")
+            nbytes = check(lib.dmvae_dp_inbox_bytes(cfg_ref, self.world), "dmvae_dp_inbox_bytes")
             group = self.group if self.group is not None else dist.group.WORLD
-            enable = getattr(symm_mem, "enable_symm_mem_for_group", None)
-            if enable is not None:
-                try:
-                    enable(group.group_name)
-                except Exception:  # noqa: BLE001 - newer torch enables every group implicitly
-                    pass
-            buf = symm_mem.empty(2 * stride + nflags, dtype=torch.float32, device=dev)
+            buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=dev)
             hdl = symm_mem.rendezvous(buf, group)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
         if len(ptrs) != self.world or int(hdl.rank) != self.rank:
@@ -141,18 +134,17 @@ class DataParallelTrainer:
         peers = DmvaeDpPeers()
         peers.world, peers.rank = self.world, self.rank
         for p in range(self.world):
-            peers.exchange[p] = ptrs[p]
-            peers.flags[p] = ptrs[p] + 2 * stride * 4
+            peers.inbox[p] = ptrs[p]
         self._symm = (buf, hdl)
-        self._flag_view = buf[2 * stride:]
         self.peers = peers
         self._reset_flags()
 
     def _reset_flags(self) -> None:
-        """Collective: every rank zeroes its own flag words between two barriers (start of a step sequence)."""
+        """Collective: every rank zeroes its own inbox (the step index in every word) between two barriers:
+        the start of a step sequence."""
         torch.cuda.synchronize(self._device())
         dist.barrier(group=self.group)
-        self._flag_view.zero_()
+        self._symm[0].zero_()
         torch.cuda.synchronize(self._device())
         dist.barrier(group=self.group)
 

@@ -70,16 +70,14 @@ typedef struct DmvaeAdam {
 } DmvaeAdam;
 
 /* Data-parallel peers of one training job: one process per GPU of a node, every GPU mapping the others'
- * exchange buffers (CUDA peer access over NVLink; torch.distributed's symmetric memory provides the
- * mapping, cudaIpc would do as well).  Entry p of each array is rank p's buffer as addressed from THIS
- * device.  exchange[p]: 2 * dmvae_dp_exchange_floats() floats; flags[p]: dmvae_dp_flag_words() 32-bit
- * words, zero before the first step (every rank zeroes its own, then a barrier). */
+ * inbox (CUDA peer access over NVLink; torch.distributed's symmetric memory provides the mapping, cudaIpc
+ * would do as well).  inbox[p] is rank p's inbox as addressed from THIS device: dmvae_dp_inbox_bytes()
+ * bytes, zero before the first step (every rank zeroes its own, then a barrier). */
 #define DMVAE_MAX_PEERS 8
 typedef struct DmvaeDpPeers {
   int32_t world;
   int32_t rank;
-  float* exchange[DMVAE_MAX_PEERS];
-  uint32_t* flags[DMVAE_MAX_PEERS];
+  void* inbox[DMVAE_MAX_PEERS];
 } DmvaeDpPeers;
 
 int dmvae_abi_version(void);
@@ -193,16 +191,15 @@ int dmvae_adam_step_dev(const DmvaeCfg* cfg, float* params, const float* grads, 
                         const DmvaeAdam* adam, int64_t* step_dev, float* packed, void* stream);
 /* The whole data-parallel step without a library collective (replaces loss.backward() + the gradient
  * all-reduce the north star adds + optimizer.step(), Training_VAE.py:351-363): the fused pass on this rank's
- * rows (inv_batch = 1 / global batch), then ONE kernel that sums the partial slabs, writes the result to this
- * rank's exchange buffer, publishes a per-block flag to every peer, waits for the peers' flags, reads their
- * buffers over NVLink, adds the ranks in rank order (bit-identical replicas, no broadcast), applies Adam and
- * refreshes `packed`.  Blocks exchange independently: no grid-wide or job-wide barrier.  grads receives the
- * global gradient and the five loss terms of the global batch.  step_dev may be NULL (host-driven: the step
- * is adam->step) or the device-side counter of dmvae_train_step_dev (graph-capturable).  The exchange is
- * double-buffered by step parity and the flags carry the step index, so steps need no reset; all ranks must
- * call with the same step.  Tensor-core path only. */
-int64_t dmvae_dp_exchange_floats(const DmvaeCfg* cfg);
-int64_t dmvae_dp_flag_words(const DmvaeCfg* cfg);
+ * rows (inv_batch = 1 / global batch), then ONE kernel in which every thread sums the partial slabs of its
+ * gradient, writes {value, step index} as one 8-byte word into every peer's inbox over NVLink, polls its own
+ * inbox for the peers' words of the same step, adds the ranks in rank order (bit-identical replicas, no
+ * broadcast), applies Adam and refreshes `packed`.  No fence, flag, grid-wide or job-wide barrier.  grads
+ * receives the global gradient and the five loss terms of the global batch.  step_dev may be NULL
+ * (host-driven: the step is adam->step) or the device-side counter of dmvae_train_step_dev
+ * (graph-capturable).  The inbox is double-buffered by step parity and every word carries its step, so
+ * steps need no reset; all ranks must call with the same step.  Tensor-core path only. */
+int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world);
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
                         const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                         const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
