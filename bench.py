@@ -83,6 +83,30 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+def traffic_from_profile(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed
+    `ncu --set full` summary under profiles/ (scripts/ncu_summary.py writes them); None when there is none."""
+    import glob
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_prof_*.txt")), reverse=True):
+        try:
+            text = open(path).read()
+        except OSError:
+            continue
+        if f"--- {kernel}" not in text and f"--- dmvae::{kernel}" not in text:
+            continue
+        total, seen = 0.0, 0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(name + r"\s+([0-9.]+)\s+(\w+)", text)
+            if m and m.group(2) in unit:
+                total += float(m.group(1)) * unit[m.group(2)]
+                seen += 1
+        if seen == 2:
+            return {"bytes_per_launch": total, "source": os.path.relpath(path, ROOT)}
+    return None
+
+
 def flops_per_unit():
     I = 3 * T
     cond = 2 * H + H * H
@@ -619,7 +643,9 @@ def run_cuda(args):
                                   "peer": "no library collective: the update kernel exchanges the 128947 fp32 of every rank "
                                           "over peer memory (NVLink), block by block, and sums them in rank order"}[dp.exchange]},
         "roofline": {"bound": "tensor" if on_tensor else "fp32", "kernel": dominant, "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s", "frac": ach / peak if peak else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                     "traffic": (traffic_from_profile(dominant) or {}).get("bytes_per_launch"),
+                     "traffic_source": (traffic_from_profile(dominant) or {}).get("source"),
                      "peak_source": ("dmvae_ffma_probe measured in this run (FP32 FFMA, all SMs)" if not on_tensor else
                                      "MEASURED_PEAKS.json bf16_tflops (dense bf16, burst: the kernel is timed alone)" if peaks
                                      else "fallback 1682.8 TFLOP/s: MEASURED_PEAKS.json absent"),
@@ -650,7 +676,11 @@ def run_cuda(args):
             "steps": Kd, "ms_per_step": dec_ms / Kd,
             "per_row_start_value": R * world / (pr_ms * 1e-3),
             "roofline": {"bound": "tensor", "kernel": "decode_tc_kernel", "achieved": dach, "peak": tensor_burst, "unit": "TFLOP/s",
-                         "frac": dach / tensor_burst if tensor_burst else None, "traffic": None,
+                         "frac": dach / tensor_burst if tensor_burst else None,
+                         "traffic": (traffic_from_profile("decode_tc_kernel") or {}).get("bytes_per_launch"),
+                         "traffic_source": (traffic_from_profile("decode_tc_kernel") or {}).get("source"),
+                         "traffic_note": "captured by scripts/gpu_check.sh at 262144 rows per launch (31 MB of output, which "
+                                         "stays in the 126 MB L2 for the length of the kernel); the algorithmic bytes are 120 B per row",
                          "tf32x3_ceiling": tensor_burst / 6.0, "frac_of_tf32x3_ceiling": dach / (tensor_burst / 6.0),
                          "ffma_peak_tflops": peak_ffma,
                          "flop_per_launch": R * fl["decode_shared_start"], "kernel_ms": dec_kernel_ms,

@@ -15,8 +15,8 @@ $SMALL > gpurun_out/${tag}_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu list rc=$?"
 $SMALL > gpurun_out/${tag}_small2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:chain_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_prof_chain $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
-echo "ncu full chain rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:train_tc_fused_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_prof_fused $SMALL > gpurun_out/${tag}_ncu2.log 2>&1
+echo "ncu full fused rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 5 -c 1 -f -o gpurun_out/${tag}_prof_wgrad $SMALL > gpurun_out/${tag}_ncu3.log 2>&1
 echo "ncu full wgrad rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:decode_tc_kernel -s 4 -c 1 -f -o gpurun_out/${tag}_prof_decode_tc $SMALL > gpurun_out/${tag}_ncu4.log 2>&1
