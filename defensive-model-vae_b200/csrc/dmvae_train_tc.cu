@@ -82,6 +82,9 @@ struct COp {
   int wait_a;          // wait for the epilogue warps before issuing (A operand written, D drained)
   int commit_d;        // signal the epilogue warps when the accumulator is complete
   int bias_k;          // forward: K step of the image that holds the bias row (multiplied by the ones column), or -1
+  int pipe;            // 128 x 128 layer behind a four-phase epilogue: issued as 2 x 4 blocks (output half n, 32-deep
+                       // contraction quarter k), each as soon as the epilogue of the previous layer has released what
+                       // it needs; the first output half is committed before the second is issued (see the MMA warp)
 };
 
 struct ChainArgs {
@@ -96,6 +99,7 @@ struct ChainArgs {
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
   COp ops[CH_MAX_OPS];   // the per-tile GEMM program (chain_program, built on the host)
+  int pipe_on;           // the 128 x 128 layers are issued pipelined (their bias is added by the epilogue)
   long long* trace;   // development aid: clock64 stamps of CTA 0, first tile (null in production)
   int* ready;         // when set: per-tile counter, +1 per epilogue warp and epilogue, once the stash images of that
                       // epilogue are written (the weight-gradient CTAs of train_tc_fused_kernel wait on it)
@@ -107,43 +111,51 @@ struct ChainKArgs {
 
 __host__ __device__ inline COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
                                     int wait_a = 1, int commit_d = 1) {
-  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_col, d_col, acc, wait_a, commit_d, -1};
-  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_col, d_col, acc, wait_a, commit_d, -1};
+  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_col, d_col, acc, wait_a, commit_d, -1, 0};
+  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_col, d_col, acc, wait_a, commit_d, -1, 0};
 }
 
 // The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
 // commit_d is followed by exactly one epilogue of the tile body below (same order).
-__host__ __device__ inline int chain_program(const Layout& lo, COp* ops) {
+__host__ __device__ inline int chain_program(const Layout& lo, COp* ops, int stages) {
   const int zs = lo.Lp16 / 8;
+  const int pipe = stages >= 4 ? 1 : 0;   // a pipelined layer holds its four weight stages at once
   int n = 0;
-  auto fwd = [&](int t, int k0, int nk, int d_col, int acc, bool with_bias) {
+  auto fwd = [&](int t, int k0, int nk, int d_col, int acc, bool with_bias, int piped = 0) {
     COp o = c_op(lo.tc[t], k0, nk, 0, 0, d_col, acc);
-    if (with_bias) o.bias_k = lo.tc[t].K / 8;
+    // a pipelined layer gets its bias in the epilogue (the bias stage would be a fifth stage of a four-stage ring)
+    if (with_bias && !(piped && pipe)) o.bias_k = lo.tc[t].K / 8;
+    o.pipe = piped && pipe;
+    ops[n++] = o;
+  };
+  auto bwd = [&](int t, int k0, int nk, int a_col, int d_col, int acc, int wait_a = 1, int commit_d = 1, int piped = 0) {
+    COp o = c_op(lo.tc[t], k0, nk, 1, a_col, d_col, acc, wait_a, commit_d);
+    o.pipe = piped && pipe;
     ops[n++] = o;
   };
   fwd(TC_COND0, 0, 1, CT_D, 0, false);              // start -> hc1 (bias row inside its K = 8)
-  fwd(TC_COND1, 0, 16, CT_D, 0, true);              // hc1 -> hc
+  fwd(TC_COND1, 0, 16, CT_D, 0, true, 1);           // hc1 -> hc
   fwd(TC_HEADS, 16, 16, CT_DX, 0, false);           // hc share of the heads (kept aside)
   fwd(TC_ENC0, 0, lo.Ip / 8, CT_D, 0, true);        // x_rel -> e1
-  fwd(TC_ENC1, 0, 16, CT_D, 0, true);
-  fwd(TC_ENC2, 0, 16, CT_D, 0, true);
-  fwd(TC_ENC3, 0, 16, CT_D, 0, true);               // -> e4
+  fwd(TC_ENC1, 0, 16, CT_D, 0, true, 1);
+  fwd(TC_ENC2, 0, 16, CT_D, 0, true, 1);
+  fwd(TC_ENC3, 0, 16, CT_D, 0, true, 1);            // -> e4
   fwd(TC_HEADS, 0, 16, CT_DX, 1, true);             // + h_traj share + bias -> mu, logvar
   fwd(TC_DEC0, 0, 16 + zs, CT_D, 0, true);          // [hc ; z] -> d1
-  fwd(TC_DEC1, 0, 16, CT_D, 0, true);
-  fwd(TC_DEC2, 0, 16, CT_D, 0, true);
+  fwd(TC_DEC1, 0, 16, CT_D, 0, true, 1);
+  fwd(TC_DEC2, 0, 16, CT_D, 0, true, 1);
   fwd(TC_DEC3, 0, 16, CT_D, 0, true);               // -> recon
-  ops[n++] = c_op(lo.tc[TC_DEC3], 0, 4, 1, 0, CT_D, 0);                // d recon -> d d3 (4 slices of 32 columns)
-  ops[n++] = c_op(lo.tc[TC_DEC2], 0, 4, 1, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_DEC1], 0, 4, 1, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_DEC0], 0, 4, 1, 0, CT_D, 0, 1, 0);          // d d1 -> d hc (decoder share)
-  ops[n++] = c_op(lo.tc[TC_DEC0], 4, 1, 1, 0, CT_DX, 0, 0, 1);         //      -> d z (one slice)
-  ops[n++] = c_op(lo.tc[TC_HEADS], 4, 4, 1, CT_X, CT_D, 1);            // d (mu, logvar) -> + encoder share of d hc
-  ops[n++] = c_op(lo.tc[TC_COND1], 0, 4, 1, 0, CT_D, 0);               // d hc -> d hc1
-  ops[n++] = c_op(lo.tc[TC_HEADS], 0, 4, 1, CT_X, CT_D, 0);            // d (mu, logvar) -> d e4
-  ops[n++] = c_op(lo.tc[TC_ENC3], 0, 4, 1, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_ENC2], 0, 4, 1, 0, CT_D, 0);
-  ops[n++] = c_op(lo.tc[TC_ENC1], 0, 4, 1, 0, CT_D, 0);                // -> d e1
+  bwd(TC_DEC3, 0, 4, 0, CT_D, 0);                   // d recon -> d d3 (4 slices of 32 columns)
+  bwd(TC_DEC2, 0, 4, 0, CT_D, 0, 1, 1, 1);
+  bwd(TC_DEC1, 0, 4, 0, CT_D, 0, 1, 1, 1);
+  bwd(TC_DEC0, 0, 4, 0, CT_D, 0, 1, 0);             // d d1 -> d hc (decoder share)
+  bwd(TC_DEC0, 4, 1, 0, CT_DX, 0, 0, 1);            //      -> d z (one slice)
+  bwd(TC_HEADS, 4, 4, CT_X, CT_D, 1);               // d (mu, logvar) -> + encoder share of d hc
+  bwd(TC_COND1, 0, 4, 0, CT_D, 0, 1, 1, 1);         // d hc -> d hc1
+  bwd(TC_HEADS, 0, 4, CT_X, CT_D, 0);               // d (mu, logvar) -> d e4
+  bwd(TC_ENC3, 0, 4, 0, CT_D, 0, 1, 1, 1);
+  bwd(TC_ENC2, 0, 4, 0, CT_D, 0, 1, 1, 1);
+  bwd(TC_ENC1, 0, 4, 0, CT_D, 0, 1, 1, 1);          // -> d e1
   return n;
 }
 
@@ -154,16 +166,17 @@ enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_
 // cache (the unrolled version spent as many issue slots waiting for instructions as for memory).
 enum EpiType { EP_HIDDEN = 0, EP_XREL, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
 constexpr int CH_EPIS = 22;
-__constant__ int c_epi[CH_EPIS][4] = {
-    // type, mask slot, stash slot (the image the epilogue completes), write the A operand
-    {EP_HIDDEN, MK_HC1, SX_HC1, 1}, {EP_HIDDEN, MK_HC, SX_HC, 1},  {EP_XREL, 0, SX_X, 0},
-    {EP_HIDDEN, MK_E1, SX_E1, 1},   {EP_HIDDEN, MK_E2, SX_E2, 1},  {EP_HIDDEN, MK_E3, SX_E3, 1},
-    {EP_HIDDEN, MK_E4, SX_E4, 1},   {EP_HEADS, 0, SX_Z, 0},        {EP_HIDDEN, MK_D1, SX_D1, 1},
-    {EP_HIDDEN, MK_D2, SX_D2, 1},   {EP_HIDDEN, MK_D3, SX_D3, 1},  {EP_LOSS, 0, SG_REC, 0},
-    {EP_DGRAD, MK_D3, SG_D3, 1},    {EP_DGRAD, MK_D2, SG_D2, 1},   {EP_DGRAD, MK_D1, SG_D1, 1},
-    {EP_BDEC0, 0, SG_ML, 0},        {EP_DGRAD, MK_HC, SG_HC, 1},   {EP_DGRAD, MK_HC1, SG_HC1, 0},
-    {EP_DGRAD, MK_E4, SG_E4, 1},    {EP_DGRAD, MK_E3, SG_E3, 1},   {EP_DGRAD, MK_E2, SG_E2, 1},
-    {EP_DGRAD, MK_E1, SG_E1, 0},
+__constant__ int c_epi[CH_EPIS][5] = {
+    // type, mask slot, stash slot (the image the epilogue completes), write the A operand, layer whose bias the
+    // epilogue adds when the op before it is pipelined (-1: the bias, if any, came through the MMA)
+    {EP_HIDDEN, MK_HC1, SX_HC1, 1, -1},     {EP_HIDDEN, MK_HC, SX_HC, 1, L_COND1},  {EP_XREL, 0, SX_X, 0, -1},
+    {EP_HIDDEN, MK_E1, SX_E1, 1, -1},       {EP_HIDDEN, MK_E2, SX_E2, 1, L_ENC1},   {EP_HIDDEN, MK_E3, SX_E3, 1, L_ENC2},
+    {EP_HIDDEN, MK_E4, SX_E4, 1, L_ENC3},   {EP_HEADS, 0, SX_Z, 0, -1},             {EP_HIDDEN, MK_D1, SX_D1, 1, -1},
+    {EP_HIDDEN, MK_D2, SX_D2, 1, L_DEC1},   {EP_HIDDEN, MK_D3, SX_D3, 1, L_DEC2},   {EP_LOSS, 0, SG_REC, 0, -1},
+    {EP_DGRAD, MK_D3, SG_D3, 1, -1},        {EP_DGRAD, MK_D2, SG_D2, 1, -1},        {EP_DGRAD, MK_D1, SG_D1, 1, -1},
+    {EP_BDEC0, 0, SG_ML, 0, -1},            {EP_DGRAD, MK_HC, SG_HC, 1, -1},        {EP_DGRAD, MK_HC1, SG_HC1, 0, -1},
+    {EP_DGRAD, MK_E4, SG_E4, 1, -1},        {EP_DGRAD, MK_E3, SG_E3, 1, -1},        {EP_DGRAD, MK_E2, SG_E2, 1, -1},
+    {EP_DGRAD, MK_E1, SG_E1, 0, -1},
 };
 
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
@@ -171,7 +184,7 @@ __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages
          (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */;
 }
 __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
-  return chain_smem_floats(lo, stages) * 4 + 24 * 8 + 16 + 1024;
+  return chain_smem_floats(lo, stages) * 4 + 32 * 8 + 16 + 1024;
 }
 
 // cta / ncta: index of this CTA among the chain CTAs and their number (the whole grid for chain_kernel)
@@ -181,7 +194,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   float *ring, *scratch, *xbuf, *mlb, *epb;
   uint32_t* masks;
   const COp* ops = a.ops;   // kernel parameter space: uniform reads by the producer and the MMA warp
-  uint64_t *full, *empty, *d_ready, *a_ready;
+  // d_ready[n]: output half n of the accumulator is complete (MMA -> epilogue); a_ready[k]: quarter k of the A
+  // operand is written and quarter k of the accumulator has been read (epilogue -> MMA); a_free[k]: every MMA that
+  // reads quarter k of the A operand has completed (MMA -> epilogue)
+  uint64_t *full, *empty, *d_ready, *a_ready, *a_free;
   uint32_t* tmem_slot;
   {
     const uint32_t base = smem_u32(smem_dyn);
@@ -195,8 +211,9 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     full = reinterpret_cast<uint64_t*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
     empty = full + 8;
     d_ready = empty + 8;
-    a_ready = d_ready + 1;
-    tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+    a_ready = d_ready + 2;
+    a_free = a_ready + 4;
+    tmem_slot = reinterpret_cast<uint32_t*>(a_free + 4);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
@@ -208,8 +225,12 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       mbar_init(&full[st], 1);
       mbar_init(&empty[st], 1);
     }
-    mbar_init(d_ready, 1);
-    mbar_init(a_ready, CH_EPI_WARPS);
+    mbar_init(&d_ready[0], 1);
+    mbar_init(&d_ready[1], 1);
+    for (int k = 0; k < 4; ++k) {
+      mbar_init(&a_ready[k], CH_EPI_WARPS);
+      mbar_init(&a_free[k], 1);
+    }
     mbar_fence_init();
   }
   if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
@@ -270,12 +291,89 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     for (long long tile = cta; tile < n_tiles; tile += ncta)
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
+        const bool tr = a.trace != nullptr && cta == 0 && tile == cta && lane == 0;
+        if (op.pipe) {
+          // ---- a 128 x 128 layer in 2 x 4 blocks (output half n = 64 columns, contraction quarter k = one ring
+          // stage = 32 columns of the A operand).  Block (n, k) needs quarter k of A (a_ready[k]) and half n of
+          // the accumulator drained by the previous epilogue (a_ready[1] for n = 0, a_ready[3] for n = 1).  Order:
+          // (0,0) (0,1) (0,2) (0,3) -> d_ready[0] -> (1,0) .. (1,3), stage k and a_free[k] released after (1,k)
+          // -> d_ready[1]: the epilogue of the first half runs under the MMAs of the second, and the first blocks
+          // of the next layer under the second half of the epilogue.
+          int slot[4];
+          const uint32_t d = tmem + (uint32_t)op.d_col;
+          for (int nh = 0; nh < 2; ++nh) {
+            for (int k = 0; k < 4; ++k) {
+              if (nh == 0) {
+                if (k == 0) { mbar_wait(&a_ready[0], a_phase); mbar_wait(&a_ready[1], a_phase); }
+                else if (k >= 2) mbar_wait(&a_ready[k], a_phase);
+                slot[k] = rs.stage;
+                mbar_wait(&full[rs.stage], rs.phase);
+                rs.advance();
+                tc_fence_after();
+                if (tr && k == 0) { a.trace[o * 4 + 0] = clock64(); if (o == 0) a.trace[178] = global_ns(); }
+              }
+              const uint32_t b_hi = smem_u32(ring + slot[k] * STAGE_FLOATS);
+              const uint32_t a_hi0 = tmem + CT_AHI + (uint32_t)(op.a_col + 32 * k), a_lo0 = tmem + CT_ALO + (uint32_t)(op.a_col + 32 * k);
+              const uint32_t accf0 = (op.acc || k > 0) ? 1u : 0u;
+              if (!op.dgrad) {
+                // forward: stage = 4 K steps of the K-major planes [k-step][k-chunk][n-group of 8][8 n][4 k]; output
+                // half nh starts 8 n-groups (1 KB) into every k-chunk
+                const uint32_t unit_bytes = 128u * 32u;
+                const uint32_t b_lo = b_hi + 4u * unit_bytes;
+                const uint32_t idesc = umma_idesc_tf32(CH_M, 64);
+                const uint64_t dbits = umma_desc(0u, 128u * 16u, 128u);
+                uint64_t dh = dbits | (uint64_t)((b_hi + (uint32_t)nh * 1024u) >> 4), dl = dbits | (uint64_t)((b_lo + (uint32_t)nh * 1024u) >> 4);
+                if (elect_one()) {
+                  uint32_t a_hi = a_hi0, a_lo = a_lo0, accf = accf0;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) {
+                    umma_tf32_ts(d + 64u * nh, a_hi, dh, idesc, accf);
+                    umma_tf32_ts(d + 64u * nh, a_lo, dh, idesc, 1u);
+                    umma_tf32_ts(d + 64u * nh, a_hi, dl, idesc, 1u);
+                    accf = 1u;
+                    a_hi += 8u; a_lo += 8u; dh += (uint64_t)(unit_bytes >> 4); dl += (uint64_t)(unit_bytes >> 4);
+                  }
+                }
+              } else {
+                // data gradient: stage = one contraction group of gsz = 4 steps, planes [slice of 32 outputs][step]
+                // [two 512-byte atoms]; output half nh = slices 2 nh, 2 nh + 1
+                const uint32_t plane = 4u * 4u * 1024u;
+                const uint32_t idesc = umma_idesc_tf32(CH_M, 64, UMMA_B_MN);
+                const uint64_t dbits = umma_desc(0u, 4u * 1024u, 512u, 1u);
+                uint64_t dh = dbits | (uint64_t)((b_hi + (uint32_t)nh * 8192u) >> 4), dl = dbits | (uint64_t)((b_hi + plane + (uint32_t)nh * 8192u) >> 4);
+                if (elect_one()) {
+                  uint32_t a_hi = a_hi0, a_lo = a_lo0, accf = accf0;
+#pragma unroll
+                  for (int st = 0; st < 4; ++st) {
+                    umma_tf32_ts(d + 64u * nh, a_hi, dh, idesc, accf);
+                    umma_tf32_ts(d + 64u * nh, a_lo, dh, idesc, 1u);
+                    umma_tf32_ts(d + 64u * nh, a_hi, dl, idesc, 1u);
+                    accf = 1u;
+                    a_hi += 8u; a_lo += 8u; dh += 64u; dl += 64u;  // + 1024 bytes
+                  }
+                }
+              }
+              __syncwarp();
+              if (nh == 1) {
+                if (elect_one()) {
+                  umma_commit(&empty[slot[k]]);
+                  umma_commit(&a_free[k]);
+                }
+                __syncwarp();
+              }
+            }
+            if (elect_one()) umma_commit(&d_ready[nh]);
+            __syncwarp();
+          }
+          a_phase ^= 1u;
+          if (tr) a.trace[o * 4 + 1] = clock64();
+          continue;
+        }
         if (op.wait_a) {
-          mbar_wait(a_ready, a_phase);
+          for (int k = 0; k < 4; ++k) mbar_wait(&a_ready[k], a_phase);
           a_phase ^= 1u;
         }
         tc_fence_after();
-        const bool tr = a.trace != nullptr && cta == 0 && tile == cta && lane == 0;
         if (tr) a.trace[o * 4 + 0] = clock64();
         if (tr && o == 0) a.trace[178] = global_ns();
         if (!op.dgrad) {
@@ -354,8 +452,13 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             rs.advance();
           }
         }
-        if (op.commit_d) {
-          if (elect_one()) umma_commit(d_ready);
+        if (op.commit_d) {   // everything issued so far is complete: both halves of the accumulator, all of the A operand
+          if (elect_one()) {
+            umma_commit(&d_ready[0]);
+            umma_commit(&d_ready[1]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_commit(&a_free[k]);
+          }
           __syncwarp();
         }
         if (tr) a.trace[o * 4 + 1] = clock64();
@@ -373,29 +476,54 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 
     int epi_no = 0;
     bool tr_tile = false;
-    auto wait_d = [&]() {
-      mbar_wait(d_ready, d_phase);
-      d_phase ^= 1u;
+    // ---- hand-shakes with the MMA warp.  Every op that commits completes d_ready[0..1] and a_free[0..3] once, and
+    // every epilogue completes a_ready[0..3] once: one parity bit per direction.
+    auto wait_half = [&](int n) {          // output half n (64 columns) of the accumulator is complete
+      mbar_wait(&d_ready[n], d_phase);
       tc_fence_after();
-      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
+      if (n == 0 && tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
+    };
+    auto wait_free = [&](int k) {          // quarter k of the A operand is no longer read by any MMA
+      mbar_wait(&a_free[k], d_phase);
+      tc_fence_after();
+    };
+    auto arrive_q = [&](int k) {           // this warp has read accumulator quarter k and written quarter k of A
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[k]);
+    };
+    auto wait_d = [&]() {                  // epilogues without phases: the whole accumulator, A free to overwrite
+      wait_half(0);
+      wait_half(1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) wait_free(k);
     };
     long long flag_tile = -1;   // tile whose counter the next release bumps (none before the first epilogue)
-    auto release_a = [&]() {
+    auto finish_epilogue = [&]() {
+      if (lane == 0 && a.ready != nullptr && flag_tile >= 0) {
+        // the warp's stash stores (ordered before this lane by the __syncwarp of the last arrival) -> visible
+        // device-wide, also to the bulk copies (async proxy) of the weight-gradient CTAs, before the counter moves
+        fence_proxy_async_global();
+        __threadfence();
+        atomicAdd(a.ready + flag_tile, 1);
+      }
+      d_phase ^= 1u;
+      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2 + 1] = clock64();
+      ++epi_no;
+    };
+    auto arrive_all = [&]() {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(a_ready);
-        if (a.ready != nullptr && flag_tile >= 0) {
-          // the warp's stash stores (ordered before this lane by the __syncwarp) -> visible device-wide, also to
-          // the bulk copies (async proxy) of the weight-gradient CTAs, before the counter moves
-          fence_proxy_async_global();
-          __threadfence();
-          atomicAdd(a.ready + flag_tile, 1);
-        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mbar_arrive(&a_ready[k]);
       }
-      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2 + 1] = clock64();
-      ++epi_no;
+    };
+    auto release_a = [&]() {
+      arrive_all();
+      finish_epilogue();
     };
     // a 4-feature chunk of this thread's row in a stash image (MN-major, 32-byte swizzle: dmvae_tc.cuh)
     auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
@@ -433,7 +561,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     }
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
     stage_start(cta);
-    release_a();
+    arrive_all();
 
     for (long long tile = cta; tile < n_tiles; tile += ncta) {
       const long long row = tile * CH_M + m;
@@ -447,22 +575,33 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       // (mn_image_index with the row part hoisted; f = h*64 + c*16 + j4*4)
       const int row_part = (m >> 2) * 512 + (m & 3) * 32;
       const int swz = m & 3;
-      auto unit_off = [&](int c, int up) -> int {   // 8 features h*64 + c*16 + up*8 ..: one swizzled 32-byte unit
-        return (h * 2 + (c >> 1)) * 128 + (((((c & 1) << 1) + up) ^ swz) << 3);
+      // A 128-wide epilogue walks the accumulator in four phases of 32 columns (quarter c); the two warps of a lane
+      // quarter take 16 columns each: this thread's columns of phase c are c*32 + h*16 .. + 15.
+      auto unit_off = [&](int c, int up) -> int {   // 8 features c*32 + h*16 + up*8 ..: one swizzled 32-byte unit
+        return c * 128 + ((((h << 1) + up) ^ swz) << 3);
       };
-      // hidden layer (the bias is already in D): relu -> mask, stash image, A operand;
-      // 16 columns at a time, the next tensor-memory load in flight while a chunk is processed.
-      // Mask word w holds columns 32 w .. 32 w + 31 of this thread's 64, first column in the top bit.
-      auto epi_hidden = [&](int ms, int xslot) {
+      // hidden layer: (+ bias) relu -> mask, stash image, A operand.  Phases 0, 1 need the first output half of
+      // the accumulator, phases 2, 3 the second; each phase hands its quarter of A (and of D) to the MMA warp.
+      // Mask word w holds the columns of phases 2 w, 2 w + 1, first column in the top bit.
+      auto epi_hidden = [&](int ms, int xslot, int bias_l) {
         float* xs = ts + lo.slot_off[xslot] + row_part;
-        wait_d();
+        const float* __restrict__ bias = bias_l >= 0 ? pk + lo.q_b[bias_l] + h * 16 : nullptr;
         uint32_t v[2][16];
-        tmem_ld16(lane_base + CT_D + h * 64, v[0]);
         uint32_t mw[2] = {0u, 0u};
+        wait_half(0);
+        tmem_ld16(lane_base + CT_D + h * 16, v[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tmem_ld_wait();
-          if (c < 3) tmem_ld16(lane_base + CT_D + h * 64 + (c + 1) * 16, v[(c + 1) & 1]);
+          if (c == 0 || c == 2) tmem_ld16(lane_base + CT_D + (c + 1) * 32 + h * 16, v[(c + 1) & 1]);
+          float bv[16];
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + j4);
+              bv[4 * j4] = b4.x; bv[4 * j4 + 1] = b4.y; bv[4 * j4 + 2] = b4.z; bv[4 * j4 + 3] = b4.w;
+            }
+          }
           uint32_t hi[16], lw[16];
 #pragma unroll
           for (int up = 0; up < 2; ++up) {
@@ -470,7 +609,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = up * 8 + i;
-              const uint32_t bits = v[c & 1][j];
+              uint32_t bits = v[c & 1][j];
+              if (bias != nullptr) bits = __float_as_uint(__uint_as_float(bits) + bv[j]);
               // positive <=> the negated bit pattern is negative as an integer: shift its sign into the mask
               mw[c >> 1] = __funnelshift_l(0u - bits, mw[c >> 1], 1);
               const float x = fmaxf(__uint_as_float(bits), 0.f);
@@ -479,24 +619,31 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             }
             st_global_v8(xs + unit_off(c, up), xv);
           }
-          tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
-          tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+          wait_free(c);
+          tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);
+          tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
+          arrive_q(c);   // (handing the quarter over one phase later, to hide the store latency, was measured slower)
+          if (c == 1) {
+            wait_half(1);
+            tmem_ld16(lane_base + CT_D + 64 + h * 16, v[0]);
+          }
         }
         my_mask[(ms * 2) * CH_EPI_THREADS] = mw[0];
         my_mask[(ms * 2 + 1) * CH_EPI_THREADS] = mw[1];
-        release_a();
+        finish_epilogue();
       };
-      // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand)
-      auto epi_dgrad = [&](int ms, int gslot, bool write_a) {
+      // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand); same four phases.
+      // defer: the caller arrives for all four quarters itself (the last epilogue stages the next tile first)
+      auto epi_dgrad = [&](int ms, int gslot, bool write_a, bool defer) {
         float* gs = ts + lo.slot_off[gslot] + row_part;
-        wait_d();
         uint32_t v[2][16];
-        tmem_ld16(lane_base + CT_D + h * 64, v[0]);
         uint32_t mw[2] = {my_mask[(ms * 2) * CH_EPI_THREADS], my_mask[(ms * 2 + 1) * CH_EPI_THREADS]};
+        wait_half(0);
+        tmem_ld16(lane_base + CT_D + h * 16, v[0]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           tmem_ld_wait();
-          if (c < 3) tmem_ld16(lane_base + CT_D + h * 64 + (c + 1) * 16, v[(c + 1) & 1]);
+          if (c == 0 || c == 2) tmem_ld16(lane_base + CT_D + (c + 1) * 32 + h * 16, v[(c + 1) & 1]);
           uint32_t hi[16], lw[16];
           float gv[16];
 #pragma unroll
@@ -514,8 +661,14 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             st_global_v8(gs + unit_off(c, up), g8);
           }
           if (write_a) {
-            tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
-            tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+            wait_free(c);
+            tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);
+            tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
+          }
+          if (!defer) arrive_q(c);
+          if (c == 1) {
+            wait_half(1);
+            tmem_ld16(lane_base + CT_D + 64 + h * 16, v[0]);
           }
         }
       };
@@ -610,8 +763,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         uint32_t hi[16], lw[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) split_tf32(hcv[2 * c + (j >> 3)][j & 7], hi[j], lw[j]);
-        tmem_st16(lane_base + CT_AHI + h * 64 + c * 16, hi);
-        tmem_st16(lane_base + CT_ALO + h * 64 + c * 16, lw);
+        tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);   // features c*32 + h*16 .. (unit_off)
+        tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
       }
       release_a();
       };
@@ -753,17 +906,19 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       for (int e = 0; e < CH_EPIS; ++e) {
         const int ty = c_epi[e][0];
         if (ty == EP_HIDDEN) {
-          epi_hidden(c_epi[e][1], c_epi[e][2]);
+          epi_hidden(c_epi[e][1], c_epi[e][2], a.pipe_on ? c_epi[e][4] : -1);
         } else if (ty == EP_DGRAD) {
-          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0);
+          const bool last = e == CH_EPIS - 1;
+          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0, last);
           // after the first data gradient every warp is past the loss (that MMA could not finish before all of
           // them had released its A operand): the x tile can be replaced by the next tile's; after the last one
-          // the next tile's start point is staged
+          // the next tile's start point is staged, and only then is the A operand handed over
           if (next < n_tiles) {
             if (e == 12) load_x(next);
-            else if (e == CH_EPIS - 1) stage_start(next);
+            else if (last) stage_start(next);
           }
-          release_a();
+          if (last) arrive_all();
+          finish_epilogue();
         } else if (ty == EP_XREL) {
           epi_xrel();
         } else if (ty == EP_HEADS) {
@@ -1445,7 +1600,8 @@ static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const Tra
   a.trace = g_chain_trace;
   a.ready = nullptr;
   for (int o = 0; o < CH_MAX_OPS; ++o) a.ops[o] = COp{};
-  chain_program(lo, a.ops);
+  chain_program(lo, a.ops, plan.chain_stages);
+  a.pipe_on = plan.chain_stages >= 4 ? 1 : 0;
   return a;
 }
 static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs) {
