@@ -1425,12 +1425,10 @@ struct ReduceTcArgs {
 __device__ __forceinline__ void dp_push(uint2* dst, float v, unsigned int epoch) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ float dp_pull(const uint2* src, unsigned int epoch) {
-  unsigned int x, y;
-  do {
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "l"(src) : "memory");
-  } while (y != epoch);
-  return __uint_as_float(x);
+__device__ __forceinline__ uint2 dp_load(const uint2* src) {
+  uint2 w;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
+  return w;
 }
 // sum of `mine` over the ranks, in rank order (the same values in the same order on every rank: the replicas stay
 // bit-identical without a broadcast); idx = element index inside the exchange
@@ -1438,9 +1436,20 @@ __device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, 
   const size_t par = (size_t)(epoch & 1u) * stride + idx;
   for (int p = 0; p < dp.world; ++p)
     if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+  // all peers' words are requested at once (independent loads), then those that had not arrived yet are polled
+  const uint2* in = reinterpret_cast<const uint2*>(dp.inbox[dp.rank]) + par;
+  uint2 w[DMVAE_MAX_PEERS];
+#pragma unroll
+  for (int p = 0; p < DMVAE_MAX_PEERS; ++p)
+    if (p < dp.world && p != dp.rank) w[p] = dp_load(in + (size_t)p * 2 * stride);
   float g = 0.f;
-  for (int p = 0; p < dp.world; ++p)
-    g += p == dp.rank ? mine : dp_pull(reinterpret_cast<const uint2*>(dp.inbox[dp.rank]) + (size_t)p * 2 * stride + par, epoch);
+#pragma unroll
+  for (int p = 0; p < DMVAE_MAX_PEERS; ++p) {
+    if (p >= dp.world) break;
+    if (p == dp.rank) { g += mine; continue; }
+    while (w[p].y != epoch) w[p] = dp_load(in + (size_t)p * 2 * stride);
+    g += __uint_as_float(w[p].x);
+  }
   return g;
 }
 
