@@ -105,6 +105,10 @@ struct Layout {
   int Lp8;           // L rounded up to 8 (K granularity of a TF32 MMA)
   int Lp16;          // L rounded up to 16 (N granularity of an M = 128 MMA)
   int NH;            // 2L padded to 16, 32, 64 or 128: width of the heads layer on the tensor cores
+  // trajectories longer than 128 floats (NC > 1): generation still runs on the tensor cores; the last decoder layer
+  // is cut into NC64 chunks of 64 outputs, each with its own forward image (high plane, then low plane, 8192
+  // floats each: [k-step][k-chunk of 4][n-group of 8][8 n][4 k] with N = 64, no bias row)
+  int NC64, d3c_off;
   TcLayer tc[NUM_TC];
   int slot_off[NUM_SLOTS];  // float offset of a stash slot inside a tile's stash
   int slot_w[NUM_SLOTS];    // features per row of the slot in memory (multiple of 32)
@@ -170,7 +174,8 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   for (int t = 0; t < NUM_TC; ++t) {
     TcLayer& c = l.tc[t];
     c.K = H; c.N = H;
-    if (l.NC > 1) {  // the tensor-core kernels cover I <= 128 only: no images
+    if (l.NC > 1 && (t == TC_ENC0 || t == TC_ENC1 || t == TC_ENC2 || t == TC_ENC3 || t == TC_HEADS || t == TC_DEC3)) {
+      // long trajectories train on the FFMA kernels (no encoder / heads images); dec3 is chunked (below)
       c.K = 0; c.Kb = 0; c.N = 16; c.kps = 32; c.off_hi = c.off_lo = q; c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
       continue;
     }
@@ -186,12 +191,19 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
     c.off_hi = q; q += c.Kb * c.N;
     c.off_lo = q; q += c.Kb * c.N;
     c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
-    if (t != TC_COND0 && t != TC_ENC0) {
+    if (t != TC_COND0 && t != TC_ENC0 && l.NC == 1) {
       c.Kt = (t == TC_DEC0) ? H + round_up(l.L, 32) : c.K;
       c.gsz = c.N / 8 < 4 ? c.N / 8 : 4;
       c.off_thi = q; q += c.Kt * c.N;
       c.off_tlo = q; q += c.Kt * c.N;
     }
+  }
+  l.NC64 = (l.I + 63) / 64;
+  l.d3c_off = q;
+  if (l.NC > 1) {
+    TcLayer& c = l.tc[TC_DEC3];
+    c.K = H; c.Kb = 0; c.N = 64; c.kps = 8; c.off_hi = q; c.off_lo = q + 8192;
+    q += l.NC64 * 16384;
   }
   {
     int o = 0;

@@ -25,6 +25,9 @@
 // With a per-row start point the first condition-encoder layer (2 -> 128) is one more tiny MMA
 // over the columns [x0, y0, 1, 0...] (the bias rides on the ones column); with a shared start
 // point the whole condition encoder is folded once per CTA into the bias of dec0.
+// Trajectories longer than 128 floats (3 * seq_len > 128, up to seq_len = 400): the last layer runs as a
+// sequence of N = 64 chunks that alternate between the two halves of the accumulator, so the output warps
+// drain chunk c (bias, start-point add, staging tile, coalesced stores) while the MMAs of chunk c + 1 run.
 #include "dmvae_common.cuh"
 #include "dmvae_tc.cuh"
 
@@ -68,35 +71,45 @@ struct TcOp {
   int kps;      // K steps per stage
   int N;
   int a_col;    // first A column inside the A regions
+  int d_col;    // first accumulator column
 };
 __device__ __forceinline__ TcOp tc_op(const TcLayer& c, int k0, int ksteps, int a_col) {
-  return TcOp{c.off_hi, c.off_lo, k0, ksteps, c.kps, c.N, a_col};
+  return TcOp{c.off_hi, c.off_lo, k0, ksteps, c.kps, c.N, a_col, 0};
 }
 // shared start:  dec0 (latent rows only) -> dec1 -> dec2 -> dec3
 // per-row start: cond0 -> cond1 -> dec0 -> dec1 -> dec2 -> dec3
-__device__ __forceinline__ int tc_program(const Layout& lo, bool shared_start, TcOp (&ops)[TC_MAX_OPS]) {
-  int n = 0;
-  if (shared_start) {  // skip the K steps of dec0's h_c rows
-    ops[n++] = tc_op(lo.tc[TC_DEC0], H / 8, lo.Lp8 / 8, (int)TM_Z);
-  } else {
-    ops[n++] = tc_op(lo.tc[TC_COND0], 0, 1, (int)TM_Z + lo.Lp8);
-    ops[n++] = tc_op(lo.tc[TC_COND1], 0, H / 8, 0);
-    ops[n++] = tc_op(lo.tc[TC_DEC0], 0, (H + lo.Lp8) / 8, 0);
+// long trajectories: dec3 = NC64 ops of 64 outputs each, on alternating halves of the accumulator
+__device__ __forceinline__ int tc_hidden_ops(bool shared_start) { return shared_start ? 3 : 5; }
+__device__ __forceinline__ TcOp tc_get_op(const Layout& lo, bool shared_start, int o) {
+  const int nh = tc_hidden_ops(shared_start);
+  if (o >= nh) {
+    if (lo.NC == 1) return tc_op(lo.tc[TC_DEC3], 0, H / 8, 0);
+    const int c = o - nh;
+    return TcOp{lo.d3c_off + c * 16384, lo.d3c_off + c * 16384 + 8192, 0, H / 8, 8, 64, 0, (c & 1) * 64};
   }
-  ops[n++] = tc_op(lo.tc[TC_DEC1], 0, H / 8, 0);
-  ops[n++] = tc_op(lo.tc[TC_DEC2], 0, H / 8, 0);
-  ops[n++] = tc_op(lo.tc[TC_DEC3], 0, H / 8, 0);
-  return n;
+  if (shared_start) {  // skip the K steps of dec0's h_c rows
+    if (o == 0) return tc_op(lo.tc[TC_DEC0], H / 8, lo.Lp8 / 8, (int)TM_Z);
+    return tc_op(lo.tc[o == 1 ? TC_DEC1 : TC_DEC2], 0, H / 8, 0);
+  }
+  if (o == 0) return tc_op(lo.tc[TC_COND0], 0, 1, (int)TM_Z + lo.Lp8);
+  if (o == 1) return tc_op(lo.tc[TC_COND1], 0, H / 8, 0);
+  if (o == 2) return tc_op(lo.tc[TC_DEC0], 0, (H + lo.Lp8) / 8, 0);
+  return tc_op(lo.tc[o == 3 ? TC_DEC1 : TC_DEC2], 0, H / 8, 0);
 }
 
 struct TcSmem {
-  float *ring, *outs, *bias, *tmp;
-  uint64_t *full, *empty, *d_hid, *d_out, *z_free, *a_ready, *tile_ready;
+  float *ring, *outs, *bias, *tmp, *b3;
+  uint64_t *full, *empty, *d_hid, *d_out, *z_free, *a_ready, *tile_ready, *d_free;
   uint32_t* tmem_slot;
 };
-// bias: one 128-float row per op in program order (the last row = dec3's bias, Ip entries)
+constexpr int TC_CHUNK_LD = 68;   // row stride (floats) of a 128 x 64 output staging tile: conflict-free 128-bit row writes
+// bias: one 128-float row per op in program order (the last row = dec3's bias, Ip entries); b3: dec3's bias of a
+// long trajectory (NC64 * 64 entries); outs: whole output tiles (out_bufs of them), or two chunk staging tiles
+__host__ __device__ inline size_t tc_out_floats(const Layout& lo, int out_bufs) {
+  return lo.NC > 1 ? (size_t)2 * TC_M * TC_CHUNK_LD : (size_t)out_bufs * TC_M * lo.I;
+}
 __host__ __device__ inline size_t tc_smem_floats(const Layout& lo, int stages, int out_bufs) {
-  return (size_t)stages * STAGE_FLOATS + (size_t)out_bufs * TC_M * lo.I + TC_MAX_OPS * H + 2 * H;
+  return (size_t)stages * STAGE_FLOATS + tc_out_floats(lo, out_bufs) + TC_MAX_OPS * H + 2 * H + (lo.NC > 1 ? lo.NC64 * 64 : 0);
 }
 __host__ __device__ inline size_t tc_smem_bytes(const Layout& lo, int stages, int out_bufs) {
   return tc_smem_floats(lo, stages, out_bufs) * 4 + 32 * 8 + 16 + 1024;
@@ -113,16 +126,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
     s.ring = reinterpret_cast<float*>(p);
     s.outs = s.ring + (size_t)a.stages * STAGE_FLOATS;
-    s.bias = s.outs + (size_t)a.out_bufs * TC_M * I;
+    s.bias = s.outs + tc_out_floats(lo, a.out_bufs);
     s.tmp = s.bias + TC_MAX_OPS * H;
-    s.full = reinterpret_cast<uint64_t*>(s.tmp + 2 * H);
+    s.b3 = s.tmp + 2 * H;
+    s.full = reinterpret_cast<uint64_t*>(s.b3 + (lo.NC > 1 ? lo.NC64 * 64 : 0));
     s.empty = s.full + 8;
     s.d_hid = s.empty + 8;
-    s.d_out = s.d_hid + 1;
-    s.z_free = s.d_out + 1;
+    s.d_out = s.d_hid + 1;        // [2]: long trajectories signal the two halves of the accumulator separately
+    s.z_free = s.d_out + 2;
     s.a_ready = s.z_free + 1;
     s.tile_ready = s.a_ready + 1;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(s.tile_ready + 1);
+    s.d_free = s.tile_ready + 1;  // [2]: output warps -> MMA, half of the accumulator drained (long trajectories)
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.d_free + 2);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
@@ -139,7 +154,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     // d_out  MMA -> output warps (last layer), z_free  MMA -> output warps (latent columns read),
     // a_ready  hidden warps -> MMA,  tile_ready  output warps -> MMA.
     mbar_init(s.d_hid, 1);
-    mbar_init(s.d_out, 1);
+    mbar_init(&s.d_out[0], 1);
+    mbar_init(&s.d_out[1], 1);
+    mbar_init(&s.d_free[0], TC_OUT_WARPS);
+    mbar_init(&s.d_free[1], TC_OUT_WARPS);
     mbar_init(s.z_free, 1);
     mbar_init(s.a_ready, TC_EPI_WARPS);
     mbar_init(s.tile_ready, TC_OUT_WARPS);
@@ -151,8 +169,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *s.tmem_slot;
 
-  TcOp ops[TC_MAX_OPS];
-  const int n_ops = tc_program(lo, shared_start, ops);
+  const int n_hidden = tc_hidden_ops(shared_start);
+  const bool chunked = lo.NC > 1;
+  const int n_last = chunked ? lo.NC64 : 1;        // ops of the last layer
+  const int n_ops = n_hidden + n_last;
   const int zop = shared_start ? 0 : 2;  // the op that reads the staged latent columns last (dec0)
 
   if (warp == TC_PRODUCER_WARP) {
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       RingStateRt rs(a.stages);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int o = 0; o < n_ops; ++o) {
-          const TcOp op = ops[o];
+          const TcOp op = tc_get_op(lo, shared_start, o);
           for (int k0 = 0; k0 < op.ksteps; k0 += op.kps) {
             const int nks = min(op.kps, op.ksteps - k0);
             const int fl = nks * op.N * 8;                       // floats per plane
@@ -180,23 +200,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     // The whole warp walks the program convergently so that every operand of tcgen05.mma is
     // warp-uniform (uniform registers, no per-thread fix-up code); one elected lane issues.
     RingStateRt rs(a.stages);
-    uint32_t a_phase = 0, t_phase = 0;
+    uint32_t a_phase = 0, t_phase = 0, f_phase[2] = {0u, 0u};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int o = 0; o < n_ops; ++o) {
-        const TcOp op = ops[o];
+        const TcOp op = tc_get_op(lo, shared_start, o);
         const uint32_t idesc = umma_idesc_tf32(TC_M, op.N);
         const uint32_t kstep_bytes = (uint32_t)op.N * 32u;  // one 8-deep K step of B: N x 8 TF32
         const uint64_t desc_hi_bits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
+        const int chunk = o - n_hidden;   // >= 0: an op of the last layer
         if (o == 0) {  // latents / start points of this tile staged, D of the previous tile drained
           mbar_wait(s.tile_ready, t_phase);
           t_phase ^= 1u;
-        } else {       // the previous layer's output is in A
+        } else if (chunk <= 0) {       // the previous layer's output is in A
           mbar_wait(s.a_ready, a_phase);
           a_phase ^= 1u;
         }
+        if (chunked && chunk >= 2) {   // this half of the accumulator was last written by chunk - 2: drained?
+          mbar_wait(&s.d_free[chunk & 1], f_phase[chunk & 1]);
+          f_phase[chunk & 1] ^= 1u;
+        }
         tc_fence_after();
         const long long tix = (tile - blockIdx.x) / gridDim.x;
-        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tix < 4 && lane == 0;
+        const bool tr = a.trace != nullptr && blockIdx.x == 0 && tix < 4 && lane == 0 && o < 8;
         if (tr) a.trace[(tix * 8 + o) * 4 + 0] = clock64();
         uint32_t acc = 0;
         uint32_t a_hi = tmem + TM_AHI + (uint32_t)op.a_col, a_lo = tmem + TM_ALO + (uint32_t)op.a_col;
@@ -211,9 +236,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
           if (elect_one()) {
 #pragma unroll 4
             for (int ks = 0; ks < nks; ++ks) {
-              umma_tf32_ts(tmem + TM_D, a_hi, dh, idesc, acc);   // a_hi * b_hi
-              umma_tf32_ts(tmem + TM_D, a_lo, dh, idesc, 1u);    // a_lo * b_hi
-              umma_tf32_ts(tmem + TM_D, a_hi, dl, idesc, 1u);    // a_hi * b_lo
+              umma_tf32_ts(tmem + TM_D + (uint32_t)op.d_col, a_hi, dh, idesc, acc);   // a_hi * b_hi
+              umma_tf32_ts(tmem + TM_D + (uint32_t)op.d_col, a_lo, dh, idesc, 1u);    // a_lo * b_hi
+              umma_tf32_ts(tmem + TM_D + (uint32_t)op.d_col, a_hi, dl, idesc, 1u);    // a_hi * b_lo
               acc = 1u;
               a_hi += 8u; a_lo += 8u; dh += dinc; dl += dinc;
             }
@@ -227,7 +252,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
         }
         if (elect_one()) {
           if (o == zop) umma_commit(s.z_free);                       // the staged columns have been read
-          umma_commit(o == n_ops - 1 ? s.d_out : s.d_hid);           // accumulator complete -> epilogue
+          // accumulator (or, for a chunk, its half) complete -> epilogue
+          umma_commit(chunk < 0 ? s.d_hid : &s.d_out[chunked ? (chunk & 1) : 0]);
         }
         __syncwarp();
         if (tr) a.trace[(tix * 8 + o) * 4 + 1] = clock64();
@@ -249,6 +275,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       s.bias[r++ * H + i] = pk[lo.q_b[L_DEC2] + i];
       s.bias[r++ * H + i] = i < lo.Ip ? pk[lo.q_b[L_DEC3] + i] : 0.f;
     }
+    if (chunked)
+      for (int i = tid; i < lo.NC64 * 64; i += TC_EPI_THREADS) s.b3[i] = i < I ? pk[lo.q_b[L_DEC3] + i] : 0.f;
     if (shared_start) {
       // one start point for the whole launch: condition encoder once per CTA, folded into
       // the bias of dec0:  hb[n] = b_dec0[n] + sum_k Wdec0[n][L+k] * h_c[k]
@@ -281,7 +309,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
 
     uint32_t d_phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int o = 0; o < n_ops - 1; ++o) {
+      for (int o = 0; o < n_hidden; ++o) {
         const float* __restrict__ bias = s.bias + o * H + h * 64;
         mbar_wait(s.d_hid, d_phase);
         d_phase ^= 1u;
@@ -365,10 +393,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     };
 
     asm volatile("bar.sync 4, %0;" ::"n"(TC_EPI_THREADS + TC_OUT_THREADS) : "memory");  // bias rows are in smem
-    const float* __restrict__ b3 = s.bias + (n_ops - 1) * H;
+    const float* __restrict__ b3 = chunked ? s.b3 : s.bias + n_hidden * H;
     // start-point add per column class n % 3 (0: time, 1: x, 2: y), Tools.py:61-63
-    uint32_t d_phase = 0;
+    uint32_t d_phase = 0, dc_phase[2] = {0u, 0u};
     int out_buf = 0;
+    unsigned int gchunk = 0;   // chunks drained so far (long trajectories): parity = staging tile in use
     stage_tile(blockIdx.x);
     sx_cur = sx_nxt; sy_cur = sy_nxt;
     release_tile();
@@ -380,6 +409,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       if (next < n_tiles) {          // stage the next tile while the hidden layers run
         tc_fence_after();
         stage_tile(next);
+      }
+      if (chunked) {
+        // ---- long trajectory: the last layer arrives as NC64 chunks of 64 columns on alternating halves of D
+        d_phase ^= 1u;
+        const float add1 = a.add_start ? sx_cur : 0.f, add2 = a.add_start ? sy_cur : 0.f;
+        float* gdst = a.out + m0 * I;
+        for (int c = 0; c < lo.NC64; ++c, ++gchunk) {
+          const int half = c & 1;
+          mbar_wait(&s.d_out[half], dc_phase[half]);
+          dc_phase[half] ^= 1u;
+          tc_fence_after();
+          float* tile_st = s.outs + (size_t)(gchunk & 1u) * TC_M * TC_CHUNK_LD;
+          float* st = tile_st + m * TC_CHUNK_LD;
+          const int nb = c * 64;
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {   // 32 columns at a time (register budget)
+            uint32_t o[2][16];
+            tmem_ld16(lane_base + TM_D + half * 64 + hf * 32, o[0]);
+            tmem_ld16(lane_base + TM_D + half * 64 + hf * 32 + 16, o[1]);
+            tmem_ld_wait();
+            if (hf == 1) {
+              // this half of D is in registers: chunk c + 2 (or the next tile) may overwrite it
+              if (c + 2 < lo.NC64) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.d_free[half]);
+              }
+              if (c == lo.NC64 - 1) release_tile();
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const int n0 = nb + hf * 32 + cc * 16;
+              const int r0 = n0 % 3;
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                float v4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int j = j4 * 4 + i;
+                  const int d = (r0 + j) % 3;
+                  const float rel = __uint_as_float(o[cc][j]) + b3[n0 + j];
+                  v4[i] = rel + (d == 0 ? 0.f : (d == 1 ? add1 : add2));
+                }
+                *reinterpret_cast<float4*>(st + hf * 32 + cc * 16 + j4 * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+              }
+            }
+          }
+          out_sync();   // the staging tile is complete; the other one may still be read by slower threads
+          const int ncol = min(64, I - nb);
+          for (int idx = otid; idx < TC_M * 64; idx += TC_OUT_THREADS) {   // 32 lanes = 128 contiguous bytes of a row
+            const int row = idx >> 6, col = idx & 63;
+            if (row < valid && col < ncol) gdst[(size_t)row * I + nb + col] = tile_st[row * TC_CHUNK_LD + col];
+          }
+        }
+        sx_cur = sx_nxt; sy_cur = sy_nxt;
+        continue;
       }
       mbar_wait(s.d_out, d_phase);
       d_phase ^= 1u;
@@ -450,7 +535,6 @@ void set_decode_tc_trace(long long* p) { g_tc_trace = p; }
 
 // false when the configuration needs more spare A columns than tensor memory has
 bool decode_tc_supported(const Layout& lo, bool shared_start) {
-  if (lo.NC > 1) return false;   // trajectories longer than 128 floats decode on the FFMA kernel
   return shared_start ? lo.Lp8 <= 64 : lo.Lp8 + 8 <= 64;
 }
 

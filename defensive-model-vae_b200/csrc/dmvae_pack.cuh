@@ -77,7 +77,7 @@ __host__ __device__ inline float tc_weight(const Layout& lo, const float* __rest
 }
 
 // The arena is cut into segments (one per image / bias row); element idx of a segment:
-enum PackSeg { PS_FW = 0, PS_FB, PS_RW, PS_RW_HEADS, PS_RW_DEC0C, PS_RW_DEC0Z, PS_TC, PS_TT };
+enum PackSeg { PS_FW = 0, PS_FB, PS_RW, PS_RW_HEADS, PS_RW_DEC0C, PS_RW_DEC0Z, PS_TC, PS_TT, PS_D3C };
 
 // index of (k, n) inside a tensor-core forward plane: [k-step][k-chunk of 4][n-group of 8][8 n][4 k]
 __host__ __device__ inline int tc_plane_index(const TcLayer& c, int k, int n) {
@@ -134,6 +134,19 @@ __host__ __device__ inline void pack_element(const Layout& lo, int type, int l, 
       q[c.off_lo + idx] = tf32_rn(w - hi);
       break;
     }
+    case PS_D3C: {
+      // last decoder layer of a long trajectory: one N = 64 forward image per chunk of 64 outputs, high plane
+      // (8192 floats) then low plane
+      const int c = idx >> 13, r = idx & 8191;
+      const int ks = r >> 9, r3 = r & 511, kc = r3 >> 8, r4 = r3 & 255;
+      const int n = c * 64 + (r4 >> 5) * 8 + ((r4 & 31) >> 2);
+      const int k = ks * 8 + kc * 4 + (r4 & 3);
+      const float w = n < lo.I ? p[lo.p_w[L_DEC3] + n * H + k] : 0.f;
+      const float hi = tf32_rn(w);
+      q[lo.d3c_off + c * 16384 + r] = hi;
+      q[lo.d3c_off + c * 16384 + 8192 + r] = tf32_rn(w - hi);
+      break;
+    }
     default: {
       // data-gradient planes: [group of gsz steps of n][slice of 32 k][step][2 atoms][4 n][32 k, 32-byte units
       // swizzled by n % 4]
@@ -177,10 +190,11 @@ inline PackPlan make_pack_plan(const Layout& lo) {
     else if (l == L_DEC0) { add(PS_RW_DEC0C, l, H * H); add(PS_RW_DEC0Z, l, H * lo.Lzp); }
     else add(PS_RW, l, lo.N[l] * lo.K[l]);
   }
-  for (int t = 0; t < NUM_TC && lo.NC == 1; ++t) {
+  for (int t = 0; t < NUM_TC; ++t) {
     add(PS_TC, t, lo.tc[t].Kb * lo.tc[t].N);
     if (lo.tc[t].off_thi >= 0) add(PS_TT, t, lo.tc[t].Kt * lo.tc[t].N);
   }
+  if (lo.NC > 1) add(PS_D3C, 0, lo.NC64 * 8192);
   plan.block0[plan.n] = blocks;
   return plan;
 }
@@ -204,8 +218,8 @@ __host__ __device__ inline void scatter_param(const Layout& lo, int e, float val
   } else {
     is_bias = true; n = e - lo.p_b[l];
   }
-  const bool tc = lo.NC == 1;
   const TcLayer c = lo.tc[l];   // TcId and LayerId enumerate the layers in the same order
+  const bool tc = c.Kb > 0;     // the layer has a tensor-core forward image
   const float hi = tf32_rn(val), lw = tf32_rn(val - hi);
   if (is_bias) {
     // FFMA image: bias row behind the weights (dec3, long trajectories: [chunk][128] = plain index n)
@@ -229,6 +243,12 @@ __host__ __device__ inline void scatter_param(const Layout& lo, int e, float val
     else q[lo.r_w[l] + n * H + (k - lo.L)] = val;
   } else if (lo.r_w[l] >= 0) {
     q[lo.r_w[l] + n * lo.K[l] + k] = val;
+  }
+  if (l == L_DEC3 && lo.NC > 1) {   // chunked N = 64 images of a long trajectory's last layer
+    const int idx = (k >> 3) * 512 + ((k >> 2) & 1) * 256 + ((n & 63) >> 3) * 32 + (n & 7) * 4 + (k & 3);
+    q[lo.d3c_off + (n >> 6) * 16384 + idx] = hi;
+    q[lo.d3c_off + (n >> 6) * 16384 + 8192 + idx] = lw;
+    return;
   }
   if (!tc) return;
   // tensor-core planes; dec0 contracts [h_c ; z]
