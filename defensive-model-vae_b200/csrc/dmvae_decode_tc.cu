@@ -415,6 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
         d_phase ^= 1u;
         const float add1 = a.add_start ? sx_cur : 0.f, add2 = a.add_start ? sy_cur : 0.f;
         float* gdst = a.out + m0 * I;
+        const bool vec_ok = (I & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15u) == 0;
+        const bool vec2_ok = (I & 1) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 7u) == 0;
         for (int c = 0; c < lo.NC64; ++c, ++gchunk) {
           const int half = c & 1;
           mbar_wait(&s.d_out[half], dc_phase[half]);
@@ -441,16 +443,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               const int n0 = nb + hf * 32 + cc * 16;
+              // start-point add per column class n % 3 (0: time, 1: x, 2: y): the three values in the order the
+              // columns of this group of 16 meet them
               const int r0 = n0 % 3;
+              const float p0 = r0 == 0 ? 0.f : (r0 == 1 ? add1 : add2);
+              const float p1 = r0 == 0 ? add1 : (r0 == 1 ? add2 : 0.f);
+              const float p2 = r0 == 0 ? add2 : (r0 == 1 ? 0.f : add1);
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b3 + n0 + j4 * 4);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                 float v4[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int j = j4 * 4 + i;
-                  const int d = (r0 + j) % 3;
-                  const float rel = __uint_as_float(o[cc][j]) + b3[n0 + j];
-                  v4[i] = rel + (d == 0 ? 0.f : (d == 1 ? add1 : add2));
+                  const float rel = __uint_as_float(o[cc][j]) + bb[i];
+                  v4[i] = rel + (j % 3 == 0 ? p0 : (j % 3 == 1 ? p1 : p2));
                 }
                 *reinterpret_cast<float4*>(st + hf * 32 + cc * 16 + j4 * 4) = make_float4(v4[0], v4[1], v4[2], v4[3]);
               }
@@ -458,9 +466,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
           }
           out_sync();   // the staging tile is complete; the other one may still be read by slower threads
           const int ncol = min(64, I - nb);
-          for (int idx = otid; idx < TC_M * 64; idx += TC_OUT_THREADS) {   // 32 lanes = 128 contiguous bytes of a row
-            const int row = idx >> 6, col = idx & 63;
-            if (row < valid && col < ncol) gdst[(size_t)row * I + nb + col] = tile_st[row * TC_CHUNK_LD + col];
+          if (vec_ok && ncol == 64) {   // rows are 16-byte aligned: 128-bit copies, 2 rows x 256 bytes per warp instruction
+            for (int idx = otid; idx < TC_M * 16; idx += TC_OUT_THREADS) {
+              const int row = idx >> 4, c4 = idx & 15;
+              if (row < valid)
+                *reinterpret_cast<float4*>(gdst + (size_t)row * I + nb + c4 * 4) =
+                    *reinterpret_cast<const float4*>(tile_st + row * TC_CHUNK_LD + c4 * 4);
+            }
+          } else if (vec2_ok && (ncol & 1) == 0) {   // rows are 8-byte aligned: 64-bit copies
+            for (int idx = otid; idx < TC_M * 32; idx += TC_OUT_THREADS) {
+              const int row = idx >> 5, c2 = idx & 31;
+              if (row < valid && c2 * 2 < ncol)
+                *reinterpret_cast<float2*>(gdst + (size_t)row * I + nb + c2 * 2) =
+                    *reinterpret_cast<const float2*>(tile_st + row * TC_CHUNK_LD + c2 * 2);
+            }
+          } else {
+            for (int idx = otid; idx < TC_M * 64; idx += TC_OUT_THREADS) {   // 32 lanes = 128 contiguous bytes of a row
+              const int row = idx >> 6, col = idx & 63;
+              if (row < valid && col < ncol) gdst[(size_t)row * I + nb + col] = tile_st[row * TC_CHUNK_LD + col];
+            }
           }
         }
         sx_cur = sx_nxt; sy_cur = sy_nxt;

@@ -21,9 +21,9 @@
  *     DMVAE_ERR_DEVICE.  There is no CPU path.
  *
  * Shape envelope: dim == 3, hidden_dim == 128,
- * 1 <= latent_dim <= 64, 2 <= seq_len <= 400.  Inside it the tensor-core kernels cover
- * 3*seq_len <= 128 (generation) and 3*seq_len <= 64, latent_dim <= 16 (training); the rest runs on the
- * FP32 FFMA kernels behind the same entry points.
+ * 1 <= latent_dim <= 64, 2 <= seq_len <= 400.  Inside it the tensor-core kernels cover all of
+ * generation (latent_dim <= 56 with a per-row start point) and 3*seq_len <= 64, latent_dim <= 16 for
+ * training; the rest runs on the FP32 FFMA kernels behind the same entry points.
  */
 #ifndef DMVAE_H_
 #define DMVAE_H_
