@@ -323,7 +323,7 @@ int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world) {
   const int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
   if (world < 1 || world > DMVAE_MAX_PEERS) return fail(DMVAE_ERR_ARG, "dp_inbox_bytes: 1..%d ranks", DMVAE_MAX_PEERS);
-  return (int64_t)world * 2 * dmvae::dp_exchange_stride(lo) * 8;   // [source][parity][stride] x {value, step}
+  return (int64_t)(world + 1) * 2 * dmvae::dp_exchange_stride(lo) * 8;   // [source | sum][parity][stride] x {value, step}
 }
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
                         const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
@@ -484,6 +484,12 @@ int dmvae_set_train_impl(int impl) {
     return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (tensor cores), 1 (FFMA) or 2 (tensor cores, always two launches)");
   g_train_impl.store(impl == 1 ? 1 : 0);
   if (impl != 1) dmvae::set_train_tc_overlap(impl == 0);
+  return DMVAE_OK;
+}
+
+int dmvae_set_dp_owned_from(int world) {
+  if (world < 2 || world > DMVAE_MAX_PEERS + 1) return fail(DMVAE_ERR_ARG, "set_dp_owned_from: 2..%d", DMVAE_MAX_PEERS + 1);
+  dmvae::set_dp_owned_from(world);
   return DMVAE_OK;
 }
 

@@ -77,6 +77,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream);
 cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* slabs,
                                      float* loss_part, int* flags, cudaStream_t stream);
+void set_dp_owned_from(int world);   // data-parallel exchange: world sizes from here on use the owner scheme
 void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (measurement / debugging)
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,

@@ -1415,13 +1415,14 @@ struct ReduceTcArgs {
   // slab sum and the update (dp_all_sum)
   DmvaeDpPeers dp;
   int dp_stride;
+  int dp_owned_from;         // smallest world size that uses the owner scheme of dp_all_sum (default 3)
   unsigned int epoch_host;   // the step index when there is no device-side counter
   long long* trace;          // development aid: %globaltimer stamps of block 0 (slots 230..)
 };
 
 // Data-parallel exchange, "low-latency" style: a gradient travels as one 8-byte word {value bits, step index}
 // written straight into the peer's inbox (a single NVLink store, atomic at that size), so the receiver polls the
-// word itself and no fence or separate flag is needed.  Inbox of a rank: [source rank][step parity][dp_stride] words.
+// word itself and no fence or separate flag is needed.
 __device__ __forceinline__ void dp_push(uint2* dst, float v, unsigned int epoch) {
   asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
@@ -1430,14 +1431,29 @@ __device__ __forceinline__ uint2 dp_load(const uint2* src) {
   asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
   return w;
 }
-// sum of `mine` over the ranks, in rank order (the same values in the same order on every rank: the replicas stay
-// bit-identical without a broadcast); idx = element index inside the exchange
-__device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, int idx, float mine, unsigned int epoch) {
+// Sum of `mine` over the ranks; idx = element index inside the exchange.  Every rank receives the same bits.
+//   up to 2 ranks (world < owned_from): every rank pushes its word to every peer and adds the ranks in rank order (one NVLink hop);
+//   more ranks:    an element has an owner ((idx / 256) mod world, i.e. block-wise round robin).  The others push
+//                  their word to the owner only; the owner adds the ranks in rank order and pushes the sum to
+//                  everyone's sum area.  Two hops, but (world + 6) / 8 MB instead of (world - 1) MB out of every
+//                  rank per step - at 8 GPUs the all-to-all version spent ~20 us per step on it.
+// Inbox of a rank: [source rank 0..world-1][step parity][dp_stride] words, then [sum][step parity][dp_stride].
+__device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, int idx, float mine, unsigned int epoch,
+                                            int owned_from) {
   const size_t par = (size_t)(epoch & 1u) * stride + idx;
-  for (int p = 0; p < dp.world; ++p)
-    if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
-  // all peers' words are requested at once (independent loads), then those that had not arrived yet are polled
   const uint2* in = reinterpret_cast<const uint2*>(dp.inbox[dp.rank]) + par;
+  const int owner = dp.world < owned_from ? -1 : (idx >> 8) % dp.world;
+  if (owner >= 0 && owner != dp.rank) {
+    dp_push(reinterpret_cast<uint2*>(dp.inbox[owner]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+    const uint2* sum_in = in + (size_t)dp.world * 2 * stride;
+    uint2 w = dp_load(sum_in);
+    while (w.y != epoch) w = dp_load(sum_in);
+    return __uint_as_float(w.x);
+  }
+  if (owner < 0)
+    for (int p = 0; p < dp.world; ++p)
+      if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+  // all peers' words are requested at once (independent loads), then those that had not arrived yet are polled
   uint2 w[DMVAE_MAX_PEERS];
 #pragma unroll
   for (int p = 0; p < DMVAE_MAX_PEERS; ++p)
@@ -1450,6 +1466,9 @@ __device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, 
     while (w[p].y != epoch) w[p] = dp_load(in + (size_t)p * 2 * stride);
     g += __uint_as_float(w[p].x);
   }
+  if (owner >= 0)
+    for (int p = 0; p < dp.world; ++p)
+      if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.world * 2 * stride + par, g, epoch);
   return g;
 }
 
@@ -1486,7 +1505,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
 #pragma unroll 8
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
     if (tr) r.trace[231] = global_ns();
-    if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s);
+    if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s, r.dp_owned_from);
     if (tr) r.trace[233] = global_ns() + (long long)(s == 123.456f);
   }
   if (e < r.n_params) {
@@ -1537,7 +1556,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     float val = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) val = lane == i ? mine[i] : val;
-    if (dp_on && lane < 5) val = dp_all_sum(r.dp, r.dp_stride, r.n_params + lane, val, epoch_s);   // the global batch's
+    if (dp_on && lane < 5) val = dp_all_sum(r.dp, r.dp_stride, r.n_params + lane, val, epoch_s, r.dp_owned_from);   // the global batch's
     if (lane < 5) grads[r.n_params + lane] = val;
   }
 }
@@ -1550,6 +1569,8 @@ bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && 
 
 static long long* g_chain_trace = nullptr;
 void set_chain_trace(long long* p) { g_chain_trace = p; }
+static int g_dp_owned_from = 3;
+void set_dp_owned_from(int world) { g_dp_owned_from = world; }
 static bool g_tc_overlap = true;
 void set_train_tc_overlap(bool on) { g_tc_overlap = on; }
 
@@ -1685,6 +1706,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
   if (dp != nullptr) r.dp = *dp;
   else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
   r.dp_stride = dp_exchange_stride(lo);
+  r.dp_owned_from = g_dp_owned_from;
   r.epoch_host = adam != nullptr ? (unsigned int)adam->step : 0u;
   r.trace = g_chain_trace;
   r.packed = adam != nullptr ? packed : nullptr;

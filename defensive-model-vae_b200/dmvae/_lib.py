@@ -63,6 +63,7 @@ SIGNATURES = {
                                         c_float, c_int64, _P, _P, _P]),
     "dmvae_adam_step_dev": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P, _P]),
     "dmvae_dp_inbox_bytes": (c_int64, [_CFG, c_int]),
+    "dmvae_set_dp_owned_from": (c_int, [c_int]),
     "dmvae_train_step_dp": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                     c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, POINTER(DmvaeDpPeers), _P]),
     "dmvae_adam_step": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P]),

@@ -192,14 +192,18 @@ int dmvae_adam_step_dev(const DmvaeCfg* cfg, float* params, const float* grads, 
 /* The whole data-parallel step without a library collective (replaces loss.backward() + the gradient
  * all-reduce the north star adds + optimizer.step(), Training_VAE.py:351-363): the fused pass on this rank's
  * rows (inv_batch = 1 / global batch), then ONE kernel in which every thread sums the partial slabs of its
- * gradient, writes {value, step index} as one 8-byte word into every peer's inbox over NVLink, polls its own
- * inbox for the peers' words of the same step, adds the ranks in rank order (bit-identical replicas, no
- * broadcast), applies Adam and refreshes `packed`.  No fence, flag, grid-wide or job-wide barrier.  grads
+ * gradient, writes {value, step index} as one 8-byte word into its peers' inboxes over NVLink, polls its own
+ * inbox for the words of the same step, adds the ranks in rank order (up to 2 ranks: everybody adds; more:
+ * the element's owner adds and pushes the sum to all - bit-identical replicas either way), applies Adam
+ * and refreshes `packed`.  No fence, flag, grid-wide or job-wide barrier.  grads
  * receives the global gradient and the five loss terms of the global batch.  step_dev may be NULL
  * (host-driven: the step is adam->step) or the device-side counter of dmvae_train_step_dev
  * (graph-capturable).  The inbox is double-buffered by step parity and every word carries its step, so
  * steps need no reset; all ranks must call with the same step.  Tensor-core path only. */
 int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world);
+/* Smallest world size that exchanges through element owners (default 3; 2 forces the owner scheme on two
+ * ranks, DMVAE_MAX_PEERS + 1 the all-to-all scheme everywhere).  All ranks must agree. */
+int dmvae_set_dp_owned_from(int world);
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
                         const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                         const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,

@@ -66,7 +66,7 @@ def test_host_side_queries(lib):
     assert lib.dmvae_param_count(ctypes.byref(cfg)) == 128942          # T = 10, L = 8
     assert lib.dmvae_grad_count(ctypes.byref(cfg)) == 128942 + 5
     assert lib.dmvae_packed_count(ctypes.byref(cfg)) > 128942
-    assert lib.dmvae_dp_inbox_bytes(ctypes.byref(cfg), 8) == 8 * 2 * 128948 * 8
+    assert lib.dmvae_dp_inbox_bytes(ctypes.byref(cfg), 8) == (8 + 1) * 2 * 128948 * 8
     cfg400 = _lib.cfg(400, 64)
     assert lib.dmvae_grad_count(ctypes.byref(cfg400)) == 465589        # T = 400, L = 64 (+ 5 loss terms)
     bad = _lib.cfg(401, 8)

@@ -129,6 +129,10 @@ def _nccl_graph_worker(rank, world, port, tmp, exchange):
     from dmvae.parallel import DataParallelTrainer, init_distributed, shard_range
     from dmvae.train import FusedTrainer
     init_distributed("nccl")
+    if exchange == "peer-owned":
+        from dmvae import _lib
+        _lib.check(_lib.lib().dmvae_set_dp_owned_from(2), "dmvae_set_dp_owned_from")
+        exchange = "peer"
     B, steps = 2048, 4
     batches = [_batch(B, 20 + s) for s in range(steps)]
     lo, hi = shard_range(B, rank, world)
@@ -167,8 +171,9 @@ def _nccl_graph_worker(rank, world, port, tmp, exchange):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+@pytest.mark.parametrize("exchange", ["peer", "peer-owned", "nccl"])
 def test_nccl_graph_step_matches_host_driven_step(tmp_path, exchange):
+    """"peer-owned": the owner scheme of the exchange (the default from 3 ranks on) forced onto two ranks."""
     port = _free_port()
     mp.spawn(_nccl_graph_worker, args=(2, port, str(tmp_path), exchange), nprocs=2, join=True)
     assert os.path.isfile(os.path.join(tmp_path, "ok"))
