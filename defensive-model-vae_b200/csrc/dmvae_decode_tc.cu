@@ -80,10 +80,11 @@ __device__ __forceinline__ TcOp tc_op(const TcLayer& c, int k0, int ksteps, int 
 // per-row start: cond0 -> cond1 -> dec0 -> dec1 -> dec2 -> dec3
 // long trajectories: dec3 = NC64 ops of 64 outputs each, on alternating halves of the accumulator
 __device__ __forceinline__ int tc_hidden_ops(bool shared_start) { return shared_start ? 3 : 5; }
+template <bool kChunked>
 __device__ __forceinline__ TcOp tc_get_op(const Layout& lo, bool shared_start, int o) {
   const int nh = tc_hidden_ops(shared_start);
   if (o >= nh) {
-    if (lo.NC == 1) return tc_op(lo.tc[TC_DEC3], 0, H / 8, 0);
+    if (!kChunked) return tc_op(lo.tc[TC_DEC3], 0, H / 8, 0);
     const int c = o - nh;
     return TcOp{lo.d3c_off + c * 16384, lo.d3c_off + c * 16384 + 8192, 0, H / 8, 8, 64, 0, (c & 1) * 64};
   }
@@ -115,6 +116,9 @@ __host__ __device__ inline size_t tc_smem_bytes(const Layout& lo, int stages, in
   return tc_smem_floats(lo, stages, out_bufs) * 4 + 32 * 8 + 16 + 1024;
 }
 
+// kChunked: long trajectories (lo.NC > 1); a separate instantiation keeps the short-trajectory kernel free of the
+// chunk path's registers
+template <bool kChunked>
 __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ unsigned char smem_dyn[];
   const Layout& lo = a.lo;
@@ -170,7 +174,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
   const uint32_t tmem = *s.tmem_slot;
 
   const int n_hidden = tc_hidden_ops(shared_start);
-  const bool chunked = lo.NC > 1;
+  constexpr bool chunked = kChunked;
+  // the hidden layers' ops (and the single last-layer op of a short trajectory) are built once; the chunk ops of a
+  // long trajectory are derived from the chunk index
+  TcOp ops_fixed[TC_MAX_OPS];
+  for (int o = 0; o < TC_MAX_OPS; ++o) ops_fixed[o] = tc_get_op<kChunked>(lo, shared_start, o < n_hidden + 1 ? o : n_hidden);
+  auto get_op = [&](int o) -> TcOp { return (!kChunked || o < n_hidden) ? ops_fixed[o] : tc_get_op<kChunked>(lo, shared_start, o); };
   const int n_last = chunked ? lo.NC64 : 1;        // ops of the last layer
   const int n_ops = n_hidden + n_last;
   const int zop = shared_start ? 0 : 2;  // the op that reads the staged latent columns last (dec0)
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
       RingStateRt rs(a.stages);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int o = 0; o < n_ops; ++o) {
-          const TcOp op = tc_get_op(lo, shared_start, o);
+          const TcOp op = get_op(o);
           for (int k0 = 0; k0 < op.ksteps; k0 += op.kps) {
             const int nks = min(op.kps, op.ksteps - k0);
             const int fl = nks * op.N * 8;                       // floats per plane
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_tc_kernel(const __grid_c
     uint32_t a_phase = 0, t_phase = 0, f_phase[2] = {0u, 0u};
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int o = 0; o < n_ops; ++o) {
-        const TcOp op = tc_get_op(lo, shared_start, o);
+        const TcOp op = get_op(o);
         const uint32_t idesc = umma_idesc_tf32(TC_M, op.N);
         const uint32_t kstep_bytes = (uint32_t)op.N * 32u;  // one 8-deep K step of B: N x 8 TF32
         const uint64_t desc_hi_bits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
@@ -582,9 +591,15 @@ cudaError_t launch_decode_tc(const Layout& lo, bool shared_start, const float* p
   const size_t smem = tc_smem_bytes(lo, stages, out_bufs);
   const long long n_tiles = (B + TC_M - 1) / TC_M;
   const int grid = (int)(n_tiles < sm_count ? n_tiles : sm_count);
-  cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  decode_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(a);
+  if (lo.NC > 1) {
+    const cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    decode_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(a);
+  } else {
+    const cudaError_t e = cudaFuncSetAttribute(decode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    decode_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
