@@ -1122,6 +1122,9 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   const uint32_t tmem = *tmem_slot;
   const WOp* ops = a.ops[role];
   const int n_ops = a.n_ops[role];
+  // Next to a running chain (one tile per unit) every op is written out as soon as its own products are complete,
+  // while the CTA waits for the chain to finish the images of its next op; otherwise once per unit.
+  const bool per_op = a.ready != nullptr && ut == 1;
   constexpr int chunks = CH_M / WG_ROWS;  // 8 ring stages per (tile, op)
 
   if (warp == WG_PRODUCER_WARP) {
@@ -1197,50 +1200,31 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           __syncwarp();
           rs.advance();
         }
+        if (per_op) {   // this op's accumulator is final (one tile per unit): the work warps write it out right away
+          if (elect_one()) umma_commit(d_done);
+          __syncwarp();
+        }
       }
       first_tile = false;
      }
-     if (elect_one()) umma_commit(d_done);
-     __syncwarp();
+     if (!per_op) {
+       if (elect_one()) umma_commit(d_done);
+       __syncwarp();
+     }
     }
   } else {
     // ===================== work warps: TF32 split of the raw stages, then the final write-out ======
     RingStateRt rs(WG_STAGES);
     uint32_t done_phase = 0;
-    for (long long unit = my_index; unit < n_units; unit += role_ctas) {
-    for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile)
-      for (int o = 0; o < n_ops; ++o) {
-        const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
-        for (int c = 0; c < chunks; ++c) {
-          float4* st4 = reinterpret_cast<float4*>(ring + rs.stage * WG_STAGE_FLOATS);
-          mbar_wait(&raw_full[rs.stage], rs.phase);
-          for (int i = tid; i < 512 + nB4; i += WG_WORK_THREADS) {
-            const int idx = i;  // A part [0,512), B part [512, 512 + nB4)
-            const float4 x = st4[idx];
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
-            st4[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-            st4[idx + 1024] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
-          }
-          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&split_full[rs.stage]);
-          rs.advance();
-        }
-      }
-
-    // ---- write-out: accumulators -> the unit's partial slab (torch layout of each tensor) ----------
-    mbar_wait(d_done, done_phase);
-    done_phase ^= 1u;
-    tc_fence_after();
-    if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
+    // one op's accumulator -> the unit's partial slab
+    auto write_op = [&](int o, long long unit) {
     const int q = warp & 3, hh = warp >> 2;
     const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     float* slab = a.slabs + (size_t)(a.unit_begin[role] + unit) * a.slab_stride;
     float* stg = wo_stage + warp * (32 * 20);   // this warp's staging tile of the write-out
     const int L = lo.L, I = lo.I;
-    for (int o = 0; o < n_ops; ++o) {
+    {
       const WOp op = ops[o];
       // columns of this op are shared between the two warps of a lane quarter in 16-column chunks
       for (int c = hh; c < op.FB / 16; c += 2) {
@@ -1351,6 +1335,44 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           }
         }
       }
+        }
+    };
+    for (long long unit = my_index; unit < n_units; unit += role_ctas) {
+    for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile)
+      for (int o = 0; o < n_ops; ++o) {
+        const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
+        for (int c = 0; c < chunks; ++c) {
+          float4* st4 = reinterpret_cast<float4*>(ring + rs.stage * WG_STAGE_FLOATS);
+          mbar_wait(&raw_full[rs.stage], rs.phase);
+          for (int i = tid; i < 512 + nB4; i += WG_WORK_THREADS) {
+            const int idx = i;  // A part [0,512), B part [512, 512 + nB4)
+            const float4 x = st4[idx];
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
+            st4[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+            st4[idx + 1024] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_full[rs.stage]);
+          rs.advance();
+        }
+        if (per_op) {
+          mbar_wait(d_done, done_phase);
+          done_phase ^= 1u;
+          tc_fence_after();
+          if (a.trace != nullptr && unit == 0 && tid == 0 && o == n_ops - 1) a.trace[180 + role * 16 + 8] = global_ns();
+          write_op(o, unit);
+        }
+      }
+
+    // ---- write-out: accumulators -> the unit's partial slab (torch layout of each tensor) ----------
+    if (!per_op) {
+      mbar_wait(d_done, done_phase);
+      done_phase ^= 1u;
+      tc_fence_after();
+      if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
+      for (int o = 0; o < n_ops; ++o) write_op(o, unit);
     }
     // accumulators read: the MMA warp may start the next unit
     tc_fence_before();
