@@ -986,6 +986,11 @@ struct WOp {
 
 // Layer groups whose accumulators fit tensor memory together; 128-wide layers are spread so that
 // the MMA time of the roles is comparable.
+// tensor-memory columns of the decoder-side role without enc2: dec3 (+ bias row), dec0 (h_c part + bias column, z part),
+// heads (h_traj part + bias row, h_c part); enc2 needs 128 + 16 more
+__host__ __device__ inline bool wgrad_enc2_in_role2(const Layout& lo) {
+  return 2 * lo.Ip + (H + 16) + lo.Lp16 + 3 * lo.NH + (H + 16) <= 512;
+}
 __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* ops) {
   int n = 0, col = 0;
   auto add = [&](int kind, int sa, int sb, int FB, int bias) {
@@ -997,11 +1002,14 @@ __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* op
     ops[n++] = w;
   };
   // within a role the ops follow the order in which the chain kernel completes their gradient images
-  // (epilogue numbers in c_epi), so that a CTA running next to the chain can start each one early
+  // (epilogue numbers in c_epi), so that a CTA running next to the chain can start each one early.  The late
+  // encoder layers are spread over the roles: enc2 joins the decoder-side role when its accumulator fits there
+  // (that role is otherwise done long before the chain ends), else it stays with enc1.
+  const bool enc2_in_role2 = wgrad_enc2_in_role2(lo);
   if (role == 0) {
     add(WK_COND1, SG_HC, SX_HC1, H, 1);       // 16
     add(WK_COND0, SG_HC1, SX_START, 16, 0);   // 17; columns 0, 1 = dW, column 2 = db (the ones column of the start image)
-    add(WK_ENC2, SG_E3, SX_E2, H, 1);         // 19
+    if (!enc2_in_role2) add(WK_ENC2, SG_E3, SX_E2, H, 1);   // 19
     add(WK_ENC1, SG_E2, SX_E1, H, 1);         // 20
   } else if (role == 1) {
     add(WK_DEC2, SG_D3, SX_D2, H, 1);         // 12
@@ -1014,6 +1022,7 @@ __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* op
     add(WK_DEC0_Z, SG_D1, SX_Z, lo.Lp16, 0);
     add(WK_HEADS_E, SX_E4, SG_ML, lo.NH, 2);  // 15; transposed: lanes = input features, columns = (mu, logvar) index
     add(WK_HEADS_C, SX_HC, SG_ML, lo.NH, 0);
+    if (enc2_in_role2) add(WK_ENC2, SG_E3, SX_E2, H, 1);    // 19
   }
   return n;
 }
@@ -1735,7 +1744,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
   r.step_inc = (adam != nullptr && done != nullptr) ? step_inc : nullptr;
   r.done = done;
   // state_dict order: cond0 (w,b) cond1 enc0 enc1 enc2 enc3 fc_mu fc_logvar dec0 dec1 dec2 dec3
-  static const int role_of_pair[12] = {0, 0, 1, 0, 0, 1, 2, 2, 2, 1, 1, 2};
+  const int role_of_pair[12] = {0, 0, 1, 0, wgrad_enc2_in_role2(lo) ? 2 : 0, 1, 2, 2, 2, 1, 1, 2};
   const int w_off[12] = {lo.p_w[L_COND0], lo.p_w[L_COND1], lo.p_w[L_ENC0], lo.p_w[L_ENC1], lo.p_w[L_ENC2], lo.p_w[L_ENC3],
                          lo.p_w[L_HEADS], lo.p_wlv,        lo.p_w[L_DEC0], lo.p_w[L_DEC1], lo.p_w[L_DEC2], lo.p_w[L_DEC3]};
   const int b_off[12] = {lo.p_b[L_COND0], lo.p_b[L_COND1], lo.p_b[L_ENC0], lo.p_b[L_ENC1], lo.p_b[L_ENC2], lo.p_b[L_ENC3],
