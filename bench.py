@@ -94,7 +94,7 @@ def traffic_from_profile(kernel: str):
             text = open(path).read()
         except OSError:
             continue
-        if f"--- {kernel}" not in text and f"--- dmvae::{kernel}" not in text:
+        if not re.search(r"^--- .*\b" + re.escape(kernel) + r"\b", text, flags=re.M):
             continue
         total, seen = 0.0, 0
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
