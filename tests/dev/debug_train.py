@@ -1,6 +1,6 @@
 """Development aid: per-tensor gradient errors of the fused train kernel vs the oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "defensive-model-vae_b200"))
 import numpy as np, torch
 from oracle import vae_oracle as O

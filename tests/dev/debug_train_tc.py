@@ -1,6 +1,6 @@
 """Development aid: the tensor-core training pass stage by stage against the oracle.
 
-    python scripts/debug_train_tc.py [B] [T] [L]
+    python tests/dev/debug_train_tc.py [B] [T] [L]
 
 Runs dmvae_train_fwd_bwd with the tensor-core kernels, reads the stash back from the workspace,
 and reports (1) every stashed layer input X against the oracle's activations, (2) the weight
@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "defensive-model-vae_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
