@@ -1051,6 +1051,10 @@ struct WgradKArgs {
   WgradArgs w;
 };
 
+// pulls a byte range (multiple of 16) into L2 without a destination
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // number of the chain epilogue (c_epi) that completes a stash image
 __device__ inline int slot_epilogue(int slot) {
   if (slot == SX_START) return 0;   // staged before the tile's first epilogue
@@ -1150,6 +1154,22 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           const uint32_t bytesA = WG_ROWS * H * 4, bytesB = (uint32_t)(WG_ROWS * FBm * 4);
           if (a.ready != nullptr) wait_tile_ready(a.ready + tile, max(slot_epilogue(op.slotA), slot_epilogue(op.slotB)));
           if (a.trace != nullptr && tile == 0) a.trace[180 + role * 16 + 1 + o] = global_ns();
+          if (a.ready == nullptr) {
+            // After a chain kernel the stash of a large batch streams from HBM, and six 16-row stages in flight do
+            // not cover that latency: the images of the NEXT op (of this tile, or the first op of the next tile
+            // of this CTA) are pulled into L2 while this op's stages go through the ring.
+            int on = o + 1;
+            long long tn = tile;
+            if (on == n_ops) {
+              on = 0;
+              tn = tile + 1 < min((unit + 1) * ut, a.n_tiles) ? tile + 1 : (unit + role_ctas) * ut;
+            }
+            if (tn < a.n_tiles) {
+              const float* tsn = a.stash + (size_t)tn * lo.tile_stash;
+              l2_prefetch(tsn + lo.slot_off[ops[on].slotA], CH_M * H * 4);
+              l2_prefetch(tsn + lo.slot_off[ops[on].slotB], (uint32_t)(CH_M * lo.slot_w[ops[on].slotB] * 4));
+            }
+          }
           for (int c = 0; c < chunks; ++c) {
             float* dst = ring + rs.stage * WG_STAGE_FLOATS;
             mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
