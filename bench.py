@@ -612,6 +612,8 @@ def run_cuda(args):
 
     peak_ffma = ffma_peak_tflops(lib)
     clk = clocks.stop(t_mark0, time.perf_counter()) if clocks is not None else None
+    # every rank applied the same updates to the same bits (collective: all ranks take part)
+    replicas_identical = dp.parameter_checksum(model.flat_parameters()) if world > 1 else None
 
     def leave():
         """Exit of a multi-rank job: the step graphs hold captured NCCL work and tearing the communicator
@@ -683,6 +685,7 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "losses_after_run": losses_end,
+        "replicas_identical": replicas_identical,
         "decode": {
             "metric": "decoded_trajectories_per_sec", "value": dec_value, "unit": "trajectories/s",
             "config": {"workload": f"configs[2]: 4 scenarios x {R} latents per GPU, in-kernel Philox, shared scenario start, "
