@@ -11,8 +11,9 @@ seq_len 10, latent 8, hidden 128, all four scenarios jointly, batch 4096 per GPU
 gradient buffer per step (weak scaling: 4096 rows per GPU per step).
 
   value      training samples/s, whole job, batches already resident in HBM
-  e2e        the same through the public API with the batch in pinned HOST memory: H2D copy
-             of the batch and a blocking D2H read of the five loss terms inside every step
+  e2e        the same through the public API with the batches in pinned HOST memory: every step
+             uploads its batch (on a copy stream, while the previous step computes) and the host
+             reads its five loss terms before it launches the next step
   roofline   the dominant kernel of the step (chain_kernel: forward + loss + data-gradient
              chain on the tcgen05 tensor cores): its algorithmic FLOP / its live CUDA-event
              duration, against the measured dense bf16 tensor peak of MEASURED_PEAKS.json.
@@ -504,63 +505,90 @@ def run_cuda(args):
                "kernel_us": {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in bprof.items()},
                "step_tflops": Bbig * world * fl["train"] / (big_ms * 1e-3) / 1e12}
 
-    # ---------------------------------------------------------------- e2e (host buffers, per-step blocking loss read)
-    host_batches = [torch.empty(B, T, 3, dtype=torch.float32).pin_memory() for _ in range(8)]
+    # ---------------------------------------------------------------- e2e (host buffers, per-step loss read)
+    # The public API used the way a training loop would use it: two captured steps (GraphStep) with their own device
+    # input buffer and pinned loss slot; the batch of step i + 1 goes host -> device on a copy stream while step i
+    # computes; the five loss terms of every step come back to pinned host memory inside the step's graph.
+    NSLOT = 8
+    host_batches = [torch.empty(B, T, 3, dtype=torch.float32).pin_memory() for _ in range(NSLOT)]
     for j, hb in enumerate(host_batches):
         hb.copy_(data[j * B:(j + 1) * B].cpu())
-    host_losses = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(8)]
-    dbuf = torch.empty(B, T, 3, dtype=torch.float32, device=dev)
-
-    # one graph per pinned host buffer = [H2D of the batch, fused step, D2H of the 5 loss terms into its own slot]
-    e2e_graphs = None
+    host_losses = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    main_stream = torch.cuda.current_stream()
     if gstep is not None:
-        e2e_graphs = [(trainer.capture(B, host_batch=hb, host_losses=hl) if world == 1 else
-                       dp.capture(B, host_batch=hb, host_losses=hl)) for hb, hl in zip(host_batches, host_losses)]
-    done = [torch.cuda.Event() for _ in range(8)]
+        e2e_graphs = [(trainer.capture(B, host_losses=hl) if world == 1 else dp.capture(B, host_losses=hl))
+                      for hl in host_losses]
+        dbufs = [g.batch for g in e2e_graphs]
+    else:
+        e2e_graphs = None
+        dbufs = [torch.empty(B, T, 3, dtype=torch.float32, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]    # batch of the slot is on the device
+    done = [torch.cuda.Event() for _ in range(2)]     # the step of the slot has finished (its device buffer is free again)
+    for ev in done:
+        ev.record(main_stream)
+
+    def e2e_upload(i):        # H2D of the batch of step i from pinned host memory, on the copy stream
+        j = i % 2
+        copy_stream.wait_event(done[j])
+        with torch.cuda.stream(copy_stream):
+            dbufs[j].copy_(host_batches[i % NSLOT], non_blocking=True)
+            ready[j].record(copy_stream)
 
     def e2e_launch(i):
-        j = i % 8
+        j = i % 2
+        main_stream.wait_event(ready[j])
         if e2e_graphs is not None:
             e2e_graphs[j].replay()
         else:
-            dbuf.copy_(host_batches[j], non_blocking=True)
-            losses = trainer.step(dbuf) if world == 1 else dp.step(dbuf)
+            losses = trainer.step(dbufs[j]) if world == 1 else dp.step(dbufs[j])
             host_losses[j].copy_(losses, non_blocking=True)
-        done[j].record()
+        done[j].record(main_stream)
 
     def e2e_read(i):          # the step's result on the host: waits for exactly that step
-        done[i % 8].synchronize()
-        return float(host_losses[i % 8][0])
+        done[i % 2].synchronize()
+        return float(host_losses[i % 2][0])
 
     def run_e2e(mode):
-        """blocking: launch, wait, read, every step (the reference loop's five .item() per step, Training_VAE.py:366-370);
+        """blocking: the host reads the loss of step i before it launches step i + 1 (the reference loop's .item() per
+        step, Training_VAE.py:366-370); the upload of batch i + 1 is already in flight;
         overlapped: the read of step i - 1 follows the launch of step i, so the device never waits for the host;
-        pipelined: every step copies its loss terms to the host, the host synchronises once at the end."""
+        serial: no copy/compute overlap at all - upload, step, read, one after the other."""
         for i in range(W):
+            e2e_upload(i)
             e2e_launch(i)
             e2e_read(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(K):
-            e2e_launch(i)
-            if mode == "blocking":
+        if mode == "serial":
+            for i in range(K):
+                e2e_upload(i)
+                e2e_launch(i)
                 e2e_read(i)
-            elif mode == "overlapped" and i > 0:
-                e2e_read(i - 1)
-        if mode == "overlapped":
-            e2e_read(K - 1)
+        else:
+            e2e_upload(0)
+            for i in range(K):
+                e2e_launch(i)                      # its batch is on the device already
+                if i + 1 < K:
+                    e2e_upload(i + 1)              # issued while step i computes
+                if mode == "blocking":
+                    e2e_read(i)
+                elif i > 0:
+                    e2e_read(i - 1)
+            if mode != "blocking":
+                e2e_read(K - 1)
         barrier()
         return K * Bg / max_over_ranks(time.perf_counter() - t0)
 
-    e2e = {m: run_e2e(m) for m in ("blocking", "overlapped", "pipelined")}
+    e2e = {m: run_e2e(m) for m in ("blocking", "overlapped", "serial")}
     e2e_obj = {"value": e2e["blocking"], "unit": UNIT, "h2d_bytes_per_step": B * T * 3 * 4 * world,
                "d2h_bytes_per_step": 20 * world,
-               "overlapped_value": e2e["overlapped"], "pipelined_value": e2e["pipelined"],
-               "note": "every step: H2D of the batch from pinned host memory + fused step + D2H of the 5 loss terms (host "
-                       "wall clock, max over ranks).  value: the host waits for and reads the loss of step i before it "
-                       "launches step i + 1; overlapped_value: it reads the loss of step i - 1 right after launching "
-                       "step i (every step's loss is read inside the timed region, the device never idles); "
-                       "pipelined_value: one host sync per K steps (the once-per-epoch read of LossMeter)"}
+               "overlapped_value": e2e["overlapped"], "serial_value": e2e["serial"],
+               "note": "every step: H2D of its batch from pinned host memory, the fused step, D2H of its 5 loss terms, "
+                       "all inside the timed region (host wall clock, max over ranks).  value: the host waits for and "
+                       "reads the loss of step i before it launches step i + 1, while the batch of step i + 1 is already "
+                       "being uploaded on a copy stream; overlapped_value: it reads the loss of step i - 1 right after "
+                       "launching step i; serial_value: upload, step and read strictly one after the other"}
 
     # ---------------------------------------------------------------- decode (second half of the metric)
     R = args.decode_rows
