@@ -24,7 +24,7 @@
 //   reduce_tc_kernel  fixed-order sum of the partial slabs (+ the loss partials), optionally with
 //                  the Adam update (torch optim/adam.py::_single_tensor_adam) in the same thread.
 //
-// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 16 (the reference uses 10/12 and 8);
+// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 32 (the reference uses 10/12 and 8);
 // anything else inside the ABI envelope runs the FFMA kernel of dmvae_train.cu.
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
@@ -540,6 +540,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         tmem_st4(lane_base + CT_AHI + 4, 0u, 0u, 0u, 0u);
         tmem_st4(lane_base + CT_ALO, xl, yl, 0u, 0u);
         tmem_st4(lane_base + CT_ALO + 4, 0u, 0u, 0u, 0u);
+        // the constant ones column: with 2 * latent_dim > 56 the (mu, logvar) gradient of the previous tile's backward
+        // half reached into it (the low halves of the extra A columns), so every tile starts by writing it again
+        tmem_st4(lane_base + CT_ONES, __float_as_uint(1.0f), 0u, 0u, 0u);
+        tmem_st4(lane_base + CT_ONES + 4, 0u, 0u, 0u, 0u);
         float* ts = a.stash + (size_t)tile * lo.tile_stash;
         *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
 #pragma unroll
@@ -1615,8 +1619,9 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
 // =========================================================================================
 // host side
 // =========================================================================================
-// the ones column sits in the last 8 extra columns: the widest small operand (NH) must stay below it
-bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && lo.NH <= 32; }
+// the extra A columns (64) hold the widest small operand (NH = 2 * latent_dim padded) and, in their last 8, the ones
+// column, which is rewritten at the start of every tile
+bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && lo.NH <= 64; }
 
 static long long* g_chain_trace = nullptr;
 void set_chain_trace(long long* p) { g_chain_trace = p; }

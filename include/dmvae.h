@@ -22,7 +22,7 @@
  *
  * Shape envelope: dim == 3, hidden_dim == 128,
  * 1 <= latent_dim <= 64, 2 <= seq_len <= 400.  Inside it the tensor-core kernels cover all of
- * generation (latent_dim <= 56 with a per-row start point) and 3*seq_len <= 64, latent_dim <= 16 for
+ * generation (latent_dim <= 56 with a per-row start point) and 3*seq_len <= 64, latent_dim <= 32 for
  * training; the rest runs on the FP32 FFMA kernels behind the same entry points.
  */
 #ifndef DMVAE_H_
@@ -154,7 +154,7 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
 int64_t dmvae_grad_count(const DmvaeCfg* cfg);
 int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
 /* Which kernels the fused training pass launches: 0 (default) = tensor cores (tcgen05, 3xTF32:
- * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 16,
+ * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 32,
  * the FFMA kernels otherwise; 1 = always the FP32 FFMA kernels (train_kernel + reduce_kernel);
  * 2 = tensor cores, always as two launches.  With 0, batches of at most (SMs / 4) * 128 rows run
  * the chain and the weight-gradient CTAs side by side in ONE launch (train_tc_fused_kernel): a

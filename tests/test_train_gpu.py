@@ -2,7 +2,7 @@
 and the reference-generated goldens.
 
 Every fused-pass test runs twice: with the tensor-core kernels (tcgen05, 3xTF32: chain_kernel +
-wgrad_kernel + reduce_tc_kernel; the default wherever 3*seq_len <= 64 and latent_dim <= 16) and with
+wgrad_kernel + reduce_tc_kernel; the default wherever 3*seq_len <= 64 and latent_dim <= 32) and with
 the FP32 FFMA kernels (train_kernel + reduce_kernel).
 
 Tolerances (fp32, summation order differs from ATen's):
@@ -96,6 +96,9 @@ def per_tensor_err(grads, grads_ref):
     (12, 8, 130, O.SCRIPT_WEIGHTS),     # the T=12 checkpoints' shape
     (2, 1, 40, O.SCRIPT_WEIGHTS),       # smallest envelope
     (21, 16, 200, O.DEFAULT_WEIGHTS),   # Ip = 64, L2p = 32
+    (10, 32, 700, O.SCRIPT_WEIGHTS),    # widest heads layer of the tensor-core path (2L = 64), several tiles per CTA path
+    (21, 32, 300, O.DEFAULT_WEIGHTS),   # the same with Ip = 64 (fewer ring stages: no pipelined layers)
+    (10, 24, 20000, O.SCRIPT_WEIGHTS),  # 2L = 48 (padded to 64), more tiles than SMs
     (30, 24, 100, O.SCRIPT_WEIGHTS),    # Ip = 128 (90), L2p = 64
     (42, 64, 70, O.SCRIPT_WEIGHTS),     # largest envelope: Ip = 128, L2p = 128
     (10, 5, 64, (0.3, 0.2, 0.0, 0.0)),  # odd latent (misaligned offsets), zero-weight terms
