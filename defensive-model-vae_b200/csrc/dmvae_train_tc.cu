@@ -727,7 +727,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll
           for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]);
         }
-        for (int jb = 0; jb < Lp16 / 4; ++jb) {
+#pragma unroll 1
+        for (int jb = 0; jb < lo.slot_w[SX_Z] / 4; ++jb) {   // past Lp16 / 4: the zero padding of the stash image
           float e4[4] = {0.f, 0.f, 0.f, 0.f};
           if (row_ok && jb * 4 < L) {
             if (a.eps != nullptr) {
@@ -750,17 +751,18 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               e = e4[i];
               z = my_ml[j * 128] + e * expf(0.5f * my_ml[(L + j) * 128]);
             }
-            my_ep[j * 128] = e;
+            if (j < Lp16) my_ep[j * 128] = e;
             zv[i] = z;
           }
-          uint32_t hi[4], lw[4];
+          if (jb < Lp16 / 4) {
+            uint32_t hi[4], lw[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_tf32(zv[i], hi[i], lw[i]);
-          tmem_st4(lane_base + CT_AHI + CT_X + jb * 4, hi[0], hi[1], hi[2], hi[3]);
-          tmem_st4(lane_base + CT_ALO + CT_X + jb * 4, lw[0], lw[1], lw[2], lw[3]);
+            for (int i = 0; i < 4; ++i) split_tf32(zv[i], hi[i], lw[i]);
+            tmem_st4(lane_base + CT_AHI + CT_X + jb * 4, hi[0], hi[1], hi[2], hi[3]);
+            tmem_st4(lane_base + CT_ALO + CT_X + jb * 4, lw[0], lw[1], lw[2], lw[3]);
+          }
           *stash_ptr(ts, SX_Z, jb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
         }
-        for (int jb = Lp16 / 4; jb < lo.slot_w[SX_Z] / 4; ++jb) *stash_ptr(ts, SX_Z, jb) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -863,46 +865,61 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       //   d/dmu = w_k mu / (B L) + g_z ;  d/dlogvar = -0.5 w_k (1 - e^lv) / (B L) + 0.5 g_z eps e^(lv/2)
       // -> the (mu, logvar) gradient becomes the A operand (extra columns) of the heads' data gradients.
       // The decoder share of d/dhc stays in the main accumulator and is completed by the next op.
+      if (tr_tile && tid == 0) a.trace[240] = clock64();
       wait_d();
+      if (tr_tile && tid == 0) a.trace[241] = clock64();
       if (h == 0) {
         const float c_k = a.w_kld * a.inv_batch / (float)L;
-        for (int c = 0; c < Lp16 / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld16(lane_base + CT_DX + c * 16, v);
+        // Rolled loops with small bodies on purpose: this code runs once per tile, long after its last use, so its
+        // instructions come from L2 every time - the fully unrolled version (600 instructions) spent ~8 000 cycles
+        // here, most of them waiting for instruction fetch.
+#pragma unroll 1
+        for (int jb = 0; jb < (L + 3) / 4; ++jb) {
+          uint32_t v[4];
+          tmem_ld4(lane_base + CT_DX + jb * 4, v);
           tmem_ld_wait();
+          float gm[4], gl[4];
 #pragma unroll
-          for (int j16 = 0; j16 < 16; ++j16) {
-            const int j = c * 16 + j16;
+          for (int i = 0; i < 4; ++i) {
+            const int j = jb * 4 + i;
+            const bool on = j < L && row_ok;
+            const float gz = __uint_as_float(v[i]);
+            const float mu = j < L ? my_ml[j * 128] : 0.f, lv = j < L ? my_ml[(L + j) * 128] : 0.f, ep = j < L ? my_ep[j * 128] : 0.f;
+            const float e_half = expf(0.5f * lv);          // exp(lv) = exp(lv / 2)^2: one exponential per element
+            gm[i] = on ? fmaf(c_k, mu, gz) : 0.f;
+            gl[i] = on ? -0.5f * c_k * (1.f - e_half * e_half) + 0.5f * gz * ep * e_half : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = jb * 4 + i;
             if (j < L) {
-              float gmu = 0.f, glv = 0.f;
-              if (row_ok) {
-                const float gz = __uint_as_float(v[j16]);
-                const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128], ep = my_ep[j * 128];
-                gmu = fmaf(c_k, mu, gz);
-                glv = -0.5f * c_k * (1.f - expf(lv)) + 0.5f * gz * ep * expf(0.5f * lv);
-              }
-              my_ml[j * 128] = gmu;
-              my_ml[(L + j) * 128] = glv;
+              my_ml[j * 128] = gm[i];
+              my_ml[(L + j) * 128] = gl[i];
             }
           }
         }
-        for (int c4 = 0; c4 < NH / 4; ++c4) {
+        if (tr_tile && tid == 0) a.trace[242] = clock64();
+#pragma unroll 1
+        for (int c4 = 0; c4 < lo.slot_w[SG_ML] / 4; ++c4) {   // past NH / 4: the zero padding of the stash image
           float gv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int n = c4 * 4 + i;
             gv[i] = n < 2 * L ? my_ml[n * 128] : 0.f;
           }
-          uint32_t hi[4], lw[4];
+          if (c4 < NH / 4) {
+            uint32_t hi[4], lw[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_tf32(gv[i], hi[i], lw[i]);
-          tmem_st4(lane_base + CT_AHI + CT_X + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
-          tmem_st4(lane_base + CT_ALO + CT_X + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+            for (int i = 0; i < 4; ++i) split_tf32(gv[i], hi[i], lw[i]);
+            tmem_st4(lane_base + CT_AHI + CT_X + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+            tmem_st4(lane_base + CT_ALO + CT_X + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          }
           *stash_ptr(ts, SG_ML, c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
         }
-        for (int c4 = NH / 4; c4 < lo.slot_w[SG_ML] / 4; ++c4) *stash_ptr(ts, SG_ML, c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tr_tile && tid == 0) a.trace[243] = clock64();
       }
       release_a();
+      if (tr_tile && tid == 0) a.trace[245] = clock64();
       };
 
       const long long next = tile + ncta;

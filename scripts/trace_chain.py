@@ -53,3 +53,7 @@ if t[176] and t[180]:
         b = 180 + 16 * r
         ops = [t[b + 1 + o] - g0 for o in range(5) if t[b + 1 + o]]
         print(f"  wgrad role {r}: start {t[b] - g0}  ops ready at {ops}  accumulators done {t[b + 8] - g0}  written {t[b + 9] - g0}")
+
+if t[240]:
+    print("bdec0 epilogue (cycles): enter", 0, "accumulator ready", t[241] - t[240], "reparam/KLD backward done", t[242] - t[240],
+          "operand + stash written", t[243] - t[240], "released", t[245] - t[240])
