@@ -590,14 +590,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       auto epi_hidden = [&](int ms, int xslot, int bias_l) {
         float* xs = ts + lo.slot_off[xslot] + row_part;
         const float* __restrict__ bias = bias_l >= 0 ? pk + lo.q_b[bias_l] + h * 16 : nullptr;
-        uint32_t v[2][16];
-        uint32_t mw[2] = {0u, 0u};
-        wait_half(0);
-        tmem_ld16(lane_base + CT_D + h * 16, v[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c == 0 || c == 2) tmem_ld16(lane_base + CT_D + (c + 1) * 32 + h * 16, v[(c + 1) & 1]);
+        // one phase: 16 accumulator values -> (+ bias) relu -> mask bits, stash image, quarter c of the A operand
+        auto phase = [&](const uint32_t (&v)[16], int c, uint32_t& mword) {
           float bv[16];
           if (bias != nullptr) {
 #pragma unroll
@@ -613,10 +607,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = up * 8 + i;
-              uint32_t bits = v[c & 1][j];
+              uint32_t bits = v[j];
               if (bias != nullptr) bits = __float_as_uint(__uint_as_float(bits) + bv[j]);
               // positive <=> the negated bit pattern is negative as an integer: shift its sign into the mask
-              mw[c >> 1] = __funnelshift_l(0u - bits, mw[c >> 1], 1);
+              mword = __funnelshift_l(0u - bits, mword, 1);
               const float x = fmaxf(__uint_as_float(bits), 0.f);
               split_tf32(x, hi[j], lw[j]);
               xv[i] = x;
@@ -627,35 +621,37 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);
           tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
           arrive_q(c);   // (handing the quarter over one phase later, to hide the store latency, was measured slower)
-          if (c == 1) {
-            wait_half(1);
-            tmem_ld16(lane_base + CT_D + 64 + h * 16, v[0]);
-          }
+        };
+        // rolled over the two halves of the accumulator (half the code of the four-phase unrolled form: this body is
+        // fetched cold at least once per tile, see the once-per-tile epilogues)
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v0[16], v1[16];
+          uint32_t mword = 0u;
+          wait_half(half);
+          tmem_ld16(lane_base + CT_D + half * 64 + h * 16, v0);
+          tmem_ld_wait();
+          tmem_ld16(lane_base + CT_D + half * 64 + 32 + h * 16, v1);
+          phase(v0, 2 * half, mword);
+          tmem_ld_wait();
+          phase(v1, 2 * half + 1, mword);
+          my_mask[(ms * 2 + half) * CH_EPI_THREADS] = mword;
         }
-        my_mask[(ms * 2) * CH_EPI_THREADS] = mw[0];
-        my_mask[(ms * 2 + 1) * CH_EPI_THREADS] = mw[1];
         finish_epilogue();
       };
       // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand); same four phases.
       // defer: the caller arrives for all four quarters itself (the last epilogue stages the next tile first)
       auto epi_dgrad = [&](int ms, int gslot, bool write_a, bool defer) {
         float* gs = ts + lo.slot_off[gslot] + row_part;
-        uint32_t v[2][16];
-        uint32_t mw[2] = {my_mask[(ms * 2) * CH_EPI_THREADS], my_mask[(ms * 2 + 1) * CH_EPI_THREADS]};
-        wait_half(0);
-        tmem_ld16(lane_base + CT_D + h * 16, v[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait();
-          if (c == 0 || c == 2) tmem_ld16(lane_base + CT_D + (c + 1) * 32 + h * 16, v[(c + 1) & 1]);
+        auto phase = [&](const uint32_t (&v)[16], int c, uint32_t& mword) {
           uint32_t hi[16], lw[16];
           float gv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             // all-ones / all-zeros from the top mask bit, then AND: no branch, no select on a predicate
-            const uint32_t keep = (uint32_t)((int32_t)mw[c >> 1] >> 31);
-            mw[c >> 1] <<= 1;
-            gv[j] = __uint_as_float(v[c & 1][j] & keep);
+            const uint32_t keep = (uint32_t)((int32_t)mword >> 31);
+            mword <<= 1;
+            gv[j] = __uint_as_float(v[j] & keep);
             split_tf32(gv[j], hi[j], lw[j]);
           }
 #pragma unroll
@@ -670,10 +666,18 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
           }
           if (!defer) arrive_q(c);
-          if (c == 1) {
-            wait_half(1);
-            tmem_ld16(lane_base + CT_D + 64 + h * 16, v[0]);
-          }
+        };
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v0[16], v1[16];
+          uint32_t mword = my_mask[(ms * 2 + half) * CH_EPI_THREADS];
+          wait_half(half);
+          tmem_ld16(lane_base + CT_D + half * 64 + h * 16, v0);
+          tmem_ld_wait();
+          tmem_ld16(lane_base + CT_D + half * 64 + 32 + h * 16, v1);
+          phase(v0, 2 * half, mword);
+          tmem_ld_wait();
+          phase(v1, 2 * half + 1, mword);
         }
       };
       // encoder input: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
