@@ -396,18 +396,25 @@ def run_cuda(args):
 
     # single GPU: the whole step is one CUDA graph (dmvae_train_step_dev: Adam step index in device memory);
     # the batch of the step is copied device-to-device into the graph's input buffer
+    # The set stays in HBM and the kernel picks the batch of update t from the device-side step counter
+    # (dmvae_train_step_resident): a step is one graph replay, nothing else.
+    resident = not args.no_graph and (world == 1 or dp.exchange == "peer")
     if args.no_graph:
         gstep = None
     elif world == 1:
-        gstep = trainer.capture(B)
+        gstep = trainer.capture(B, dataset=data)
+    elif resident:
+        gstep = dp.capture(B, dataset=data)     # + the exchange of [grads | losses] inside the update kernel
     else:
-        gstep = dp.capture(B)     # + the exchange of [grads | losses]: inside the update kernel, or NCCL captured in the graph
+        gstep = dp.capture(B)                   # + the NCCL all-reduce captured in the graph
 
     def train_step(i):
         b = data[(i % n_batches) * B:(i % n_batches + 1) * B]
-        if gstep is not None:
+        if gstep is not None and resident:
+            gstep.replay()                               # chain + wgrad (one launch at this batch), reduce + Adam + packed refresh
+        elif gstep is not None:
             gstep.batch.copy_(b, non_blocking=True)
-            gstep.replay()                               # chain + wgrad (one launch at this batch), reduce+Adam, pack
+            gstep.replay()
         elif world == 1:
             trainer.step(b, sample_offset=0)
         else:
@@ -680,7 +687,8 @@ def run_cuda(args):
                                "transform + forward + 5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128",
                    "batch_per_gpu": B, "global_batch": Bg, "parallelism": f"dp{world}",
                    "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows,
-                   "launch": ("one CUDA graph per step (device-side Adam step counter" +
+                   "launch": ("one CUDA graph per step, batch picked in the kernel from the resident set (device-side step counter" if resident else
+                              "one CUDA graph per step (device-side Adam step counter") + (
                               ("; the NCCL all-reduce is captured in it)" if dp.exchange == "nccl" else ")")) if gstep is not None else "host-driven launches",
                    "l2": f"each step reads a different batch of a {rows * T * 3 * 4 / 1e6:.0f} MB resident set (> 126 MB L2); "
                          "weights and the per-step stash / slabs are L2-resident by design",

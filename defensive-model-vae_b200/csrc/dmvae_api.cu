@@ -244,7 +244,7 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
                         uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
                         void* workspace, float* grads, const DmvaeAdam* adam, float* params, float* m, float* v,
                         float* packed_rw, void* stream, const char* what, long long* step_dev = nullptr,
-                        const DmvaeDpPeers* dp = nullptr) {
+                        const DmvaeDpPeers* dp = nullptr, int64_t x_batches = 0) {
   dmvae::Layout lo;
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
@@ -257,7 +257,7 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   dmvae::TrainIO io;
-  io.packed = packed; io.x = x; io.eps = eps;
+  io.packed = packed; io.x = x; io.eps = eps; io.x_batches = x_batches;
   io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.step_dev = step_dev; io.B = B;
   io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
@@ -339,6 +339,19 @@ int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float
   return train_common(cfg, packed, x, eps, seed, sample_offset, step_dev ? 0 : (uint64_t)adam->step, w, inv_batch, B,
                       workspace, grads, adam, params, m, v, packed, stream, "train_step_dp",
                       reinterpret_cast<long long*>(step_dev), peers);
+}
+
+int dmvae_train_step_resident(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x_set,
+                              int64_t n_batches, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
+                              float inv_batch, int64_t B, const DmvaeAdam* adam, int64_t* step_dev, void* workspace,
+                              float* grads, const DmvaeDpPeers* peers, void* stream) {
+  if (!adam || !step_dev || !packed) return fail(DMVAE_ERR_ARG, "train_step_resident: adam, step_dev or packed is null");
+  if (n_batches < 1) return fail(DMVAE_ERR_ARG, "train_step_resident: the resident set holds at least one batch");
+  if (peers && (peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world))
+    return fail(DMVAE_ERR_ARG, "train_step_resident: peers must name 1..%d ranks and this rank among them", DMVAE_MAX_PEERS);
+  return train_common(cfg, packed, x_set, nullptr, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, adam, params, m, v,
+                      packed, stream, "train_step_resident", reinterpret_cast<long long*>(step_dev),
+                      (peers && peers->world > 1) ? peers : nullptr, n_batches);
 }
 
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,

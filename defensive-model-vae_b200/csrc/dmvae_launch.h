@@ -40,6 +40,7 @@ TrainPlan plan_train(const Layout& lo, long long B, int sm_count, bool per_tile_
 struct TrainIO {
   const float* packed = nullptr;
   const float* x = nullptr;
+  long long x_batches = 0;   // tensor-core path with step_dev: x is a resident set of this many batches (0: one batch)
   const float* start = nullptr;
   const float* eps = nullptr;
   float* stash = nullptr;

@@ -89,7 +89,8 @@ struct COp {
 
 struct ChainArgs {
   const float* packed;
-  const float* x;     // (B, T, 3) absolute
+  const float* x;     // (B, T, 3) absolute; with x_batches > 0: a resident set of x_batches such batches, back to back
+  long long x_batches;   // resident set: the pass reads batch (*step_dev mod x_batches) - no per-step copy or host work
   const float* eps;   // (B, L) or null (Philox)
   float* stash;       // [n_tiles][tile_stash]
   float* loss_part;   // [grid][4 warps][4 terms]
@@ -551,12 +552,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       }
     };
 
+    // the batch of this pass: the caller's, or the one the device-side step counter selects in a resident set
+    const float* __restrict__ x_batch =
+        a.x + (a.x_batches > 0 ? (size_t)((unsigned long long)(*a.step_dev) % (unsigned long long)a.x_batches) * (size_t)a.B * I : 0);
     // the tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end
     auto load_x = [&](long long tile) {
       const long long base = tile * CH_M * I;
       const long long left = a.B * I - base;
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
-      for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(a.x + base + i) : 0.f;
+      for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(x_batch + base + i) : 0.f;
     };
     load_x(cta);
     if (h == 0) {  // the constant ones column (never overwritten)
@@ -1700,6 +1704,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
 static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part) {
   ChainArgs a;
   a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
+  a.x_batches = io.step_dev != nullptr ? io.x_batches : 0;
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;

@@ -59,6 +59,8 @@ SIGNATURES = {
                                  c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P]),
     "dmvae_train_step_dev": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                      c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, _P]),
+    "dmvae_train_step_resident": (c_int, [_CFG, _P, _P, _P, _P, _P, c_int64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
+                                          c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, POINTER(DmvaeDpPeers), _P]),
     "dmvae_train_fwd_bwd_dev": (c_int, [_CFG, _P, _P, _P, c_uint64, c_uint64, _P, POINTER(DmvaeLossWeights),
                                         c_float, c_int64, _P, _P, _P]),
     "dmvae_adam_step_dev": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P, _P]),

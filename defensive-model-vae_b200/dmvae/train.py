@@ -96,10 +96,11 @@ class FusedTrainer:
 
     def capture(self, B: int, host_batch: Optional[torch.Tensor] = None, host_losses: Optional[torch.Tensor] = None,
                 sample_offset: int = 0, all_reduce=None, global_batch: Optional[int] = None, peers=None,
-                peers_reset=None) -> "GraphStep":
+                peers_reset=None, dataset: Optional[torch.Tensor] = None) -> "GraphStep":
         """The whole step for batch size ``B`` as one CUDA graph (host-driven ``step()`` / ``apply()`` calls may
         be mixed in: ``replay()`` re-synchronises the device-side step counter when needed)."""
-        return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch, peers, peers_reset)
+        return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch, peers, peers_reset,
+                         dataset)
 
     # ------------------------------------------------------------------ passes
     def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
@@ -186,11 +187,15 @@ class GraphStep:
 
     def __init__(self, trainer: "FusedTrainer", B: int, host_batch: Optional[torch.Tensor] = None,
                  host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0,
-                 all_reduce=None, global_batch: Optional[int] = None, peers=None, peers_reset=None):
+                 all_reduce=None, global_batch: Optional[int] = None, peers=None, peers_reset=None,
+                 dataset: Optional[torch.Tensor] = None):
         """``all_reduce``: data-parallel ranks pass a callable that SUM-all-reduces a tensor in place (captured
         in the graph between the fused pass and the Adam update) and ``global_batch`` / ``sample_offset`` =
         the global batch size and this rank's row offset.  ``peers`` (a ``DmvaeDpPeers``) instead selects the
-        step whose update kernel exchanges the gradients over peer memory itself (``dmvae_train_step_dp``)."""
+        step whose update kernel exchanges the gradients over peer memory itself (``dmvae_train_step_dp``).
+        ``dataset``: a device tensor ``(n_batches * B, T, 3)`` that stays resident; update t then reads batch
+        ``(t - 1) mod n_batches`` of it, selected in the kernel from the device-side step counter
+        (``dmvae_train_step_resident``): replaying the graph walks the set with no per-step copy (``batch`` is unused)."""
         model = trainer.model
         self.trainer = trainer
         self.B = int(B)
@@ -208,10 +213,26 @@ class GraphStep:
         lib = trainer.lib
         inv = 1.0 / float(global_batch if global_batch is not None else B)
 
+        if dataset is not None:
+            if all_reduce is not None or host_batch is not None:
+                raise ValueError("dataset= excludes host_batch= and all_reduce= (use peers= for data parallel)")
+            if (dataset.device != dev or dataset.dtype != torch.float32 or not dataset.is_contiguous() or dataset.dim() != 3
+                    or dataset.shape[1] != model.seq_len or dataset.shape[2] != 3 or dataset.shape[0] < B):
+                raise ValueError(f"dataset must be a contiguous fp32 ({'>='}{B}, {model.seq_len}, 3) tensor on {dev}")
+            self.n_batches = int(dataset.shape[0]) // int(B)
+            self._keep = self._keep + (dataset,)
+
         def launch():
             if host_batch is not None:
                 self.batch.copy_(host_batch, non_blocking=True)
-            if peers is not None:
+            if dataset is not None:
+                check(lib.dmvae_train_step_resident(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
+                                                    ptr(dataset), self.n_batches, ctypes.c_uint64(trainer.seed),
+                                                    ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,
+                                                    byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
+                                                    byref(peers) if peers is not None else None, stream_ptr()),
+                      "dmvae_train_step_resident")
+            elif peers is not None:
                 check(lib.dmvae_train_step_dp(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
                                               ptr(self.batch), None, ctypes.c_uint64(trainer.seed),
                                               ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,

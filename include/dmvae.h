@@ -179,6 +179,17 @@ int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, floa
                          const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                          const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
                          int64_t* step_dev, void* workspace, float* grads, void* stream);
+/* dmvae_train_step_dev over a data set that is resident in device memory (the reference's
+ * DataLoader hands out one batch per step on the host): x_set holds n_batches batches of B rows back to back
+ * and update t reads batch (t - 1) mod n_batches, selected in the kernel from the device-side step counter -
+ * an epoch is n_batches replays of one captured graph with no per-step copy or host work.  Shuffle by
+ * permuting the set between epochs.  peers: NULL, or the data-parallel peers of dmvae_train_step_dp (every
+ * rank walks its own resident shard).  Tensor-core path only. */
+int dmvae_train_step_resident(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
+                              const float* x_set, int64_t n_batches, uint64_t seed, uint64_t sample_offset,
+                              const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
+                              int64_t* step_dev, void* workspace, float* grads, const DmvaeDpPeers* peers,
+                              void* stream);
 /* The two halves of the data-parallel step in the same graph-capturable form: forward + loss + backward
  * with the Philox stream taken from *step_dev + 2 (the counter is only read), and the Adam update for
  * step *step_dev + 1 followed by the repack, whose kernel increments the counter.  Between them the

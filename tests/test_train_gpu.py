@@ -377,3 +377,22 @@ def test_overlapped_launch_is_bit_identical_to_two_launches(B):
                 assert rel_inf(l0.cpu().numpy(), l2.cpu().numpy()) < 1e-5, rep
     finally:
         _lib.check(lib.dmvae_set_train_impl(0), "dmvae_set_train_impl")
+
+
+def test_resident_dataset_graph_walks_the_set_in_step_order():
+    """dmvae_train_step_resident: one captured graph, the batch of update t picked in the kernel as batch
+    (t - 1) mod n_batches of a device-resident set - against host-driven steps on the same slices."""
+    from dmvae.train import FusedTrainer
+    T, L, B, nb = 10, 8, 512, 3
+    p = O.init_params(T, L, seed=13)
+    data = torch.cat([synth_batch(B, T, seed=70 + i) for i in range(nb)], 0).cuda()
+    ma, mb = make_model(p, T, L), make_model(p, T, L)
+    ta, tb = FusedTrainer(ma, lr=1e-3, seed=5), FusedTrainer(mb, lr=1e-3, seed=5)
+    gs = tb.capture(B, dataset=data)
+    assert gs.n_batches == nb
+    for t in range(2 * nb + 1):                     # wraps around the set twice
+        la = ta.step(data[(t % nb) * B:(t % nb + 1) * B]).clone()
+        lb = gs.replay().clone()
+        np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-6)
+    assert rel_inf(mb.flat_parameters().cpu().numpy(), ma.flat_parameters().cpu().numpy()) < 1e-6
+    assert int(tb.step_dev.item()) == 2 * nb + 1
