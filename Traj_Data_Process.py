@@ -18,29 +18,51 @@ import numpy as np
 import pandas as pd
 
 # ===================== scenes and actions (reference :8-28) =====================
-# 'end_cond' keeps the reference's row-wise form; 'end_cond_vec' is the same rule on whole columns.
+# One start rule and one end rule per scenario, written once on whole columns; the row-wise 'end_cond' of the
+# reference's table is the same rule applied to a single row (comparisons and `&` work on scalars too).
+def _sce1_start(df):
+    return (df['ego_y'] >= 18) & (df['sv2_vx'] != 0) & (df['sv2_vy'] != 0)
+
+
+def _sce1_end(df):
+    return df['ego_y'] >= 95
+
+
+def _sce2_start(df):
+    return df['sv1_yaw'] < -170
+
+
+def _sce2_end(df):
+    return df['ego_x'] < -186
+
+
+def _sce3_start(df):
+    moving = (df['sv1_vx'] != 0) & (df['sv1_vy'] != 0)
+    return moving & (df['ego_y'] <= 40) & (df['ego_y'] != 0)
+
+
+def _sce3_end(df):
+    return df['ego_y'] <= -80
+
+
+def _sce4_start(df):
+    gap2 = (df['ego_x'] - df['sv1_x']) ** 2 + (df['ego_y'] - df['sv1_y']) ** 2
+    return (gap2 <= 40 ** 2) & (df['sv1_yaw'] >= -89.9)
+
+
+def _sce4_end(df):
+    return (df['sv1_x'] > 15) & (df['sv1_yaw'] < -85)
+
+
+def _scene(start_rule, end_rule):
+    return {'start_cond': start_rule, 'end_cond': lambda row: bool(end_rule(row)), 'end_cond_vec': end_rule}
+
+
 SCENE_CONFIG = {
-    'StaticBlindTown05': {
-        'start_cond': lambda df: (df['ego_y'] >= 18) & (df['sv2_vx'] != 0) & (df['sv2_vy'] != 0),
-        'end_cond': lambda row: row['ego_y'] >= 95,
-        'end_cond_vec': lambda df: df['ego_y'] >= 95,
-    },
-    'DynamicBlindTown05': {
-        'start_cond': lambda df: df['sv1_yaw'] < -170,
-        'end_cond': lambda row: row['ego_x'] < -186,
-        'end_cond_vec': lambda df: df['ego_x'] < -186,
-    },
-    'PredictableMovementTown05': {
-        'start_cond': lambda df: (df['sv1_vx'] != 0) & (df['sv1_vy'] != 0) & (df['ego_y'] <= 40) & (df['ego_y'] != 0),
-        'end_cond': lambda row: row['ego_y'] <= -80,
-        'end_cond_vec': lambda df: df['ego_y'] <= -80,
-    },
-    'UnpredictableMovementTown04': {
-        'start_cond': lambda df: ((df['ego_x'] - df['sv1_x']) ** 2 + (df['ego_y'] - df['sv1_y']) ** 2 <= 40 ** 2)
-                                 & (df['sv1_yaw'] >= -89.9),
-        'end_cond': lambda row: (row['sv1_x'] > 15) and (row['sv1_yaw'] < -85),
-        'end_cond_vec': lambda df: (df['sv1_x'] > 15) & (df['sv1_yaw'] < -85),
-    },
+    'StaticBlindTown05': _scene(_sce1_start, _sce1_end),
+    'DynamicBlindTown05': _scene(_sce2_start, _sce2_end),
+    'PredictableMovementTown05': _scene(_sce3_start, _sce3_end),
+    'UnpredictableMovementTown04': _scene(_sce4_start, _sce4_end),
 }
 
 ACTIONS = ['减速', '减速+转向', '转向']
@@ -63,58 +85,65 @@ def generate_random_trajectories(num_trajs, traj_length, max_angle_deviation=5.0
     return out
 
 
-# ===================== one log -> one trajectory (reference :72-122) =====================
+# ===================== one log -> one trajectory (reference :72-122), all logs (:125-141) =====================
+def _first_true(mask):
+    """Index of the first True of a boolean array, or None."""
+    mask = np.asarray(mask, dtype=bool)
+    return int(np.argmax(mask)) if mask.any() else None
+
+
 def process_csv(csv_path, scene, action, target_points=5, point_mode='normal', time_interval=0.015):
-    df = pd.read_csv(csv_path)
-    config = SCENE_CONFIG[scene]
-    # first row that satisfies the start rule (:75-81)
-    start_mask = np.asarray(config['start_cond'](df), dtype=bool)
-    if not start_mask.any():
+    """One log -> ``(target_points, 3)`` float64 ``[t, x, y]`` or None (same rules and prints as the reference)."""
+    log = pd.read_csv(csv_path)
+    rules = SCENE_CONFIG[scene]
+    first = _first_true(rules['start_cond'](log))          # :75-81 first row that satisfies the start rule
+    if first is None:
         return None
-    start_idx = int(np.argmax(start_mask))
-    # first row AFTER the start row that satisfies the end rule; it is excluded (:85-95)
-    end_mask = np.asarray(config['end_cond_vec'](df), dtype=bool)
-    after = end_mask[start_idx + 1:]
-    stop = start_idx + 1 + int(np.argmax(after)) if after.any() else len(df)
-    sub_df = df.iloc[start_idx:stop]
-    if 'ego_x' not in sub_df.columns or 'ego_y' not in sub_df.columns:
+    # :85-95 the cut ends before the first LATER row that satisfies the end rule (that row is excluded)
+    hit = _first_true(np.asarray(rules['end_cond_vec'](log), dtype=bool)[first + 1:])
+    last = len(log) if hit is None else first + 1 + hit
+    cut = log.iloc[first:last]
+    if not {'ego_x', 'ego_y'} <= set(cut.columns):
         return None
-    traj = sub_df[['ego_x', 'ego_y']].values
-    if len(traj) < target_points:
+    xy = cut[['ego_x', 'ego_y']].values
+    n = len(xy)
+    if n < target_points:
         return None
-    # equidistant picks including both ends; dtype=int truncates (:106)
-    indices = np.linspace(0, len(traj) - 1, target_points, dtype=int)
-    print(((len(traj) - 1) * time_interval) / (target_points - 1))
-    if point_mode == 'normal':
-        traj = traj[indices]
-    elif point_mode == 'extend_mid':
-        part1 = indices[:-1]
-        part2 = indices[1:]
-        indices1 = np.ceil((part1 + part2) / 2).astype(int)
-        indices_new = np.append(np.insert(indices1[:-1], 0, indices[0]), indices[-1])
-        traj = traj[indices_new]
-    # time column: sample k at k * tick * (n - 1) / (T - 1) (:118)
-    times = np.arange(target_points) * time_interval * ((len(sub_df) - 1) / (target_points - 1))
-    return np.column_stack((times, traj))
+    # :106 equidistant picks including both ends; dtype=int truncates
+    picks = np.linspace(0, n - 1, target_points, dtype=int)
+    print(((n - 1) * time_interval) / (target_points - 1))
+    if point_mode == 'extend_mid':     # :110-115 the midpoints (rounded up) between neighbouring picks, ends kept
+        mids = np.ceil((picks[:-1] + picks[1:]) / 2).astype(int)
+        xy = xy[np.append(np.insert(mids[:-1], 0, picks[0]), picks[-1])]
+    elif point_mode == 'normal':
+        xy = xy[picks]
+    # :118 sample k sits at k * tick * (n - 1) / (T - 1)
+    stamps = np.arange(target_points) * time_interval * ((n - 1) / (target_points - 1))
+    return np.column_stack((stamps, xy))
+
+
+def _logs_of(data_root, scenes, actions):
+    """(scene, action, file name, path) of every CSV, in the reference's visiting order (os.listdir order inside a
+    scene / action directory: it fixes the row order of the saved array)."""
+    for scene in scenes:
+        for action in actions:
+            folder = os.path.join(data_root, scene, action)
+            if not os.path.exists(folder):
+                continue
+            for fname in os.listdir(folder):
+                if fname.endswith('.csv'):
+                    yield scene, action, fname, os.path.join(folder, fname)
 
 
 def collect_trajectories(data_root, scenes, actions, target_points=5, point_mode='normal', time_interval=0.015):
-    all_trajs = []
-    for scene in scenes:
-        scene_path = os.path.join(data_root, scene)
-        for action in actions:
-            action_path = os.path.join(scene_path, action)
-            if not os.path.exists(action_path):
-                continue
-            for fname in os.listdir(action_path):
-                if fname.endswith('.csv'):
-                    csv_path = os.path.join(action_path, fname)
-                    traj = process_csv(csv_path, scene, action, target_points, point_mode, time_interval)
-                    if traj is not None and len(traj) == target_points:
-                        all_trajs.append(traj)
-                    else:
-                        print(f"No trajectory found for {scene}, {action}, {fname}")
-    return all_trajs
+    kept = []
+    for scene, action, fname, path in _logs_of(data_root, scenes, actions):
+        traj = process_csv(path, scene, action, target_points, point_mode, time_interval)
+        if traj is None or len(traj) != target_points:
+            print(f"No trajectory found for {scene}, {action}, {fname}")
+            continue
+        kept.append(traj)
+    return kept
 
 
 def pad_and_save(trajs, save_path):
