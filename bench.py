@@ -394,6 +394,39 @@ def run_cuda(args):
     if rank == 0 and dp.exchange_note:
         print("bench.py: " + dp.exchange_note, file=sys.stderr)
 
+    # ---------------------------------------------------------------- N > 1: is the exchanged sum RIGHT?
+    # (replicas_identical below only proves that the ranks agree.)  Before anything is timed, every rank takes 3
+    # data-parallel steps on its slice of one global batch that all ranks generate identically (injected noise)
+    # and, on a clone of the model, the same 3 steps single-rank on the whole global batch; parameters and loss
+    # terms must agree within 2e-5 or the run is abandoned.
+    dp_parity = None
+    if world > 1:
+        gdata = synth_trajectories(Bg, 4242, dev)                       # same seed on every rank
+        geps = torch.randn(3, Bg, L, generator=torch.Generator(device=dev).manual_seed(4243), device=dev)
+        m_dp, m_one = ConditionalTrajectoryVAE(T, D, L).to(dev), ConditionalTrajectoryVAE(T, D, L).to(dev)
+        for m_ in (m_dp, m_one):
+            m_.load_state_dict(model.state_dict())
+        dp_chk = DataParallelTrainer(FusedTrainer(m_dp, lr=LR, weights=WEIGHTS, seed=0), exchange=dp.exchange)
+        one_chk = FusedTrainer(m_one, lr=LR, weights=WEIGHTS, seed=0)
+        lo_r = rank * B
+        loss_err = 0.0
+        for s_ in range(3):
+            l_dp = dp_chk.step(gdata[lo_r:lo_r + B], eps=geps[s_, lo_r:lo_r + B]).double().cpu()
+            l_one = one_chk.step(gdata, eps=geps[s_]).double().cpu()
+            loss_err = max(loss_err, float(((l_dp - l_one).abs() / l_one.abs().clamp_min(1e-30)).max()))
+        dp_chk.check_exchange()
+        p_dp, p_one = m_dp.flat_parameters().double(), m_one.flat_parameters().double()
+        g_dp, g_one = dp_chk.engine.grads.double(), one_chk.grads.double()
+        dp_parity = {"world": world, "exchange": dp_chk.exchange, "steps": 3, "global_batch": Bg,
+                     "param_rel_err": max_over_ranks(float((p_dp - p_one).abs().max() / p_one.abs().max())),
+                     "grad_rel_err": max_over_ranks(float((g_dp - g_one).abs().max() / g_one.abs().max())),
+                     "loss_rel_err": max_over_ranks(loss_err),
+                     "reference": "FusedTrainer.step on the whole global batch, one rank, same injected eps", "tol": 2e-5}
+        if max(dp_parity["param_rel_err"], dp_parity["loss_rel_err"], dp_parity["grad_rel_err"]) > 2e-5 or \
+                not all(v == v for v in (dp_parity["param_rel_err"], dp_parity["loss_rel_err"])):
+            raise SystemExit(f"bench.py: data-parallel step disagrees with the single-rank step: {dp_parity}")
+        del gdata, geps, m_dp, m_one, dp_chk, one_chk
+
     # single GPU: the whole step is one CUDA graph (dmvae_train_step_dev: Adam step index in device memory);
     # the batch of the step is copied device-to-device into the graph's input buffer
     # The set stays in HBM and the kernel picks the batch of update t from the device-side step counter
@@ -722,6 +755,7 @@ def run_cuda(args):
         "clocks": clk,
         "losses_after_run": losses_end,
         "replicas_identical": replicas_identical,
+        "dp_parity": dp_parity,
         "decode": {
             "metric": "decoded_trajectories_per_sec", "value": dec_value, "unit": "trajectories/s",
             "config": {"workload": f"configs[2]: 4 scenarios x {R} latents per GPU, in-kernel Philox, shared scenario start, "

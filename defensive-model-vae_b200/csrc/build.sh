@@ -10,7 +10,11 @@ mkdir -p build
 objs=()
 for s in "${SRCS[@]}"; do
   o="build/${s%.cu}.o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ dmvae_common.cuh -nt "$o" ] || [ dmvae_tc.cuh -nt "$o" ] || [ dmvae_launch.h -nt "$o" ] || [ dmvae_prof.h -nt "$o" ] || [ ../../include/dmvae.h -nt "$o" ]; then
+  # stale when the source or any header of this directory / include/ is newer (every .cu sees most of them)
+  stale=0
+  [ -f "$o" ] || stale=1
+  for dep in "$s" build.sh *.cuh *.h ../../include/*.h; do [ "$dep" -nt "$o" ] && stale=1; done
+  if [ "$stale" = 1 ]; then
     echo "nvcc $s"
     "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" 2> "build/${s%.cu}.ptxas.log" || { cat "build/${s%.cu}.ptxas.log"; exit 1; }
   fi

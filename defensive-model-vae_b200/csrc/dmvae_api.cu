@@ -7,6 +7,7 @@
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
 #include "dmvae_prof.h"
+#include "../../include/dmvae_debug.h"
 
 // count (and, when profiling, time) the kernel launched by `call`
 #define PROF(kernel, stream, call) [&] { dmvae::ProfScope _ps((kernel), (stream)); return (call); }()
@@ -59,10 +60,15 @@ int require_device(int* sm_count) {
   return DMVAE_OK;
 }
 
+// Per host thread (include/dmvae.h): a thread that switches kernels for its own calls does not disturb another
+// thread's stream.
 // 0 = tensor cores (tcgen05, 3xTF32; default), 1 = FP32 FFMA kernel
-std::atomic<int> g_decode_impl{0};
-// 0 = tensor cores where supported (default), 1 = FFMA kernels
-std::atomic<int> g_train_impl{0};
+thread_local int g_decode_impl = 0;
+// 0 = tensor cores above 128 rows (default), 1 = FFMA kernels, 2 / 3 = tensor cores at any batch size
+thread_local int g_train_impl = 0;
+// batches up to this size are latency-bound on either kernel family: the default keeps the FFMA kernels' tighter
+// gradients for them (the reference trains on 16..135 rows per step, Training_VAE.py:278)
+constexpr long long TRAIN_TC_MIN_ROWS = 129;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -141,7 +147,7 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
   if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e;
-  if (g_decode_impl.load() == 0 && dmvae::decode_tc_supported(lo, start_is_shared != 0))
+  if (g_decode_impl == 0 && dmvae::decode_tc_supported(lo, start_is_shared != 0))
     e = PROF(dmvae::K_DECODE_TC, st,
              dmvae::launch_decode_tc(lo, start_is_shared != 0, packed, z, seed, sample_offset, start, out, z_out, B,
                                      add_start ? 1 : 0, sms, st));
@@ -266,7 +272,8 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
     return fail(DMVAE_ERR_SHAPE, "%s: the device-side step counter needs the tensor-core path (3*seq_len <= 64, latent_dim <= 32)", what);
   if (dp != nullptr && !dmvae::train_tc_supported(lo))
     return fail(DMVAE_ERR_SHAPE, "%s: the peer-memory exchange needs the tensor-core path (3*seq_len <= 64, latent_dim <= 32)", what);
-  if ((g_train_impl.load() == 0 || step_dev != nullptr || dp != nullptr) && dmvae::train_tc_supported(lo)) {
+  const bool want_tc = g_train_impl >= 2 || (g_train_impl == 0 && B >= TRAIN_TC_MIN_ROWS);
+  if ((want_tc || step_dev != nullptr || dp != nullptr) && dmvae::train_tc_supported(lo)) {
     // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)
     const dmvae::TrainTcPlan tp = dmvae::plan_train_tc(lo, B, sms);
     float* stash = static_cast<float*>(workspace);
@@ -323,18 +330,43 @@ int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world) {
   const int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
   if (world < 1 || world > DMVAE_MAX_PEERS) return fail(DMVAE_ERR_ARG, "dp_inbox_bytes: 1..%d ranks", DMVAE_MAX_PEERS);
-  return (int64_t)(world + 1) * 2 * dmvae::dp_exchange_stride(lo) * 8;   // [source | sum][parity][stride] x {value, step}
+  return (int64_t)dmvae::dp_inbox_bytes(lo, world);   // [source | sum][parity][stride] x {step : value}, status word
+}
+static int check_peers(const DmvaeDpPeers* peers, const char* what) {
+  if (!peers || peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
+    return fail(DMVAE_ERR_ARG, "%s: peers must name 1..%d ranks and this rank among them", what, DMVAE_MAX_PEERS);
+  if (peers->owned_from != 0 && (peers->owned_from < 2 || peers->owned_from > DMVAE_MAX_PEERS + 1))
+    return fail(DMVAE_ERR_ARG, "%s: peers->owned_from must be 0 (default) or 2..%d", what, DMVAE_MAX_PEERS + 1);
+  if (peers->timeout_ms < 0) return fail(DMVAE_ERR_ARG, "%s: peers->timeout_ms must not be negative", what);
+  for (int p = 0; p < peers->world; ++p)
+    if (!peers->inbox[p] || !aligned16(peers->inbox[p]))
+      return fail(DMVAE_ERR_ARG, "%s: null or misaligned inbox of rank %d", what, p);
+  return DMVAE_OK;
+}
+int dmvae_dp_status(const DmvaeCfg* cfg, const DmvaeDpPeers* peers, void* stream) {
+  dmvae::Layout lo;
+  int rc = layout_or_fail(cfg, &lo);
+  if (rc != DMVAE_OK) return rc;
+  if ((rc = check_peers(peers, "dp_status")) != DMVAE_OK) return rc;
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  unsigned int word = 0;
+  const char* src = static_cast<const char*>(peers->inbox[peers->rank]) + dmvae::dp_status_offset(lo, peers->world);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(&word, src, sizeof(word), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "dp_status");
+  if (word != 0u)
+    return fail(DMVAE_ERR_TIMEOUT, "dp_status: rank %d gave up waiting for a peer's gradients in step %u (peer dead, a step behind, "
+                "or the ranks disagree about world / owned_from); its parameters hold NaN", peers->rank, word & 0x7fffffffu);
+  return DMVAE_OK;
 }
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x,
                         const float* eps, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
                         float inv_batch, int64_t B, const DmvaeAdam* adam, int64_t* step_dev, void* workspace,
                         float* grads, const DmvaeDpPeers* peers, void* stream) {
   if (!adam || !packed) return fail(DMVAE_ERR_ARG, "train_step_dp: adam or packed is null");
-  if (!peers || peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world)
-    return fail(DMVAE_ERR_ARG, "train_step_dp: peers must name 1..%d ranks and this rank among them", DMVAE_MAX_PEERS);
-  for (int p = 0; p < peers->world; ++p)
-    if (!peers->inbox[p] || !aligned16(peers->inbox[p]))
-      return fail(DMVAE_ERR_ARG, "train_step_dp: null or misaligned inbox of rank %d", p);
+  const int prc = check_peers(peers, "train_step_dp");
+  if (prc != DMVAE_OK) return prc;
   if (!step_dev && adam->step < 1) return fail(DMVAE_ERR_ARG, "train_step_dp: step must be >= 1");
   return train_common(cfg, packed, x, eps, seed, sample_offset, step_dev ? 0 : (uint64_t)adam->step, w, inv_batch, B,
                       workspace, grads, adam, params, m, v, packed, stream, "train_step_dp",
@@ -347,8 +379,10 @@ int dmvae_train_step_resident(const DmvaeCfg* cfg, float* params, float* packed,
                               float* grads, const DmvaeDpPeers* peers, void* stream) {
   if (!adam || !step_dev || !packed) return fail(DMVAE_ERR_ARG, "train_step_resident: adam, step_dev or packed is null");
   if (n_batches < 1) return fail(DMVAE_ERR_ARG, "train_step_resident: the resident set holds at least one batch");
-  if (peers && (peers->world < 1 || peers->world > DMVAE_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world))
-    return fail(DMVAE_ERR_ARG, "train_step_resident: peers must name 1..%d ranks and this rank among them", DMVAE_MAX_PEERS);
+  if (peers) {
+    const int prc = check_peers(peers, "train_step_resident");
+    if (prc != DMVAE_OK) return prc;
+  }
   return train_common(cfg, packed, x_set, nullptr, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, adam, params, m, v,
                       packed, stream, "train_step_resident", reinterpret_cast<long long*>(step_dev),
                       (peers && peers->world > 1) ? peers : nullptr, n_batches);
@@ -488,21 +522,15 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
 
 int dmvae_set_decode_impl(int impl) {
   if (impl != 0 && impl != 1) return fail(DMVAE_ERR_ARG, "set_decode_impl: 0 (tensor cores) or 1 (FFMA)");
-  g_decode_impl.store(impl);
+  g_decode_impl = impl;
   return DMVAE_OK;
 }
 
 int dmvae_set_train_impl(int impl) {
-  if (impl < 0 || impl > 2)
-    return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (tensor cores), 1 (FFMA) or 2 (tensor cores, always two launches)");
-  g_train_impl.store(impl == 1 ? 1 : 0);
-  if (impl != 1) dmvae::set_train_tc_overlap(impl == 0);
-  return DMVAE_OK;
-}
-
-int dmvae_set_dp_owned_from(int world) {
-  if (world < 2 || world > DMVAE_MAX_PEERS + 1) return fail(DMVAE_ERR_ARG, "set_dp_owned_from: 2..%d", DMVAE_MAX_PEERS + 1);
-  dmvae::set_dp_owned_from(world);
+  if (impl < 0 || impl > 3)
+    return fail(DMVAE_ERR_ARG, "set_train_impl: 0 (default), 1 (FFMA), 2 (tensor cores, two launches) or 3 (tensor cores)");
+  g_train_impl = impl;
+  if (impl != 1) dmvae::set_train_tc_overlap(impl != 2);
   return DMVAE_OK;
 }
 

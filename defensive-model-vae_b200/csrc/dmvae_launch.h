@@ -78,13 +78,16 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
 cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs, cudaStream_t stream);
 cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* slabs,
                                      float* loss_part, int* flags, cudaStream_t stream);
-void set_dp_owned_from(int world);   // data-parallel exchange: world sizes from here on use the owner scheme
 void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (measurement / debugging)
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
                              const DmvaeDpPeers* dp, cudaStream_t stream);
 inline int dp_exchange_stride(const Layout& lo) { return round_up(lo.n_params + 5, 4); }
+// inbox of a rank: [source | sum][step parity][stride] 8-byte words {step : value}, then 16 bytes whose first word is
+// the rank's status (0, or 0x80000000 | step once a thread timed out waiting for a peer)
+inline size_t dp_status_offset(const Layout& lo, int world) { return (size_t)(world + 1) * 2 * dp_exchange_stride(lo) * 8; }
+inline size_t dp_inbox_bytes(const Layout& lo, int world) { return dp_status_offset(lo, world) + 16; }
 
 // grads = fixed-order sum of the slabs (+ five loss terms); with `adam` also the update.
 cudaError_t launch_reduce(const Layout& lo, const float* slabs, int n_slabs, int slab_stride, const float w[4],

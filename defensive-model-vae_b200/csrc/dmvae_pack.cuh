@@ -8,6 +8,7 @@
 // Both are __host__ __device__: tests/test_pack_scatter.py compiles them for the host and checks that the scatter
 // of every parameter reproduces the gather of the whole arena.
 #pragma once
+#include <cassert>
 
 #include "dmvae_common.cuh"
 
@@ -178,6 +179,7 @@ inline PackPlan make_pack_plan(const Layout& lo) {
   int blocks = 0;
   auto add = [&](int type, int id, int count) {
     if (count <= 0) return;
+    assert(plan.n < 64 && "PackPlan holds at most 64 segments");
     plan.type[plan.n] = type; plan.id[plan.n] = id; plan.count[plan.n] = count; plan.block0[plan.n] = blocks;
     blocks += (count + PACK_THREADS - 1) / PACK_THREADS;
     ++plan.n;

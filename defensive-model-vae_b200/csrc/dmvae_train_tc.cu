@@ -1474,6 +1474,11 @@ constexpr int REDUCE_TC_THREADS = 256;
 struct AdamScalarsTc {
   float w1, b2, w2, step_size, bc2_sqrt, eps;
 };
+struct DpCtl {
+  int owned_from;              // smallest world size that uses the owner scheme
+  long long timeout_ns;        // how long a thread polls before it gives up
+  unsigned int* status;        // the status word at the end of this rank's inbox
+};
 struct ReduceTcArgs {
   int tensor_end[24];   // end offset (floats) of each state_dict tensor
   int tensor_role[24];
@@ -1495,21 +1500,45 @@ struct ReduceTcArgs {
   // slab sum and the update (dp_all_sum)
   DmvaeDpPeers dp;
   int dp_stride;
-  int dp_owned_from;         // smallest world size that uses the owner scheme of dp_all_sum (default 3)
+  DpCtl dp_ctl;              // owner-scheme threshold, poll time-out and status word of dp_all_sum
   unsigned int epoch_host;   // the step index when there is no device-side counter
   long long* trace;          // development aid: %globaltimer stamps of block 0 (slots 230..)
 };
 
-// Data-parallel exchange, "low-latency" style: a gradient travels as one 8-byte word {value bits, step index}
-// written straight into the peer's inbox (a single NVLink store, atomic at that size), so the receiver polls the
-// word itself and no fence or separate flag is needed.
-__device__ __forceinline__ void dp_push(uint2* dst, float v, unsigned int epoch) {
-  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+// Data-parallel exchange, "low-latency" style: a gradient travels as ONE 8-byte word {step index : value bits}
+// written straight into the peer's inbox with a single 64-bit store (one register, one NVLink write - unlike a
+// two-element vector access, which the PTX memory model treats as two scalar accesses, the word cannot be
+// observed half-written), so the receiver polls the word itself and no fence or separate flag is needed.
+__device__ __forceinline__ void dp_push(unsigned long long* dst, float v, unsigned int epoch) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
 }
-__device__ __forceinline__ uint2 dp_load(const uint2* src) {
-  uint2 w;
-  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(src) : "memory");
+__device__ __forceinline__ unsigned long long dp_load(const unsigned long long* src) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
   return w;
+}
+// Polls until the word carries `epoch`.  A dead or lagging peer (or ranks that disagree about the scheme) must not
+// hang the GPU: after timeout_ns the thread raises the rank's status word, returns NaN for the element - the
+// parameters of the rank turn NaN, loudly - and the kernel runs to its end (dmvae_dp_status reports the word).
+__device__ __noinline__ unsigned long long dp_wait_slow(const unsigned long long* src, unsigned int epoch, const DpCtl& c) {
+  const long long t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      const unsigned long long w = dp_load(src);
+      if ((unsigned int)(w >> 32) == epoch) return w;
+    }
+    if (global_ns() - t0 > c.timeout_ns) {
+      atomicExch(c.status, 0x80000000u | epoch);
+      return ((unsigned long long)epoch << 32) | 0x7fc00000ull;
+    }
+  }
+}
+__device__ __forceinline__ unsigned long long dp_wait(unsigned long long w, const unsigned long long* src, unsigned int epoch,
+                                                      const DpCtl& c) {
+  if ((unsigned int)(w >> 32) == epoch) return w;
+  return dp_wait_slow(src, epoch, c);
 }
 // Sum of `mine` over the ranks; idx = element index inside the exchange.  Every rank receives the same bits.
 //   up to 2 ranks (world < owned_from): every rank pushes its word to every peer and adds the ranks in rank order (one NVLink hop);
@@ -1517,24 +1546,24 @@ __device__ __forceinline__ uint2 dp_load(const uint2* src) {
 //                  their word to the owner only; the owner adds the ranks in rank order and pushes the sum to
 //                  everyone's sum area.  Two hops, but (world + 6) / 8 MB instead of (world - 1) MB out of every
 //                  rank per step - at 8 GPUs the all-to-all version spent ~20 us per step on it.
-// Inbox of a rank: [source rank 0..world-1][step parity][dp_stride] words, then [sum][step parity][dp_stride].
+// Inbox of a rank: [source rank 0..world-1][step parity][dp_stride] words, then [sum][step parity][dp_stride], then
+// the status word.
 __device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, int idx, float mine, unsigned int epoch,
-                                            int owned_from) {
+                                            const DpCtl& c) {
+  typedef unsigned long long u64;
   const size_t par = (size_t)(epoch & 1u) * stride + idx;
-  const uint2* in = reinterpret_cast<const uint2*>(dp.inbox[dp.rank]) + par;
-  const int owner = dp.world < owned_from ? -1 : (idx >> 8) % dp.world;
+  const u64* in = reinterpret_cast<const u64*>(dp.inbox[dp.rank]) + par;
+  const int owner = dp.world < c.owned_from ? -1 : (idx >> 8) % dp.world;
   if (owner >= 0 && owner != dp.rank) {
-    dp_push(reinterpret_cast<uint2*>(dp.inbox[owner]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
-    const uint2* sum_in = in + (size_t)dp.world * 2 * stride;
-    uint2 w = dp_load(sum_in);
-    while (w.y != epoch) w = dp_load(sum_in);
-    return __uint_as_float(w.x);
+    dp_push(reinterpret_cast<u64*>(dp.inbox[owner]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+    const u64* sum_in = in + (size_t)dp.world * 2 * stride;
+    return __uint_as_float((unsigned int)dp_wait(dp_load(sum_in), sum_in, epoch, c));
   }
   if (owner < 0)
     for (int p = 0; p < dp.world; ++p)
-      if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
+      if (p != dp.rank) dp_push(reinterpret_cast<u64*>(dp.inbox[p]) + (size_t)dp.rank * 2 * stride + par, mine, epoch);
   // all peers' words are requested at once (independent loads), then those that had not arrived yet are polled
-  uint2 w[DMVAE_MAX_PEERS];
+  u64 w[DMVAE_MAX_PEERS];
 #pragma unroll
   for (int p = 0; p < DMVAE_MAX_PEERS; ++p)
     if (p < dp.world && p != dp.rank) w[p] = dp_load(in + (size_t)p * 2 * stride);
@@ -1543,12 +1572,11 @@ __device__ __forceinline__ float dp_all_sum(const DmvaeDpPeers& dp, int stride, 
   for (int p = 0; p < DMVAE_MAX_PEERS; ++p) {
     if (p >= dp.world) break;
     if (p == dp.rank) { g += mine; continue; }
-    while (w[p].y != epoch) w[p] = dp_load(in + (size_t)p * 2 * stride);
-    g += __uint_as_float(w[p].x);
+    g += __uint_as_float((unsigned int)dp_wait(w[p], in + (size_t)p * 2 * stride, epoch, c));
   }
   if (owner >= 0)
     for (int p = 0; p < dp.world; ++p)
-      if (p != dp.rank) dp_push(reinterpret_cast<uint2*>(dp.inbox[p]) + (size_t)dp.world * 2 * stride + par, g, epoch);
+      if (p != dp.rank) dp_push(reinterpret_cast<u64*>(dp.inbox[p]) + (size_t)dp.world * 2 * stride + par, g, epoch);
   return g;
 }
 
@@ -1585,7 +1613,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
 #pragma unroll 8
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
     if (tr) r.trace[231] = global_ns();
-    if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s, r.dp_owned_from);
+    if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s, r.dp_ctl);
     if (tr) r.trace[233] = global_ns() + (long long)(s == 123.456f);
   }
   if (e < r.n_params) {
@@ -1636,7 +1664,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     float val = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) val = lane == i ? mine[i] : val;
-    if (dp_on && lane < 5) val = dp_all_sum(r.dp, r.dp_stride, r.n_params + lane, val, epoch_s, r.dp_owned_from);   // the global batch's
+    if (dp_on && lane < 5) val = dp_all_sum(r.dp, r.dp_stride, r.n_params + lane, val, epoch_s, r.dp_ctl);   // the global batch's
     if (lane < 5) grads[r.n_params + lane] = val;
   }
 }
@@ -1650,9 +1678,7 @@ bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && 
 
 static long long* g_chain_trace = nullptr;
 void set_chain_trace(long long* p) { g_chain_trace = p; }
-static int g_dp_owned_from = 3;
-void set_dp_owned_from(int world) { g_dp_owned_from = world; }
-static bool g_tc_overlap = true;
+static thread_local bool g_tc_overlap = true;   // per host thread, like dmvae_set_train_impl
 void set_train_tc_overlap(bool on) { g_tc_overlap = on; }
 
 TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overlap) {
@@ -1730,13 +1756,11 @@ static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const flo
   a.trace = g_chain_trace;
   return a;
 }
-// the opt-in shared-memory limit of a kernel only ever needs to grow
+// The opt-in shared-memory limit is an attribute of (kernel, device): it is set on every launch, as the other
+// launchers do (a cached "already set" would be wrong on a second device of the process and racy between threads).
 template <typename Kernel>
-static cudaError_t grow_smem_limit(Kernel kernel, size_t bytes, size_t* current) {
-  if (bytes <= *current) return cudaSuccess;
-  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) *current = bytes;
-  return e;
+static cudaError_t set_smem_limit(Kernel kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
@@ -1744,8 +1768,7 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
   ChainKArgs k;
   k.lo = lo;
   k.c = chain_args(lo, plan, io, stash, loss_part);
-  static size_t limit = 0;
-  const cudaError_t e = grow_smem_limit(chain_kernel, plan.chain_smem, &limit);
+  const cudaError_t e = set_smem_limit(chain_kernel, plan.chain_smem);
   if (e != cudaSuccess) return e;
   chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(k);
   return cudaGetLastError();
@@ -1755,8 +1778,7 @@ cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float*
   WgradKArgs k;
   k.lo = lo;
   k.w = wgrad_args(lo, plan, stash, slabs);
-  static size_t limit = 0;
-  const cudaError_t e = grow_smem_limit(wgrad_kernel, WG_SMEM_BYTES, &limit);
+  const cudaError_t e = set_smem_limit(wgrad_kernel, WG_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(k);
   return cudaGetLastError();
@@ -1773,8 +1795,7 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
   k.w.ready = flags;
   k.chain_grid = plan.chain_grid;
   const size_t smem = plan.chain_smem > WG_SMEM_BYTES ? plan.chain_smem : WG_SMEM_BYTES;
-  static size_t limit = 0;
-  cudaError_t e = grow_smem_limit(train_tc_fused_kernel, smem, &limit);
+  cudaError_t e = set_smem_limit(train_tc_fused_kernel, smem);
   if (e != cudaSuccess) return e;
   train_tc_fused_kernel<<<plan.chain_grid + plan.wgrad_grid, CH_THREADS, smem, stream>>>(k);
   return cudaGetLastError();
@@ -1788,7 +1809,11 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
   if (dp != nullptr) r.dp = *dp;
   else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
   r.dp_stride = dp_exchange_stride(lo);
-  r.dp_owned_from = g_dp_owned_from;
+  r.dp_ctl.owned_from = r.dp.owned_from > 0 ? r.dp.owned_from : 3;
+  r.dp_ctl.timeout_ns = (long long)(r.dp.timeout_ms > 0 ? r.dp.timeout_ms : 2000) * 1000000ll;
+  r.dp_ctl.status = r.dp.world > 1 ? reinterpret_cast<unsigned int*>(static_cast<char*>(r.dp.inbox[r.dp.rank]) +
+                                                                     dp_status_offset(lo, r.dp.world))
+                                   : nullptr;
   r.epoch_host = adam != nullptr ? (unsigned int)adam->step : 0u;
   r.trace = g_chain_trace;
   r.packed = adam != nullptr ? packed : nullptr;

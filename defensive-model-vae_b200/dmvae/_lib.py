@@ -36,7 +36,8 @@ MAX_PEERS = 8
 
 
 class DmvaeDpPeers(ctypes.Structure):
-    _fields_ = [("world", c_int32), ("rank", c_int32), ("inbox", c_void_p * MAX_PEERS)]
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("owned_from", c_int32), ("timeout_ms", c_int32),
+                ("inbox", c_void_p * MAX_PEERS)]
 
 
 # name -> (restype, argtypes); mirrors include/dmvae.h one to one
@@ -65,7 +66,7 @@ SIGNATURES = {
                                         c_float, c_int64, _P, _P, _P]),
     "dmvae_adam_step_dev": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P, _P]),
     "dmvae_dp_inbox_bytes": (c_int64, [_CFG, c_int]),
-    "dmvae_set_dp_owned_from": (c_int, [c_int]),
+    "dmvae_dp_status": (c_int, [_CFG, POINTER(DmvaeDpPeers), _P]),
     "dmvae_train_step_dp": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                     c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, POINTER(DmvaeDpPeers), _P]),
     "dmvae_adam_step": (c_int, [_CFG, _P, _P, _P, _P, POINTER(DmvaeAdam), _P, _P]),
@@ -78,8 +79,6 @@ SIGNATURES = {
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
     "dmvae_set_decode_impl": (c_int, [c_int]),
     "dmvae_set_train_impl": (c_int, [c_int]),
-    "dmvae_debug_decode_trace": (c_int, [_P]),
-    "dmvae_debug_train_trace": (c_int, [_P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),
@@ -87,6 +86,12 @@ SIGNATURES = {
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
 }
 KERNEL_COUNT = 16
+ABI_VERSION = 2
+# include/dmvae_debug.h (development aids, outside the drop-in boundary)
+DEBUG_SIGNATURES = {
+    "dmvae_debug_decode_trace": (c_int, [_P]),
+    "dmvae_debug_train_trace": (c_int, [_P]),
+}
 
 _lib = None
 
@@ -100,13 +105,13 @@ def lib() -> ctypes.CDLL:
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or defensive-model-vae_b200/csrc/build.sh).  dmvae has no CPU or PyTorch fallback.")
     handle = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(handle, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
     got = handle.dmvae_abi_version()
-    if got != 1:
-        raise DmvaeError(f"libdmvae ABI version {got}, expected 1")
+    if got != ABI_VERSION:
+        raise DmvaeError(f"libdmvae ABI version {got}, expected {ABI_VERSION}: rebuild (csrc/build.sh)")
     _lib = handle
     return _lib
 

@@ -78,14 +78,18 @@ class DataParallelTrainer:
     the same step; sizes may differ).  Equivalent to one single-process step on the
     concatenated batch: same loss (means over the global batch), same update."""
 
-    def __init__(self, engine: GradEngine, group=None, exchange: str = "auto"):
+    def __init__(self, engine: GradEngine, group=None, exchange: str = "auto", owned_from: int = 0,
+                 timeout_ms: int = 0):
         """``exchange``: "peer" (gradient exchange inside the update kernel over peer memory; raises where it
         cannot be set up), "nccl" (one all-reduce per step), or "auto" (peer when possible, else nccl - the
-        reason is kept in ``exchange_note``).  All ranks must pass the same value."""
+        reason is kept in ``exchange_note``).  ``owned_from`` / ``timeout_ms``: the fields of ``DmvaeDpPeers``
+        (0 = the library defaults: owner scheme from 3 ranks on, 2 s poll limit).  All ranks must pass the
+        same values; the constructor checks that they do."""
         if exchange not in ("auto", "peer", "nccl"):
             raise ValueError(f"exchange={exchange!r}")
         self.engine = engine
         self.group = group
+        self.owned_from, self.timeout_ms = int(owned_from), int(timeout_ms)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._sizes = torch.zeros(self.world, dtype=torch.int64)
@@ -106,6 +110,13 @@ class DataParallelTrainer:
                 if exchange == "peer":
                     raise RuntimeError(self.exchange_note or "peer exchange unavailable on another rank")
                 self.peers = None
+            # every rank must describe the exchange identically: a rank on another scheme would wait for words that
+            # nobody sends (the kernel's poll limit would end that wait, but the step would be lost)
+            mine = [self.owned_from, -self.owned_from, self.timeout_ms, -self.timeout_ms]
+            seen = torch.tensor(mine, dtype=torch.int64, device=self._device())
+            dist.all_reduce(seen, op=dist.ReduceOp.MAX, group=self.group)
+            if seen.tolist() != mine:
+                raise RuntimeError("the ranks disagree about owned_from / timeout_ms of the peer exchange")
         self.exchange = "peer" if self.peers is not None else ("nccl" if self.world > 1 else "none")
 
     def _device(self):
@@ -133,6 +144,7 @@ class DataParallelTrainer:
             raise RuntimeError("symmetric memory handle does not match the process group")
         peers = DmvaeDpPeers()
         peers.world, peers.rank = self.world, self.rank
+        peers.owned_from, peers.timeout_ms = self.owned_from, self.timeout_ms
         for p in range(self.world):
             peers.inbox[p] = ptrs[p]
         self._symm = (buf, hdl)
@@ -147,6 +159,15 @@ class DataParallelTrainer:
         self._symm[0].zero_()
         torch.cuda.synchronize(self._device())
         dist.barrier(group=self.group)
+
+    def check_exchange(self) -> None:
+        """Raises if a thread of an earlier step of this rank gave up waiting for a peer (``dmvae_dp_status``;
+        synchronises the stream).  Cheap enough for once per epoch; the step itself never synchronises."""
+        if self.peers is None:
+            return
+        from ._lib import byref, check, stream_ptr
+        with torch.cuda.device(self._device()):
+            check(self.engine.lib.dmvae_dp_status(self.engine._cfg_ref, byref(self.peers), stream_ptr()), "dmvae_dp_status")
 
     def global_batch_layout(self, local_rows: int, equal: bool = True) -> Tuple[int, int]:
         """(global batch size, this rank's row offset).  With ``equal`` every rank holds

@@ -200,7 +200,12 @@ class GraphStep:
         self.trainer = trainer
         self.B = int(B)
         dev = trainer.device
-        self.batch = torch.empty(B, model.seq_len, 3, dtype=torch.float32, device=dev)   # static input buffer
+        if peers is not None and peers_reset is None:
+            # the warm-up launch below publishes words tagged with step t + 1 in the peers' inboxes and the counter
+            # is then rewound: without a collective reset the first replay could match those stale words
+            raise ValueError("peers= needs peers_reset= (a collective that zeroes every rank's inbox between two "
+                             "barriers; DataParallelTrainer.capture passes its own)")
+        self.batch = torch.zeros(B, model.seq_len, 3, dtype=torch.float32, device=dev)   # static input buffer
         self.host_batch, self.host_losses = host_batch, host_losses
         if host_batch is not None and (not host_batch.is_pinned() or tuple(host_batch.shape) != tuple(self.batch.shape)):
             raise ValueError("host_batch must be a pinned (B, T, 3) fp32 tensor")
@@ -274,9 +279,11 @@ class GraphStep:
             arena.copy_(saved[0]); trainer.m.copy_(saved[1]); trainer.v.copy_(saved[2]); trainer.step_dev.copy_(saved[3])
             check(lib.dmvae_pack_weights(trainer._cfg_ref, ptr(arena), ptr(packed), stream_ptr()), "dmvae_pack_weights")
             model.mark_packed_current()
-            if peers is not None and peers_reset is not None:
-                # the warm-up published its step index in the peers' flags and the counter was just rewound:
-                # the flags start over (collective: every rank resets its own between two barriers)
+            if peers is not None:
+                # the warm-up published its step index in the peers' inboxes and the counter was just rewound:
+                # the inboxes start over (collective: every rank resets its own between two barriers).  The same
+                # reset is needed whenever the step counter moves backwards (e.g. resuming an earlier checkpoint
+                # with the same symmetric buffer): a word of the old run with the same step index would match.
                 peers_reset()
 
     def replay(self) -> torch.Tensor:

@@ -34,13 +34,14 @@
 extern "C" {
 #endif
 
-#define DMVAE_ABI_VERSION 1
+#define DMVAE_ABI_VERSION 2
 
 #define DMVAE_OK 0
 #define DMVAE_ERR_SHAPE (-1)   /* configuration outside the supported envelope */
 #define DMVAE_ERR_ARG (-2)     /* null / misaligned pointer, bad size */
 #define DMVAE_ERR_DEVICE (-3)  /* no sm_100 device / wrong device */
 #define DMVAE_ERR_CUDA (-4)    /* a CUDA runtime call failed */
+#define DMVAE_ERR_TIMEOUT (-5) /* a data-parallel peer did not deliver its gradients in time (dmvae_dp_status) */
 
 /* ConditionalTrajectoryVAE(seq_len, dim, latent_dim, hidden_dim=128)
  * (Training_VAE.py:124-129). */
@@ -72,11 +73,19 @@ typedef struct DmvaeAdam {
 /* Data-parallel peers of one training job: one process per GPU of a node, every GPU mapping the others'
  * inbox (CUDA peer access over NVLink; torch.distributed's symmetric memory provides the mapping, cudaIpc
  * would do as well).  inbox[p] is rank p's inbox as addressed from THIS device: dmvae_dp_inbox_bytes()
- * bytes, zero before the first step (every rank zeroes its own, then a barrier). */
+ * bytes, zero before the first step (every rank zeroes its own, then a barrier).
+ *   owned_from  smallest world size that exchanges through element owners (0 = default 3; 2 forces the owner
+ *               scheme on two ranks, DMVAE_MAX_PEERS + 1 the all-to-all scheme everywhere).  Part of the
+ *               peers description because every rank must use the same value.
+ *   timeout_ms  how long a thread polls for a peer's word before it gives up (0 = default 2000): the rank
+ *               then stores NaN for that element, raises the status word at the end of its own inbox and
+ *               finishes the step, so a dead or lagging peer cannot hang the GPU; dmvae_dp_status reports it. */
 #define DMVAE_MAX_PEERS 8
 typedef struct DmvaeDpPeers {
   int32_t world;
   int32_t rank;
+  int32_t owned_from;
+  int32_t timeout_ms;
   void* inbox[DMVAE_MAX_PEERS];
 } DmvaeDpPeers;
 
@@ -111,18 +120,11 @@ int dmvae_decode(const DmvaeCfg* cfg, const float* packed, const float* z, uint6
                  uint64_t sample_offset, const float* start, int start_is_shared, float* out,
                  float* z_out, int64_t B, int add_start, void* stream);
 
-/* Which kernel dmvae_decode launches: 0 (default) = decode_tc_kernel, the dense layers on the
+/* Which kernel dmvae_decode launches (per host thread, like dmvae_set_train_impl): 0 (default) = decode_tc_kernel, the dense layers on the
  * tcgen05 tensor cores as error-compensated 3xTF32 with activations resident in tensor
  * memory; 1 = decode_kernel, everything in FP32 FFMA.  Both hold the 1e-5 tolerance; the
  * switch exists so that bench.py can report the two side by side. */
 int dmvae_set_decode_impl(int impl);
-/* Development aid: device buffer of 128 int64 that CTA 0 of decode_tc_kernel fills with
- * clock64 stamps per layer step (NULL = off, the default). */
-int dmvae_debug_decode_trace(void* device_int64x128);
-/* Same for chain_kernel (first tile of CTA 0): 256 int64; [4 o + 0 / 1] = MMA warp starts / has issued
- * op o, [128 + 2 e + 0 / 1] = epilogue e starts (accumulator complete) / has released the A operand. */
-int dmvae_debug_train_trace(void* device_int64x256);
-
 /* model.condition_encoder(c) on its own (Training_VAE.py:132-137; called directly
  * at Tools.py:55, :898): start (B,2) -> h_c (B,128). */
 int dmvae_cond_encode(const DmvaeCfg* cfg, const float* packed, const float* start, float* h_c, int64_t B,
@@ -153,14 +155,20 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
  * (Training_VAE.py:351-363) in three launches, no host synchronisation. */
 int64_t dmvae_grad_count(const DmvaeCfg* cfg);
 int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B);
-/* Which kernels the fused training pass launches: 0 (default) = tensor cores (tcgen05, 3xTF32:
- * chain_kernel + wgrad_kernel + reduce_tc_kernel) whenever 3*seq_len <= 64 and latent_dim <= 32,
- * the FFMA kernels otherwise; 1 = always the FP32 FFMA kernels (train_kernel + reduce_kernel);
- * 2 = tensor cores, always as two launches.  With 0, batches of at most (SMs / 4) * 128 rows run
- * the chain and the weight-gradient CTAs side by side in ONE launch (train_tc_fused_kernel): a
- * weight-gradient CTA starts on an image of its tile as soon as the chain has written it.  The
- * results of 0 and 2 are bit-identical.  All hold the tolerances of tests/test_train_gpu.py;
- * dmvae_train_workspace_bytes covers all three. */
+/* Which kernels the fused training pass launches (a per-THREAD setting: it applies to the calls the calling
+ * host thread makes afterwards, so threads driving different streams do not disturb each other):
+ *   0 (default)  tensor cores (tcgen05, 3xTF32: chain_kernel + wgrad_kernel + reduce_tc_kernel) inside their
+ *                envelope for batches of more than 128 rows; the FP32 FFMA kernels otherwise - the
+ *                reference's own batch sizes (16..135 rows, Training_VAE.py:278) are latency-bound either
+ *                way and keep the FFMA kernels' 1e-6-class gradients;
+ *   1            always the FP32 FFMA kernels (train_kernel + reduce_kernel);
+ *   2            tensor cores at any batch size, always as two launches;
+ *   3            tensor cores at any batch size.
+ * With 0 and 3, batches of at most (SMs / 4) * 128 rows run the chain and the weight-gradient CTAs side by
+ * side in ONE launch (train_tc_fused_kernel): a weight-gradient CTA starts on an image of its tile as soon
+ * as the chain has written it.  The results of 2 and 3 are bit-identical.  The entry points with a
+ * device-side step counter or data-parallel peers always run the tensor-core kernels.  All hold the
+ * tolerances of tests/test_train_gpu.py; dmvae_train_workspace_bytes covers every setting. */
 int dmvae_set_train_impl(int impl);
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps,
                         uint64_t seed, uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w,
@@ -212,9 +220,9 @@ int dmvae_adam_step_dev(const DmvaeCfg* cfg, float* params, const float* grads, 
  * (graph-capturable).  The inbox is double-buffered by step parity and every word carries its step, so
  * steps need no reset; all ranks must call with the same step.  Tensor-core path only. */
 int64_t dmvae_dp_inbox_bytes(const DmvaeCfg* cfg, int world);
-/* Smallest world size that exchanges through element owners (default 3; 2 forces the owner scheme on two
- * ranks, DMVAE_MAX_PEERS + 1 the all-to-all scheme everywhere).  All ranks must agree. */
-int dmvae_set_dp_owned_from(int world);
+/* Reads the status word of this rank's inbox (synchronises `stream`): DMVAE_OK, or DMVAE_ERR_TIMEOUT when a
+ * thread of an earlier step gave up waiting for a peer (the parameters of this rank then hold NaN). */
+int dmvae_dp_status(const DmvaeCfg* cfg, const DmvaeDpPeers* peers, void* stream);
 int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
                         const float* x, const float* eps, uint64_t seed, uint64_t sample_offset,
                         const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,

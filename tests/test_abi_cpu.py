@@ -10,10 +10,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "dmvae.h")
+DEBUG_HEADER = os.path.join(ROOT, "include", "dmvae_debug.h")
 
 
-def declared_functions():
-    text = open(HEADER).read()
+def declared_functions(header=HEADER):
+    text = open(header).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)          # comments
     return sorted(set(re.findall(r"\b(dmvae_[a-z0-9_]+)\s*\(", text)))
 
@@ -44,8 +45,10 @@ def test_ctypes_table_mirrors_the_header():
     header, table = set(declared_functions()), set(_lib.SIGNATURES)
     assert table <= header, f"bound but not declared: {sorted(table - header)}"
     # everything the Python layer does not bind is listed here on purpose (debug / unused-by-Python entry points)
-    unbound = header - table
-    assert unbound <= {"dmvae_train_step_dev_unused"} | {n for n in unbound if n.startswith("dmvae_debug_")}, sorted(unbound)
+    assert header == table, sorted(header ^ table)
+    # the development aids live in their own header, outside the drop-in boundary
+    assert not [n for n in header if n.startswith("dmvae_debug_")]
+    assert set(declared_functions(DEBUG_HEADER)) == set(_lib.DEBUG_SIGNATURES)
 
 
 def test_struct_layouts_match_the_header():
@@ -53,7 +56,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.DmvaeCfg) == 16
     assert ctypes.sizeof(_lib.DmvaeLossWeights) == 16
     assert ctypes.sizeof(_lib.DmvaeAdam) == 40
-    assert _lib.MAX_PEERS == 8 and ctypes.sizeof(_lib.DmvaeDpPeers) == 8 + 8 * 8
+    assert _lib.MAX_PEERS == 8 and ctypes.sizeof(_lib.DmvaeDpPeers) == 16 + 8 * 8
     text = open(HEADER).read()
     assert "#define DMVAE_MAX_PEERS 8" in text
     assert f"#define DMVAE_KERNEL_COUNT {_lib.KERNEL_COUNT}" in text
@@ -61,12 +64,13 @@ def test_struct_layouts_match_the_header():
 
 def test_host_side_queries(lib):
     from dmvae import _lib
-    assert lib.dmvae_abi_version() == 1
+    assert lib.dmvae_abi_version() == _lib.ABI_VERSION == 2
+    assert f"#define DMVAE_ABI_VERSION {_lib.ABI_VERSION}" in open(HEADER).read()
     cfg = _lib.cfg(10, 8)
     assert lib.dmvae_param_count(ctypes.byref(cfg)) == 128942          # T = 10, L = 8
     assert lib.dmvae_grad_count(ctypes.byref(cfg)) == 128942 + 5
     assert lib.dmvae_packed_count(ctypes.byref(cfg)) > 128942
-    assert lib.dmvae_dp_inbox_bytes(ctypes.byref(cfg), 8) == (8 + 1) * 2 * 128948 * 8
+    assert lib.dmvae_dp_inbox_bytes(ctypes.byref(cfg), 8) == (8 + 1) * 2 * 128948 * 8 + 16
     cfg400 = _lib.cfg(400, 64)
     assert lib.dmvae_grad_count(ctypes.byref(cfg400)) == 465589        # T = 400, L = 64 (+ 5 loss terms)
     bad = _lib.cfg(401, 8)

@@ -37,7 +37,7 @@ def impl(request):
     """Selects the kernels behind the fused training pass for one test, then restores the default."""
     from dmvae import _lib
     lib = _lib.lib()
-    _lib.check(lib.dmvae_set_train_impl(0 if request.param == "tc" else 1), "dmvae_set_train_impl")
+    _lib.check(lib.dmvae_set_train_impl(3 if request.param == "tc" else 1), "dmvae_set_train_impl")   # 3: tensor cores at any batch size
     yield request.param
     _lib.check(lib.dmvae_set_train_impl(0), "dmvae_set_train_impl")
 
@@ -366,7 +366,7 @@ def test_overlapped_launch_is_bit_identical_to_two_launches(B):
         _lib.check(lib.dmvae_set_train_impl(2), "dmvae_set_train_impl")
         l2, g2 = tr.loss_and_grads(batch)          # eps: in-kernel Philox (seed of the trainer, step 1)
         l2, g2 = l2.clone(), g2.clone()
-        _lib.check(lib.dmvae_set_train_impl(0), "dmvae_set_train_impl")
+        _lib.check(lib.dmvae_set_train_impl(3), "dmvae_set_train_impl")
         for rep in range(25):
             l0, g0 = tr.loss_and_grads(batch)
             if B <= 4096:    # same units, same slabs, same order of every sum
