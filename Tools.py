@@ -6,9 +6,15 @@ In scope: ``load_model_and_generate_trajectory
 the entry points need, ``get_start_conditions_from_csv`` (``:69-134``) and
 ``plot_losses`` (``:662-771``).  New, additive: ``generate_trajectories`` - the
 batched sample-and-decode the reference runs one trajectory (and one checkpoint
-load) at a time.  The rest of the reference's ``Tools.py`` (GIF animation, curve
-smoothing, CSV re-stamping) is plotting glue outside the accelerated path and is
-not provided.
+load) at a time.
+
+The rest of the reference's ``Tools.py`` (``get_human_and_bv_trajectories``, GIF
+animation, ``create_smooth_curve``, CSV re-stamping: plotting / CSV glue outside the
+accelerated path) is NOT re-implemented.  Its callers (``Distribution.py:10``,
+``Plot_case.py:11``, ``Traj_Tracking_Intact.py:5-6``, ``Plot_Gif.py:24``) keep working
+when the reference's own file stays next to this one under the name ``Tools_host.py``:
+every public name this module does not define is taken from there (INTEGRATION.md
+section 2).  Without that file those names raise an ImportError that says so.
 """
 import csv
 import math
@@ -16,7 +22,14 @@ import os
 import sys
 
 import numpy as np
+import pandas as pd  # noqa: F401
 import torch
+# names the reference's ``from Tools import *`` hands to its importers (Tools.py:1-14, star-imported at
+# Training_VAE.py:102): kept importable from here
+import torch.nn as nn  # noqa: F401
+import torch.optim as optim  # noqa: F401
+from torch.utils.data import DataLoader, Dataset  # noqa: F401
+from tqdm import tqdm  # noqa: F401
 
 _PKG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "defensive-model-vae_b200")
 if _PKG not in sys.path:
@@ -126,7 +139,6 @@ def get_start_conditions_from_csv(csv_path, model_name):
     dx, dy = _DEFAULT_START[key]
     fallback = (dx, dy, -90 * math.pi / 180)
     try:
-        import pandas as pd
         df = pd.read_csv(csv_path)
         mask = _start_mask(df, key)
         if not mask.any():
@@ -240,3 +252,36 @@ def visualize_trajectories(model, dataset, model_save_path, axis_flip='none', us
     plt.close(fig)
     print(f"figure saved to {out}")
     return train_data, generated
+
+
+# ------------------------------------------------------------------------------------------
+# the rest of the reference's Tools.py: served from the reference's own file, kept as Tools_host.py
+# ------------------------------------------------------------------------------------------
+_HOST_NAMES = ("get_human_and_bv_trajectories", "process_model_trajectory", "create_vehicle_rectangle",
+               "plot_gif_human_vs_model", "save_animation_as_gif", "create_smooth_curve")   # reference Tools.py:138-830
+
+
+def _merge_host_module():
+    """Every public name of ``Tools_host`` (the reference's unmodified Tools.py under that name) that this module
+    does not define itself becomes importable from here; the accelerated entry points above always win."""
+    try:
+        import importlib
+        host = importlib.import_module("Tools_host")
+    except ImportError:
+        return False
+    mine = globals()
+    for name, value in vars(host).items():
+        if not name.startswith("_") and name not in mine:
+            mine[name] = value
+    return True
+
+
+_HOST_MERGED = _merge_host_module()
+
+
+def __getattr__(name):
+    if name in _HOST_NAMES:
+        raise ImportError(
+            f"Tools.{name} is plotting / CSV glue of the reference's Tools.py that the B200 drop-in does not "
+            "re-implement: keep the reference's file next to this one as Tools_host.py (INTEGRATION.md section 2)")
+    raise AttributeError(f"module 'Tools' has no attribute {name!r}")

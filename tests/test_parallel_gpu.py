@@ -159,6 +159,7 @@ def _dp_graph_worker(rank, world, port, tmp, exchange):
                               owned_from=owned_from)
     assert dpa.exchange == kind, dpa.exchange_note
     ha = [dpa.step(b[lo:hi].cuda()).cpu().clone() for b in batches]
+    pa4 = model_a.flat_parameters().cpu().clone()
     # ... against the same steps replayed from one CUDA graph (exchange / all-reduce captured inside)
     model_b, _ = _model(seed=6)
     dpb = DataParallelTrainer(FusedTrainer(model_b, lr=1e-3, weights=O.SCRIPT_WEIGHTS, seed=77), exchange=kind,
@@ -199,7 +200,7 @@ def _dp_graph_worker(rank, world, port, tmp, exchange):
         assert (pa - pc).abs().max().item() <= 1e-6 * pa.abs().max().item()
         gc.graph.reset()
     if rank == 0:
-        torch.save({"params": pa, "hist": torch.stack(ha)}, os.path.join(tmp, "graph.pt"))
+        torch.save({"params": pa, "params4": pa4, "hist": torch.stack(ha)}, os.path.join(tmp, "graph.pt"))
     # the graph holds captured NCCL work: release it before the communicator goes away
     gs.graph.reset()
     del gs
@@ -226,11 +227,17 @@ def test_graph_step_matches_host_driven_step(tmp_path, world, exchange):
     batches = [_batch(B, 20 + s).cuda() for s in range(steps)]
     hist = torch.stack([tr.step(b).cpu().clone() for b in batches])
     np.testing.assert_allclose(got["hist"].numpy(), hist.numpy(), rtol=1e-5, atol=1e-7)
+    ref4 = model.flat_parameters().cpu().clone()
+    assert (got["params4"] - ref4).abs().max().item() <= 2e-5 * ref4.abs().max().item() + 2e-5
     for rep in range(5):
         for b in batches:
             tr.step(b)
+    # 24 updates: Adam turns a rounding-level difference of a near-zero gradient into a +-lr difference of that one
+    # parameter (update = lr * g / (|g| + eps)), so single elements drift apart; the update as a whole must not
     ref = model.flat_parameters().cpu()
-    assert (got["params"] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-5   # 24 updates of fp32 drift
+    p0 = _model(seed=6)[0].flat_parameters().cpu()
+    drift = ((got["params"] - ref).norm() / (ref - p0).norm()).item()
+    assert drift < 0.02, drift
 
 
 def _dp_timeout_worker(rank, world, port, tmp):
