@@ -49,7 +49,11 @@ def _cached_model(model_path, seq_len, dim, latent_dim):
     key = (os.path.abspath(model_path), st.st_mtime_ns, st.st_size, seq_len, dim, latent_dim)
     model = _MODEL_CACHE.get(key)
     if model is None:
-        model = ConditionalTrajectoryVAE(seq_len, dim, latent_dim)
+        # the default initialisation draws from the host generator: forked, so that a cache miss and a cache hit
+        # leave the caller's RNG stream in the same state (the draws the reference makes are burnt explicitly,
+        # _burn_init_draws)
+        with torch.random.fork_rng(devices=[]):
+            model = ConditionalTrajectoryVAE(seq_len, dim, latent_dim)
         model.load_state_dict(torch.load(model_path, map_location='cpu'))
         model.eval()
         if len(_MODEL_CACHE) >= 16:
