@@ -540,7 +540,11 @@ int dmvae_debug_decode_trace(void* device_int64x128) {
 }
 
 int dmvae_debug_train_trace(void* device_int64x256) {
-  dmvae::set_chain_trace(static_cast<long long*>(device_int64x256));
+  dmvae::set_chain_trace(static_cast<long long*>(device_int64x256), 0);
+  return DMVAE_OK;
+}
+int dmvae_debug_train_trace_tile(void* device_int64x256, int tile) {
+  dmvae::set_chain_trace(static_cast<long long*>(device_int64x256), tile);
   return DMVAE_OK;
 }
 

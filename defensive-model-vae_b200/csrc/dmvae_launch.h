@@ -71,7 +71,7 @@ struct TrainTcPlan {
                               // finished-block counter of the reduction
 };
 bool train_tc_supported(const Layout& lo);
-void set_chain_trace(long long* device_buffer);  // development aid (256 int64), null = off
+void set_chain_trace(long long* device_buffer, int tile = 0);  // development aid (256 int64), null = off; which of CTA 0's tiles
 TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overlap = -1);  // -1: the current setting
 cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainIO& io, float* stash, float* loss_part,
                          cudaStream_t stream);

@@ -61,13 +61,17 @@ constexpr int CH_EPI_WARPS = 8;
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
 constexpr int CH_PRODUCER_WARP = CH_EPI_WARPS;
 constexpr int CH_MMA_WARP = CH_EPI_WARPS + 1;
-constexpr int CH_THREADS = (CH_MMA_WARP + 1) * 32;
+constexpr int CH_SIGNAL_WARP = CH_EPI_WARPS + 2;   // publishes the per-tile progress counter of the fused launch
+constexpr int CH_THREADS = (CH_SIGNAL_WARP + 1) * 32;
 constexpr int CH_M = 128;
-constexpr int CH_MAX_OPS = 24;
+constexpr int CH_MAX_OPS = 28;
 // tensor-memory columns: accumulator, then the A operand regions (128 main + 64 extra each)
 constexpr uint32_t CT_D = 0, CT_AHI = 128, CT_ALO = 320, CT_X = 128, CT_COLS = 512;
 constexpr uint32_t CT_DX = CT_AHI + CT_X;  // small accumulators (heads, d/dz) live in the extra A_hi columns
-constexpr uint32_t CT_ONES = CT_ALO + CT_X + 56;  // constant A columns [1, 0 x 7]: multiply the bias row of a weight image
+// the start point of the tile's rows, [x0, y0, 1, 0 x 5] as TF32 high and low halves: the A operand of cond0.  It is
+// staged at the start of a tile, long before cond0 runs (after the encoder), in extra A_lo columns that nothing else
+// uses during the forward half (z occupies the first Lp16 <= 32 of them)
+constexpr uint32_t CT_START_HI = CT_ALO + CT_X + 32, CT_START_LO = CT_ALO + CT_X + 40;
 
 struct COp {
   int off_hi, off_lo;  // planes of the layer image in the packed arena (floats): forward or data-gradient image
@@ -76,12 +80,11 @@ struct COp {
   int kps;             // forward: K steps per ring stage; data gradient: contraction steps per group (= per stage)
   int S;               // data gradient: slices in the whole image
   int dgrad;           // 0 forward (B read K-major); 1 data gradient (B read MN-major)
-  int a_col;           // column inside the A regions of the first contraction step
+  int a_hi, a_lo;      // tensor-memory columns of the first contraction step of the A operand (TF32 high / low halves)
   int d_col;           // tensor-memory column of the accumulator (dgrad: of the first slice)
   int acc;             // accumulate onto what the accumulator already holds
   int wait_a;          // wait for the epilogue warps before issuing (A operand written, D drained)
   int commit_d;        // signal the epilogue warps when the accumulator is complete
-  int bias_k;          // forward: K step of the image that holds the bias row (multiplied by the ones column), or -1
   int pipe;            // 128 x 128 layer behind a four-phase epilogue: issued as 2 x 4 blocks (output half n, 32-deep
                        // contraction quarter k), each as soon as the epilogue of the previous layer has released what
                        // it needs; the first output half is committed before the second is issued (see the MMA warp)
@@ -100,8 +103,9 @@ struct ChainArgs {
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
   COp ops[CH_MAX_OPS];   // the per-tile GEMM program (chain_program, built on the host)
-  int pipe_on;           // the 128 x 128 layers are issued pipelined (their bias is added by the epilogue)
-  long long* trace;   // development aid: clock64 stamps of CTA 0, first tile (null in production)
+  int n_ops;
+  long long* trace;   // development aid: clock64 stamps of CTA 0, one of its tiles (null in production)
+  int trace_tile;     // which of CTA 0's tiles (0 = its first)
   int* ready;         // when set: per-tile counter, +1 per epilogue warp and epilogue, once the stash images of that
                       // epilogue are written (the weight-gradient CTAs of train_tc_fused_kernel wait on it)
 };
@@ -112,20 +116,25 @@ struct ChainKArgs {
 
 __host__ __device__ inline COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
                                     int wait_a = 1, int commit_d = 1) {
-  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_col, d_col, acc, wait_a, commit_d, -1, 0};
-  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_col, d_col, acc, wait_a, commit_d, -1, 0};
+  const int a_hi = (int)CT_AHI + a_col, a_lo = (int)CT_ALO + a_col;
+  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_hi, a_lo, d_col, acc, wait_a, commit_d, 0};
+  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_hi, a_lo, d_col, acc, wait_a, commit_d, 0};
 }
 
 // The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
 // commit_d is followed by exactly one epilogue of the tile body below (same order).
+//
+// Forward order: the encoder first (its input x_rel and the start point are staged at the START of a tile, before
+// any accumulator exists to wait for), its share of the heads kept aside, then the condition encoder, whose output
+// h_c stays in the A operand for the three products that read it (its share of the heads, and the h_c rows of the
+// first decoder layer, issued back to back); the reparameterisation runs on the CUDA cores UNDER the decoder
+// product and only adds the z rows afterwards.  No bias travels through the tensor cores: every epilogue adds its own.
 __host__ __device__ inline int chain_program(const Layout& lo, COp* ops, int stages) {
   const int zs = lo.Lp16 / 8;
   const int pipe = stages >= 4 ? 1 : 0;   // a pipelined layer holds its four weight stages at once
   int n = 0;
-  auto fwd = [&](int t, int k0, int nk, int d_col, int acc, bool with_bias, int piped = 0) {
-    COp o = c_op(lo.tc[t], k0, nk, 0, 0, d_col, acc);
-    // a pipelined layer gets its bias in the epilogue (the bias stage would be a fifth stage of a four-stage ring)
-    if (with_bias && !(piped && pipe)) o.bias_k = lo.tc[t].K / 8;
+  auto fwd = [&](int t, int k0, int nk, int a_col, int d_col, int acc, int wait_a = 1, int commit_d = 1, int piped = 0) {
+    COp o = c_op(lo.tc[t], k0, nk, 0, a_col, d_col, acc, wait_a, commit_d);
     o.pipe = piped && pipe;
     ops[n++] = o;
   };
@@ -134,23 +143,27 @@ __host__ __device__ inline int chain_program(const Layout& lo, COp* ops, int sta
     o.pipe = piped && pipe;
     ops[n++] = o;
   };
-  fwd(TC_COND0, 0, 1, CT_D, 0, false);              // start -> hc1 (bias row inside its K = 8)
-  fwd(TC_COND1, 0, 16, CT_D, 0, true, 1);           // hc1 -> hc
-  fwd(TC_HEADS, 16, 16, CT_DX, 0, false);           // hc share of the heads (kept aside)
-  fwd(TC_ENC0, 0, lo.Ip / 8, CT_D, 0, true);        // x_rel -> e1
-  fwd(TC_ENC1, 0, 16, CT_D, 0, true, 1);
-  fwd(TC_ENC2, 0, 16, CT_D, 0, true, 1);
-  fwd(TC_ENC3, 0, 16, CT_D, 0, true, 1);            // -> e4
-  fwd(TC_HEADS, 0, 16, CT_DX, 1, true);             // + h_traj share + bias -> mu, logvar
-  fwd(TC_DEC0, 0, 16 + zs, CT_D, 0, true);          // [hc ; z] -> d1
-  fwd(TC_DEC1, 0, 16, CT_D, 0, true, 1);
-  fwd(TC_DEC2, 0, 16, CT_D, 0, true, 1);
-  fwd(TC_DEC3, 0, 16, CT_D, 0, true);               // -> recon
+  fwd(TC_ENC0, 0, lo.Ip / 8, 0, CT_D, 0);           // x_rel -> e1
+  fwd(TC_ENC1, 0, 16, 0, CT_D, 0, 1, 1, 1);
+  fwd(TC_ENC2, 0, 16, 0, CT_D, 0, 1, 1, 1);
+  fwd(TC_ENC3, 0, 16, 0, CT_D, 0, 1, 1, 1);         // -> e4
+  fwd(TC_HEADS, 0, 16, 0, CT_DX, 0, 1, 0);          // h_traj share of the heads (kept aside, no epilogue)
+  fwd(TC_COND0, 0, 1, 0, CT_D, 0, 0, 1);            // start -> hc1 (bias row inside its K = 8)
+  ops[n - 1].a_hi = (int)CT_START_HI;
+  ops[n - 1].a_lo = (int)CT_START_LO;
+  fwd(TC_COND1, 0, 16, 0, CT_D, 0, 1, 1, 1);        // hc1 -> hc
+  fwd(TC_HEADS, 16, 16, 0, CT_DX, 1, 1, 1);         // + hc share -> mu, logvar: the reparameterisation epilogue
+  fwd(TC_DEC0, 0, 16, 0, CT_D, 0, 0, 0);            // hc rows of dec0, running under that epilogue
+  fwd(TC_DEC0, 16, zs, CT_X, CT_D, 1, 1, 1);        // + z rows -> d1
+  fwd(TC_DEC1, 0, 16, 0, CT_D, 0, 1, 1, 1);
+  fwd(TC_DEC2, 0, 16, 0, CT_D, 0, 1, 1, 1);
+  fwd(TC_DEC3, 0, 16, 0, CT_D, 0);                  // -> recon
   bwd(TC_DEC3, 0, 4, 0, CT_D, 0);                   // d recon -> d d3 (4 slices of 32 columns)
   bwd(TC_DEC2, 0, 4, 0, CT_D, 0, 1, 1, 1);
   bwd(TC_DEC1, 0, 4, 0, CT_D, 0, 1, 1, 1);
-  bwd(TC_DEC0, 0, 4, 0, CT_D, 0, 1, 0);             // d d1 -> d hc (decoder share)
-  bwd(TC_DEC0, 4, 1, 0, CT_DX, 0, 0, 1);            //      -> d z (one slice)
+  bwd(TC_DEC0, 4, 1, 0, CT_DX, 0, 1, 1);            // d d1 -> d z (one slice) first: its epilogue (the reparameterisation
+                                                    // backward, CUDA cores) runs under the next product
+  bwd(TC_DEC0, 0, 4, 0, CT_D, 0, 0, 0);             //      -> d hc (decoder share), no epilogue of its own
   bwd(TC_HEADS, 4, 4, CT_X, CT_D, 1);               // d (mu, logvar) -> + encoder share of d hc
   bwd(TC_COND1, 0, 4, 0, CT_D, 0, 1, 1, 1);         // d hc -> d hc1
   bwd(TC_HEADS, 0, 4, CT_X, CT_D, 0);               // d (mu, logvar) -> d e4
@@ -165,15 +178,16 @@ enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_
 // The epilogues of a tile, in the order of the ops that signal them (chain_program).  The tile body is a
 // loop over this table rather than 22 inlined epilogues: the code stays small enough for the instruction
 // cache (the unrolled version spent as many issue slots waiting for instructions as for memory).
-enum EpiType { EP_HIDDEN = 0, EP_XREL, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
-constexpr int CH_EPIS = 22;
+enum EpiType { EP_HIDDEN = 0, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
+constexpr int CH_EPIS = 21;
+constexpr int CH_EPI_FIRST_DGRAD = 11;
 __constant__ int c_epi[CH_EPIS][5] = {
     // type, mask slot, stash slot (the image the epilogue completes), write the A operand, layer whose bias the
-    // epilogue adds when the op before it is pipelined (-1: the bias, if any, came through the MMA)
-    {EP_HIDDEN, MK_HC1, SX_HC1, 1, -1},     {EP_HIDDEN, MK_HC, SX_HC, 1, L_COND1},  {EP_XREL, 0, SX_X, 0, -1},
-    {EP_HIDDEN, MK_E1, SX_E1, 1, -1},       {EP_HIDDEN, MK_E2, SX_E2, 1, L_ENC1},   {EP_HIDDEN, MK_E3, SX_E3, 1, L_ENC2},
-    {EP_HIDDEN, MK_E4, SX_E4, 1, L_ENC3},   {EP_HEADS, 0, SX_Z, 0, -1},             {EP_HIDDEN, MK_D1, SX_D1, 1, -1},
-    {EP_HIDDEN, MK_D2, SX_D2, 1, L_DEC1},   {EP_HIDDEN, MK_D3, SX_D3, 1, L_DEC2},   {EP_LOSS, 0, SG_REC, 0, -1},
+    // epilogue adds (-1: none - cond0 carries its bias row inside its K = 8)
+    {EP_HIDDEN, MK_E1, SX_E1, 1, L_ENC0},   {EP_HIDDEN, MK_E2, SX_E2, 1, L_ENC1},   {EP_HIDDEN, MK_E3, SX_E3, 1, L_ENC2},
+    {EP_HIDDEN, MK_E4, SX_E4, 1, L_ENC3},   {EP_HIDDEN, MK_HC1, SX_HC1, 1, -1},     {EP_HIDDEN, MK_HC, SX_HC, 1, L_COND1},
+    {EP_HEADS, 0, SX_Z, 0, -1},             {EP_HIDDEN, MK_D1, SX_D1, 1, L_DEC0},   {EP_HIDDEN, MK_D2, SX_D2, 1, L_DEC1},
+    {EP_HIDDEN, MK_D3, SX_D3, 1, L_DEC2},   {EP_LOSS, 0, SG_REC, 0, -1},
     {EP_DGRAD, MK_D3, SG_D3, 1, -1},        {EP_DGRAD, MK_D2, SG_D2, 1, -1},        {EP_DGRAD, MK_D1, SG_D1, 1, -1},
     {EP_BDEC0, 0, SG_ML, 0, -1},            {EP_DGRAD, MK_HC, SG_HC, 1, -1},        {EP_DGRAD, MK_HC1, SG_HC1, 0, -1},
     {EP_DGRAD, MK_E4, SG_E4, 1, -1},        {EP_DGRAD, MK_E3, SG_E3, 1, -1},        {EP_DGRAD, MK_E2, SG_E2, 1, -1},
@@ -182,7 +196,8 @@ __constant__ int c_epi[CH_EPIS][5] = {
 
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
   return (size_t)stages * STAGE_FLOATS + (size_t)lo.Ip * 128 /* recon scratch */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
-         (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */;
+         (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */ +
+         NUM_LAYERS * 128 /* biases */;
 }
 __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
   return chain_smem_floats(lo, stages) * 4 + 32 * 8 + 16 + 1024;
@@ -192,13 +207,14 @@ __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages)
 __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a, const int cta, const int ncta,
                                            unsigned char* smem_dyn) {
   const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
-  float *ring, *scratch, *xbuf, *mlb, *epb;
+  float *ring, *scratch, *xbuf, *mlb, *epb, *bias_s;
   uint32_t* masks;
   const COp* ops = a.ops;   // kernel parameter space: uniform reads by the producer and the MMA warp
   // d_ready[n]: output half n of the accumulator is complete (MMA -> epilogue); a_ready[k]: quarter k of the A
   // operand is written and quarter k of the accumulator has been read (epilogue -> MMA); a_free[k]: every MMA that
   // reads quarter k of the A operand has completed (MMA -> epilogue)
-  uint64_t *full, *empty, *d_ready, *a_ready, *a_free;
+  // stash_done: every epilogue warp has issued the stash stores of the current epilogue (epilogue -> signal warp)
+  uint64_t *full, *empty, *d_ready, *a_ready, *a_free, *stash_done;
   uint32_t* tmem_slot;
   {
     const uint32_t base = smem_u32(smem_dyn);
@@ -209,12 +225,14 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     mlb = xbuf + round_up(128 * I, 4);
     epb = mlb + (size_t)NH * 128;
     masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
-    full = reinterpret_cast<uint64_t*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
+    bias_s = reinterpret_cast<float*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
+    full = reinterpret_cast<uint64_t*>(bias_s + NUM_LAYERS * 128);
     empty = full + 8;
     d_ready = empty + 8;
     a_ready = d_ready + 2;
     a_free = a_ready + 4;
-    tmem_slot = reinterpret_cast<uint32_t*>(a_free + 4);
+    stash_done = a_free + 4;
+    tmem_slot = reinterpret_cast<uint32_t*>(stash_done + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
@@ -232,6 +250,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       mbar_init(&a_ready[k], CH_EPI_WARPS);
       mbar_init(&a_free[k], 1);
     }
+    mbar_init(stash_done, CH_EPI_WARPS);
     mbar_fence_init();
   }
   if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
@@ -239,7 +258,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  constexpr int n_ops = 23;
+  const int n_ops = a.n_ops;
 
   if (warp == CH_PRODUCER_WARP) {
     // ===================== producer warp: weight planes L2 -> smem ring =======================
@@ -253,16 +272,6 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               const int nks = min(op.kps, op.nk - k);
               const int fl = nks * op.N * 8;
               const size_t src = (size_t)(op.k0 + k) * op.N * 8;
-              float* dst = ring + rs.stage * STAGE_FLOATS;
-              mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
-              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
-              tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
-              tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
-              rs.advance();
-            }
-            if (op.bias_k >= 0) {  // one more stage: the K step with the bias row
-              const int fl = op.N * 8;
-              const size_t src = (size_t)op.bias_k * op.N * 8;
               float* dst = ring + rs.stage * STAGE_FLOATS;
               mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
               mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
@@ -292,7 +301,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     for (long long tile = cta; tile < n_tiles; tile += ncta)
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
-        const bool tr = a.trace != nullptr && cta == 0 && tile == cta && lane == 0;
+        const bool tr = a.trace != nullptr && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
         if (op.pipe) {
           // ---- a 128 x 128 layer in 2 x 4 blocks (output half n = 64 columns, contraction quarter k = one ring
           // stage = 32 columns of the A operand).  Block (n, k) needs quarter k of A (a_ready[k]) and half n of
@@ -314,7 +323,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
                 if (tr && k == 0) { a.trace[o * 4 + 0] = clock64(); if (o == 0) a.trace[178] = global_ns(); }
               }
               const uint32_t b_hi = smem_u32(ring + slot[k] * STAGE_FLOATS);
-              const uint32_t a_hi0 = tmem + CT_AHI + (uint32_t)(op.a_col + 32 * k), a_lo0 = tmem + CT_ALO + (uint32_t)(op.a_col + 32 * k);
+              const uint32_t a_hi0 = tmem + (uint32_t)(op.a_hi + 32 * k), a_lo0 = tmem + (uint32_t)(op.a_lo + 32 * k);
               const uint32_t accf0 = (op.acc || k > 0) ? 1u : 0u;
               if (!op.dgrad) {
                 // forward: stage = 4 K steps of the K-major planes [k-step][k-chunk][n-group of 8][8 n][4 k]; output
@@ -390,7 +399,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
             uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)(b_lo >> 4);
             const uint64_t dinc = (uint64_t)(unit_bytes >> 4);
-            uint32_t a_hi = tmem + CT_AHI + (uint32_t)(op.a_col + 8 * k), a_lo = tmem + CT_ALO + (uint32_t)(op.a_col + 8 * k);
+            uint32_t a_hi = tmem + (uint32_t)(op.a_hi + 8 * k), a_lo = tmem + (uint32_t)(op.a_lo + 8 * k);
             uint32_t accf = (op.acc || k > 0) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll 4
@@ -406,20 +415,6 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             __syncwarp();
             rs.advance();
           }
-          if (op.bias_k >= 0) {  // D += ones column x bias row (high and low halves)
-            mbar_wait(&full[rs.stage], rs.phase);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
-            const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
-            const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
-            if (elect_one()) {
-              umma_tf32_ts(tmem + (uint32_t)op.d_col, tmem + CT_ONES, dbits | (uint64_t)(b_hi >> 4), idesc, 1u);
-              umma_tf32_ts(tmem + (uint32_t)op.d_col, tmem + CT_ONES, dbits | (uint64_t)((b_hi + unit_bytes) >> 4), idesc, 1u);
-              umma_commit(&empty[rs.stage]);
-            }
-            __syncwarp();
-            rs.advance();
-          }
         } else {
           // D[128 x 32 nk] (+)= G[128 x N] x W[:, those inputs]; B MN-major (32-byte swizzle): LBO = slice
           // stride (next 32 outputs) = gsz KB, SBO = 512 (next 4 of the contraction); step st of the group
@@ -429,7 +424,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           const uint32_t idesc = umma_idesc_tf32(CH_M, 32 * op.nk, UMMA_B_MN);
           const uint64_t dbits = umma_desc(0u, (uint32_t)op.kps * 1024u, 512u, 1u);
           const uint32_t d = tmem + (uint32_t)op.d_col;
-          uint32_t a_hi = tmem + CT_AHI + (uint32_t)op.a_col, a_lo = tmem + CT_ALO + (uint32_t)op.a_col;
+          uint32_t a_hi = tmem + (uint32_t)op.a_hi, a_lo = tmem + (uint32_t)op.a_lo;
           uint32_t accf = op.acc ? 1u : 0u;
           for (int jg = 0; jg < ngroups; ++jg) {
             mbar_wait(&full[rs.stage], rs.phase);
@@ -447,8 +442,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               umma_commit(&empty[rs.stage]);
             }
             __syncwarp();
-            a_hi = tmem + CT_AHI + (uint32_t)(op.a_col + 8 * (jg + 1) * op.kps);
-            a_lo = tmem + CT_ALO + (uint32_t)(op.a_col + 8 * (jg + 1) * op.kps);
+            a_hi = tmem + (uint32_t)(op.a_hi + 8 * (jg + 1) * op.kps);
+            a_lo = tmem + (uint32_t)(op.a_lo + 8 * (jg + 1) * op.kps);
             accf = 1u;
             rs.advance();
           }
@@ -464,6 +459,24 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         }
         if (tr) a.trace[o * 4 + 1] = clock64();
       }
+  } else if (warp == CH_SIGNAL_WARP) {
+    // ===================== signal warp (fused launch only) ======================================
+    // Publishes the chain's progress to the weight-gradient CTAs: once all eight epilogue warps have issued the
+    // stash stores of an epilogue (their arrival on stash_done releases those stores to this thread), one thread
+    // makes them visible device-wide - also to the bulk copies (async proxy) of the other CTAs - and bumps the
+    // tile's counter.  The device-scope fence is cumulative over the stores it has observed through the barrier;
+    // keeping it in this warp takes it off the epilogue warps' critical path (it costs several hundred cycles).
+    if (lane == 0 && a.ready != nullptr) {
+      uint32_t phase = 0;
+      for (long long tile = cta; tile < n_tiles; tile += ncta)
+        for (int e = 0; e < CH_EPIS; ++e) {
+          mbar_wait(stash_done, phase);
+          phase ^= 1u;
+          fence_proxy_async_global();
+          __threadfence();
+          atomicAdd(a.ready + tile, CH_EPI_WARPS);
+        }
+    }
   } else {
     // ===================== epilogue warps =======================================================
     const int q = warp & 3, h = warp >> 2;   // tensor-memory lane quarter, column half
@@ -488,7 +501,17 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       mbar_wait(&a_free[k], d_phase);
       tc_fence_after();
     };
+    // the warp's stash stores of this epilogue are issued: tell the signal warp.  Always BEFORE the warp's last
+    // arrival on a_ready of the same epilogue, so that no warp can be an epilogue ahead of a warp that has not
+    // reported yet (the next epilogue starts only after all eight a_ready arrivals).
+    auto report_stash = [&]() {
+      if (a.ready != nullptr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stash_done);
+      }
+    };
     auto arrive_q = [&](int k) {           // this warp has read accumulator quarter k and written quarter k of A
+      if (k == 3) report_stash();
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -500,20 +523,13 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll
       for (int k = 0; k < 4; ++k) wait_free(k);
     };
-    long long flag_tile = -1;   // tile whose counter the next release bumps (none before the first epilogue)
     auto finish_epilogue = [&]() {
-      if (lane == 0 && a.ready != nullptr && flag_tile >= 0) {
-        // the warp's stash stores (ordered before this lane by the __syncwarp of the last arrival) -> visible
-        // device-wide, also to the bulk copies (async proxy) of the weight-gradient CTAs, before the counter moves
-        fence_proxy_async_global();
-        __threadfence();
-        atomicAdd(a.ready + flag_tile, 1);
-      }
       d_phase ^= 1u;
       if (tr_tile && tid == 0) a.trace[128 + epi_no * 2 + 1] = clock64();
       ++epi_no;
     };
-    auto arrive_all = [&]() {
+    auto arrive_all = [&](bool epilogue = true) {
+      if (epilogue) report_stash();
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -530,25 +546,79 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
       return reinterpret_cast<float4*>(tile_stash + lo.slot_off[slot] + mn_image_index(4 * chunk, m, 128, lo.slot_w[slot] * 4));
     };
-    // start point of the tile's row -> A columns [x0, y0, 1, 0...] and the 16-wide stash image
+    // start point of the tile's row -> the A columns of cond0, [x0, y0, 1, 0...], and the 16-wide stash image
     auto stage_start = [&](long long tile) {
       if (h == 0) {
         const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];   // zeros past the batch end
         uint32_t xh, xl, yh, yl;
         split_tf32(sx, xh, xl);
         split_tf32(sy, yh, yl);
-        tmem_st4(lane_base + CT_AHI, xh, yh, __float_as_uint(1.0f), 0u);
-        tmem_st4(lane_base + CT_AHI + 4, 0u, 0u, 0u, 0u);
-        tmem_st4(lane_base + CT_ALO, xl, yl, 0u, 0u);
-        tmem_st4(lane_base + CT_ALO + 4, 0u, 0u, 0u, 0u);
-        // the constant ones column: with 2 * latent_dim > 56 the (mu, logvar) gradient of the previous tile's backward
-        // half reached into it (the low halves of the extra A columns), so every tile starts by writing it again
-        tmem_st4(lane_base + CT_ONES, __float_as_uint(1.0f), 0u, 0u, 0u);
-        tmem_st4(lane_base + CT_ONES + 4, 0u, 0u, 0u, 0u);
+        tmem_st4(lane_base + CT_START_HI, xh, yh, __float_as_uint(1.0f), 0u);
+        tmem_st4(lane_base + CT_START_HI + 4, 0u, 0u, 0u, 0u);
+        tmem_st4(lane_base + CT_START_LO, xl, yl, 0u, 0u);
+        tmem_st4(lane_base + CT_START_LO + 4, 0u, 0u, 0u, 0u);
         float* ts = a.stash + (size_t)tile * lo.tile_stash;
         *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
 #pragma unroll
         for (int c = 1; c < 8; ++c) *stash_ptr(ts, SX_START, c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // encoder input of the tile's row: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
+    // -> the A operand of enc0 and the stash image.  Like the start point it is staged before the tile's first MMA.
+    auto stage_xrel = [&](long long tile) {
+      if (h * 64 < Ip) {
+        float* ts = a.stash + (size_t)tile * lo.tile_stash;
+        const float* xr = xbuf + m * I;
+        const float sx = xr[1], sy = xr[2];
+        const int nc = min(Ip - h * 64, 64) >> 2;
+        for (int c4 = 0; c4 < nc; ++c4) {
+          float xv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = h * 64 + c4 * 4 + i;
+            float val = 0.f;
+            if (n < I) {
+              val = xr[n];
+              const int d = n % 3;
+              if (d == 1) val = val - sx;
+              else if (d == 2) val = val - sy;
+            }
+            xv[i] = val;
+          }
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + h * 64 + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + h * 64 + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SX_X, h * 16 + c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        }
+      }
+    };
+
+    // reparameterisation noise of the tile's row (injected, or Philox keyed by the global row index): nothing depends
+    // on it before the heads epilogue, so it is drawn while the first encoder product runs
+    auto stage_eps = [&](long long tile) {
+      if (h == 0) {
+        const long long row = tile * CH_M + m;
+        const bool row_ok = row < a.B;
+#pragma unroll 1
+        for (int jb = 0; jb < Lp16 / 4; ++jb) {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (row_ok && jb * 4 < L) {
+            if (a.eps != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
+            } else {
+              const unsigned long long step = a.step_dev != nullptr ? (unsigned long long)(*a.step_dev + 1) : a.step;
+              const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
+                                              (uint32_t)(step + 1));
+              e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) my_ep[(jb * 4 + i) * 128] = jb * 4 + i < L ? e4[i] : 0.f;
+        }
       }
     };
 
@@ -562,22 +632,27 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
       for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(x_batch + base + i) : 0.f;
     };
+    if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[249] = global_ns();
     load_x(cta);
-    if (h == 0) {  // the constant ones column (never overwritten)
-      tmem_st4(lane_base + CT_ONES, __float_as_uint(1.0f), 0u, 0u, 0u);
-      tmem_st4(lane_base + CT_ONES + 4, 0u, 0u, 0u, 0u);
+    // the (padded) biases of all layers: read by every epilogue, kept in shared memory for the whole launch
+    for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS) {
+      const int l = i >> 7, n = i & 127;
+      bias_s[i] = n < lo.Np[l] ? __ldg(pk + lo.q_b[l] + n) : 0.f;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+    if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[250] = global_ns();
     stage_start(cta);
-    arrive_all();
+    stage_xrel(cta);
+    arrive_all(false);   // not an epilogue: the staged images are covered by the report of the tile's first epilogue
+    if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[251] = global_ns();
 
     for (long long tile = cta; tile < n_tiles; tile += ncta) {
       const long long row = tile * CH_M + m;
       const bool row_ok = row < a.B;
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
-      tr_tile = a.trace != nullptr && cta == 0 && tile == cta;
+      tr_tile = a.trace != nullptr && cta == 0 && tile == cta + (long long)a.trace_tile * ncta;
       epi_no = 0;
-      flag_tile = tile;
+      stage_eps(tile);   // under the first encoder product
 
       // this thread's 64 features of a 128-wide stash image: base of its row, then per 4-feature chunk
       // (mn_image_index with the row part hoisted; f = h*64 + c*16 + j4*4)
@@ -593,14 +668,14 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       // Mask word w holds the columns of phases 2 w, 2 w + 1, first column in the top bit.
       auto epi_hidden = [&](int ms, int xslot, int bias_l) {
         float* xs = ts + lo.slot_off[xslot] + row_part;
-        const float* __restrict__ bias = bias_l >= 0 ? pk + lo.q_b[bias_l] + h * 16 : nullptr;
+        const float* bias = bias_l >= 0 ? bias_s + bias_l * 128 + h * 16 : nullptr;
         // one phase: 16 accumulator values -> (+ bias) relu -> mask bits, stash image, quarter c of the A operand
         auto phase = [&](const uint32_t (&v)[16], int c, uint32_t& mword) {
           float bv[16];
           if (bias != nullptr) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + j4);
+              const float4 b4 = *(reinterpret_cast<const float4*>(bias + c * 32) + j4);
               bv[4 * j4] = b4.x; bv[4 * j4 + 1] = b4.y; bv[4 * j4 + 2] = b4.z; bv[4 * j4 + 3] = b4.w;
             }
           }
@@ -684,82 +759,36 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           phase(v1, 2 * half + 1, mword);
         }
       };
-      // encoder input: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
-      auto epi_xrel = [&]() {
-      wait_d();
-      if (h * 64 < Ip) {
-        const int nc = min(Ip - h * 64, 64) >> 2;
-        for (int c4 = 0; c4 < nc; ++c4) {
-          float xv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = h * 64 + c4 * 4 + i;
-            float val = 0.f;
-            if (n < I) {
-              val = xbuf[m * I + n];
-              const int d = n % 3;
-              if (d == 1) val = val - xbuf[m * I + 1];
-              else if (d == 2) val = val - xbuf[m * I + 2];
-            }
-            xv[i] = val;
-          }
-          uint32_t hi[4], lw[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
-          tmem_st4(lane_base + CT_AHI + h * 64 + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
-          tmem_st4(lane_base + CT_ALO + h * 64 + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
-          *stash_ptr(ts, SX_X, h * 16 + c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-        }
-      }
-      release_a();
-      };
       auto epi_heads = [&]() {
-      // heads: mu, logvar (Training_VAE.py:193-196); z = mu + eps * exp(0.5 logvar) (:199-206);
-      // then [hc ; z] becomes the A operand of dec0.  hc comes back from this thread's own part of its stash
-      // image (L2); the loads are issued before waiting for the accumulator
-      float hcv[8][8];
-      {
-        const float* hs = ts + lo.slot_off[SX_HC] + row_part;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ld_global_v8(hs + unit_off(c, 0), hcv[2 * c]);
-          ld_global_v8(hs + unit_off(c, 1), hcv[2 * c + 1]);
-        }
-      }
+      // heads: mu, logvar (Training_VAE.py:193-196); z = mu + eps * exp(0.5 logvar) (:199-206); z becomes the A
+      // operand (extra columns) of the z rows of dec0.  The h_c rows of dec0 are already running on the tensor
+      // cores (h_c is still the main A operand: this epilogue must not touch it).  The KLD term of the loss
+      // (:243) is summed here, where mu and logvar are at hand.
       wait_d();
       if (h == 0) {
+        const float* bias = bias_s + L_HEADS * 128;
         for (int c = 0; c < NH / 16; ++c) {
           uint32_t v[16];
           tmem_ld16(lane_base + CT_DX + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bias[c * 16 + j];
         }
+        if (tr_tile && tid == 0) a.trace[246] = clock64();
+        float s_k = 0.f;
 #pragma unroll 1
         for (int jb = 0; jb < lo.slot_w[SX_Z] / 4; ++jb) {   // past Lp16 / 4: the zero padding of the stash image
-          float e4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (row_ok && jb * 4 < L) {
-            if (a.eps != nullptr) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
-            } else {
-              const unsigned long long step = a.step_dev != nullptr ? (unsigned long long)(*a.step_dev + 1) : a.step;
-              const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
-                                              (uint32_t)(step + 1));
-              e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
-            }
-          }
           float zv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int j = jb * 4 + i;
-            float z = 0.f, e = 0.f;
+            float z = 0.f;
             if (j < L) {
-              e = e4[i];
-              z = my_ml[j * 128] + e * expf(0.5f * my_ml[(L + j) * 128]);
+              const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128];
+              const float e_half = expf(0.5f * lv);          // exp(lv) = exp(lv / 2)^2: one exponential per element
+              z = fmaf(my_ep[j * 128], e_half, mu);
+              s_k += 1.f + lv - mu * mu - e_half * e_half;
             }
-            if (j < Lp16) my_ep[j * 128] = e;
             zv[i] = z;
           }
           if (jb < Lp16 / 4) {
@@ -771,14 +800,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           }
           *stash_ptr(ts, SX_Z, jb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t hi[16], lw[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) split_tf32(hcv[2 * c + (j >> 3)][j & 7], hi[j], lw[j]);
-        tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);   // features c*32 + h*16 .. (unit_off)
-        tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
+        if (row_ok) loss_acc[1] += -0.5f * s_k * (a.inv_batch / (float)L);
       }
       release_a();
       };
@@ -789,13 +811,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       wait_d();
       if (h == 0) {
         float* rb = scratch + m;   // [n * 128 + m]
+        const float* bias = bias_s + L_DEC3 * 128;
         for (int c = 0; c < Ip / 16; ++c) {
           uint32_t v[16];
           tmem_ld16(lane_base + CT_D + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bias[c * 16 + j];
         }
+        if (tr_tile && tid == 0) a.trace[248] = clock64();
         if (row_ok) {
           const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
           const float c_start = a.w_start * a.inv_batch;
@@ -841,13 +865,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             }
           }
           rb[(3 * (T - 1)) * 128] = g_prev;
-          float s_k = 0.f;
-          for (int j = 0; j < L; ++j) {
-            const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128];
-            s_k += 1.f + lv - mu * mu - expf(lv);
-          }
           loss_acc[0] += s_rec * (a.inv_batch / (float)I);
-          loss_acc[1] += -0.5f * s_k * (a.inv_batch / (float)L);
           loss_acc[2] += s_start * (a.inv_batch * 0.5f);
           loss_acc[3] += s_t0 * a.inv_batch + (T > 1 ? s_mono * (a.inv_batch / (float)(T - 1)) : 0.f);
         }
@@ -935,21 +953,24 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       for (int e = 0; e < CH_EPIS; ++e) {
         const int ty = c_epi[e][0];
         if (ty == EP_HIDDEN) {
-          epi_hidden(c_epi[e][1], c_epi[e][2], a.pipe_on ? c_epi[e][4] : -1);
+          epi_hidden(c_epi[e][1], c_epi[e][2], c_epi[e][4]);
         } else if (ty == EP_DGRAD) {
           const bool last = e == CH_EPIS - 1;
           epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0, last);
           // after the first data gradient every warp is past the loss (that MMA could not finish before all of
           // them had released its A operand): the x tile can be replaced by the next tile's; after the last one
-          // the next tile's start point is staged, and only then is the A operand handed over
+          // the next tile's start point and encoder input are staged, and only then is the A operand handed over
           if (next < n_tiles) {
-            if (e == 12) load_x(next);
-            else if (last) stage_start(next);
+            if (e == CH_EPI_FIRST_DGRAD) {
+              load_x(next);
+            } else if (last) {
+              asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");   // the x tile is complete
+              stage_start(next);
+              stage_xrel(next);
+            }
           }
           if (last) arrive_all();
           finish_epilogue();
-        } else if (ty == EP_XREL) {
-          epi_xrel();
         } else if (ty == EP_HEADS) {
           epi_heads();
         } else if (ty == EP_LOSS) {
@@ -993,7 +1014,7 @@ constexpr int WG_WORK_WARPS = 8;
 constexpr int WG_WORK_THREADS = WG_WORK_WARPS * 32;
 constexpr int WG_PRODUCER_WARP = WG_WORK_WARPS;
 constexpr int WG_MMA_WARP = WG_WORK_WARPS + 1;
-constexpr int WG_THREADS = (WG_MMA_WARP + 1) * 32;
+constexpr int WG_THREADS = (WG_MMA_WARP + 2) * 32;   // + one idle warp: the fused launch runs both bodies with the chain's block size
 constexpr int WG_ROWS = 16;                 // batch rows per ring stage (two 8-deep contraction steps)
 constexpr int WG_STAGE_FLOATS = 8192;       // [A_hi 2048][B_hi <= 2048][A_lo 2048][B_lo <= 2048]
 constexpr int WG_MAX_OPS = 6;
@@ -1086,7 +1107,7 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
 }
 // number of the chain epilogue (c_epi) that completes a stash image
 __device__ inline int slot_epilogue(int slot) {
-  if (slot == SX_START) return 0;   // staged before the tile's first epilogue
+  if (slot == SX_START || slot == SX_X) return 0;   // staged before the tile's first epilogue
   for (int e = 0; e < CH_EPIS; ++e)
     if (c_epi[e][2] == slot) return e;
   return CH_EPIS - 1;
@@ -1270,7 +1291,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
        __syncwarp();
      }
     }
-  } else {
+  } else if (warp < WG_WORK_WARPS) {
     // ===================== work warps: TF32 split of the raw stages, then the final write-out ======
     RingStateRt rs(WG_STAGES);
     uint32_t done_phase = 0;
@@ -1677,7 +1698,8 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
 bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && lo.NH <= 64; }
 
 static long long* g_chain_trace = nullptr;
-void set_chain_trace(long long* p) { g_chain_trace = p; }
+static int g_chain_trace_tile = 0;
+void set_chain_trace(long long* p, int tile) { g_chain_trace = p; g_chain_trace_tile = tile; }
 static thread_local bool g_tc_overlap = true;   // per host thread, like dmvae_set_train_impl
 void set_train_tc_overlap(bool on) { g_tc_overlap = on; }
 
@@ -1736,10 +1758,10 @@ static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const Tra
   a.stages = plan.chain_stages;
   a.step_dev = io.step_dev;
   a.trace = g_chain_trace;
+  a.trace_tile = g_chain_trace_tile;
   a.ready = nullptr;
   for (int o = 0; o < CH_MAX_OPS; ++o) a.ops[o] = COp{};
-  chain_program(lo, a.ops, plan.chain_stages);
-  a.pipe_on = plan.chain_stages >= 4 ? 1 : 0;
+  a.n_ops = chain_program(lo, a.ops, plan.chain_stages);
   return a;
 }
 static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs) {

@@ -91,6 +91,7 @@ ABI_VERSION = 2
 DEBUG_SIGNATURES = {
     "dmvae_debug_decode_trace": (c_int, [_P]),
     "dmvae_debug_train_trace": (c_int, [_P]),
+    "dmvae_debug_train_trace_tile": (c_int, [_P, c_int]),
 }
 
 _lib = None

@@ -18,6 +18,8 @@ int dmvae_debug_decode_trace(void* device_int64x128);
  * op o, [128 + 2 e + 0 / 1] = epilogue e starts (accumulator complete) / has released the A operand;
  * from 176: %globaltimer stamps of the launch, the weight-gradient roles and the reduction kernel. */
 int dmvae_debug_train_trace(void* device_int64x256);
+/* The same for the tile-th tile that CTA 0 walks (0 = its first): steady-state timing of a persistent CTA. */
+int dmvae_debug_train_trace_tile(void* device_int64x256, int tile);
 
 #ifdef __cplusplus
 }

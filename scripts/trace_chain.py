@@ -11,16 +11,17 @@ for p in (ROOT, os.path.join(ROOT, "defensive-model-vae_b200")):
 from dmvae import ConditionalTrajectoryVAE, _lib  # noqa: E402
 from dmvae.train import FusedTrainer  # noqa: E402
 
-OPS = ["cond0", "cond1", "heads_c", "enc0", "enc1", "enc2", "enc3", "heads_e", "dec0", "dec1", "dec2", "dec3",
-       "b_dec3", "b_dec2", "b_dec1", "b_dec0_c", "b_dec0_z", "b_heads_c", "b_cond1", "b_heads_e", "b_enc3", "b_enc2", "b_enc1"]
+OPS = ["enc0", "enc1", "enc2", "enc3", "heads_e", "cond0", "cond1", "heads_c", "dec0_c", "dec0_z", "dec1", "dec2", "dec3",
+       "b_dec3", "b_dec2", "b_dec1", "b_dec0_z", "b_dec0_c", "b_heads_c", "b_cond1", "b_heads_e", "b_enc3", "b_enc2", "b_enc1"]
 EPI_OF_OP = {}
 e = 0
 for i, n in enumerate(OPS):
-    if n != "b_dec0_c":
+    if n not in ("b_dec0_c", "heads_e", "dec0_c"):     # ops that do not commit: no epilogue of their own
         EPI_OF_OP[i] = e
         e += 1
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+TILE = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # which of CTA 0's tiles (persistent CTAs: B > 148 * 128)
 lib = _lib.lib()
 torch.manual_seed(0)
 model = ConditionalTrajectoryVAE(10, 3, 8).to("cuda")
@@ -29,13 +30,13 @@ x = torch.randn(B, 10, 3, device="cuda").cumsum(1)
 for _ in range(3):
     tr.step(x)
 buf = torch.zeros(256, dtype=torch.int64, device="cuda")
-lib.dmvae_debug_train_trace(_lib.ptr(buf))
+lib.dmvae_debug_train_trace_tile(_lib.ptr(buf), TILE)
 tr.step(x)
 torch.cuda.synchronize()
 lib.dmvae_debug_train_trace(None)
 t = buf.cpu().tolist()
 t0 = t[0]
-print(f"B={B}: per op [mma start -> issued] | [epilogue start -> released]  (cycles from first MMA start)")
+print(f"B={B}, tile {TILE} of CTA 0: per op [mma start -> issued] | [epilogue start -> released]  (cycles from first MMA start)")
 for i, n in enumerate(OPS):
     ms, mi = t[4 * i] - t0, t[4 * i + 1] - t0
     line = f"{n:10s} mma {ms:7d} -> {mi:7d} (+{mi - ms:5d})"
@@ -57,3 +58,14 @@ if t[176] and t[180]:
 if t[240]:
     print("bdec0 epilogue (cycles): enter", 0, "accumulator ready", t[241] - t[240], "reparam/KLD backward done", t[242] - t[240],
           "operand + stash written", t[243] - t[240], "released", t[245] - t[240])
+
+if t[246]:
+    e = OPS.index("heads_c"); e = EPI_OF_OP[e]
+    print("heads epilogue (cycles from its start): mu/logvar in shared memory", t[246] - t[128 + 2 * e], "released", t[128 + 2 * e + 1] - t[128 + 2 * e])
+if t[248]:
+    e = OPS.index("dec3"); e = EPI_OF_OP[e]
+    print("loss epilogue (cycles from its start): recon in shared memory", t[248] - t[128 + 2 * e], "released", t[128 + 2 * e + 1] - t[128 + 2 * e])
+
+if t[249]:
+    print(f"start-up (ns from CTA start): barriers + tensor memory {t[249] - t[176]}, x tile + biases in shared memory {t[250] - t[176]}, "
+          f"operands staged {t[251] - t[176]}, first MMA {t[178] - t[176]}")
