@@ -59,35 +59,42 @@ __device__ __forceinline__ long long global_ns() {
 // =========================================================================================
 constexpr int CH_EPI_WARPS = 8;
 constexpr int CH_EPI_THREADS = CH_EPI_WARPS * 32;
+constexpr int CH_CP = CH_EPI_WARPS / 4;            // warps per tensor-memory lane quarter: they share the columns of a phase
+constexpr int CH_CPT = 32 / CH_CP;                 // columns per thread and 32-column phase
+constexpr int CH_MW = 4 * CH_CPT / 32;             // relu' mask words per thread and layer
 constexpr int CH_PRODUCER_WARP = CH_EPI_WARPS;
 constexpr int CH_MMA_WARP = CH_EPI_WARPS + 1;
 constexpr int CH_SIGNAL_WARP = CH_EPI_WARPS + 2;   // publishes the per-tile progress counter of the fused launch
 constexpr int CH_THREADS = (CH_SIGNAL_WARP + 1) * 32;
 constexpr int CH_M = 128;
 constexpr int CH_MAX_OPS = 28;
-// tensor-memory columns: accumulator, then the A operand regions (128 main + 64 extra each)
-constexpr uint32_t CT_D = 0, CT_AHI = 128, CT_ALO = 320, CT_X = 128, CT_COLS = 512;
-constexpr uint32_t CT_DX = CT_AHI + CT_X;  // small accumulators (heads, d/dz) live in the extra A_hi columns
-// the start point of the tile's rows, [x0, y0, 1, 0 x 5] as TF32 high and low halves: the A operand of cond0.  It is
-// staged at the start of a tile, long before cond0 runs (after the encoder), in extra A_lo columns that nothing else
-// uses during the forward half (z occupies the first Lp16 <= 32 of them)
-constexpr uint32_t CT_START_HI = CT_ALO + CT_X + 32, CT_START_LO = CT_ALO + CT_X + 40;
+// Tensor-memory columns: TWO accumulators and the A operand (TF32 high and low halves, 128 columns each).  Consecutive
+// 128 x 128 layers alternate between the accumulators, so the products of layer l + 1 (into the other accumulator) run
+// while the epilogue warps still read layer l's.  The small operands and accumulators of the odd-shaped steps (heads,
+// z, the start point, d/dz, d/d(mu, logvar)) live in whichever accumulator is idle at that point of the program:
+constexpr uint32_t CT_D0 = 0, CT_D1 = 128, CT_AHI = 256, CT_ALO = 384, CT_COLS = 512;
+constexpr uint32_t CT_HEADS = CT_D0;                                  // forward: (mu, logvar) accumulator, NH <= 64 columns
+constexpr uint32_t CT_START_HI = CT_D0 + 64, CT_START_LO = CT_D0 + 72; // forward: [x0, y0, 1, 0 x 5], the A operand of cond0
+constexpr uint32_t CT_Z_HI = CT_D0 + 64, CT_Z_LO = CT_D0 + 96;         // forward: z (Lp16 <= 32), the A operand of dec0's z rows
+constexpr uint32_t CT_DZ = CT_D0;                                     // backward: d/dz accumulator (32 columns)
+constexpr uint32_t CT_GML_HI = CT_D0, CT_GML_LO = CT_D0 + 64;          // backward: d/d(mu, logvar) (NH <= 64), A operand of the heads' data gradients
 
 struct COp {
   int off_hi, off_lo;  // planes of the layer image in the packed arena (floats): forward or data-gradient image
   int N;               // output width of the layer (forward N; the contraction length of its data gradient)
   int k0, nk;          // forward: K-step range of the image; data gradient: slice range (32 outputs each)
-  int kps;             // forward: K steps per ring stage; data gradient: contraction steps per group (= per stage)
+  int kps;             // forward: K steps per ring stage; data gradient: contraction steps per group
   int S;               // data gradient: slices in the whole image
   int dgrad;           // 0 forward (B read K-major); 1 data gradient (B read MN-major)
+  int gps;             // data gradient: groups per ring stage (a small image travels as ONE stage)
   int a_hi, a_lo;      // tensor-memory columns of the first contraction step of the A operand (TF32 high / low halves)
   int d_col;           // tensor-memory column of the accumulator (dgrad: of the first slice)
   int acc;             // accumulate onto what the accumulator already holds
   int wait_a;          // wait for the epilogue warps before issuing (A operand written, D drained)
   int commit_d;        // signal the epilogue warps when the accumulator is complete
-  int pipe;            // 128 x 128 layer behind a four-phase epilogue: issued as 2 x 4 blocks (output half n, 32-deep
-                       // contraction quarter k), each as soon as the epilogue of the previous layer has released what
-                       // it needs; the first output half is committed before the second is issued (see the MMA warp)
+  int pipe;            // 128 x 128 layer behind a four-phase epilogue, writing the accumulator that epilogue does NOT read:
+                       // its ring stage k (a 32-deep quarter of the contraction) is issued as soon as the epilogue has
+                       // written quarter k of the A operand (a_ready[k]) instead of after the whole epilogue
 };
 
 struct ChainArgs {
@@ -96,7 +103,7 @@ struct ChainArgs {
   long long x_batches;   // resident set: the pass reads batch (*step_dev mod x_batches) - no per-step copy or host work
   const float* eps;   // (B, L) or null (Philox)
   float* stash;       // [n_tiles][tile_stash]
-  float* loss_part;   // [grid][4 warps][4 terms]
+  float* loss_part;   // [grid][epilogue warps][4 terms]
   unsigned long long seed, sample_offset, step;
   const long long* step_dev;   // when set: the step index is *step_dev + 1 (graph-capturable launches)
   long long B;
@@ -106,7 +113,7 @@ struct ChainArgs {
   int n_ops;
   long long* trace;   // development aid: clock64 stamps of CTA 0, one of its tiles (null in production)
   int trace_tile;     // which of CTA 0's tiles (0 = its first)
-  int* ready;         // when set: per-tile counter, +1 per epilogue warp and epilogue, once the stash images of that
+  int* ready;         // when set: per-tile counter, + (epilogue warps) per epilogue, once the stash images of that
                       // epilogue are written (the weight-gradient CTAs of train_tc_fused_kernel wait on it)
 };
 struct ChainKArgs {
@@ -114,94 +121,117 @@ struct ChainKArgs {
   ChainArgs c;
 };
 
-__host__ __device__ inline COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_col, int d_col, int acc,
-                                    int wait_a = 1, int commit_d = 1) {
-  const int a_hi = (int)CT_AHI + a_col, a_lo = (int)CT_ALO + a_col;
-  if (dgrad) return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, a_hi, a_lo, d_col, acc, wait_a, commit_d, 0};
-  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, a_hi, a_lo, d_col, acc, wait_a, commit_d, 0};
+__host__ __device__ inline COp c_op(const TcLayer& c, int k0, int nk, int dgrad, int a_hi, int a_lo, int d_col, int acc,
+                                    int wait_a, int commit_d, int pipe) {
+  if (dgrad) {
+    // groups of a small image (few slices) share one ring stage: one wait instead of one per group
+    const int ngroups = (c.N >> 3) / c.gsz;
+    const int group_bytes = 2 * nk * c.gsz * 1024;
+    const int gps = (!pipe && ngroups * group_bytes <= STAGE_BYTES) ? ngroups : 1;
+    return COp{c.off_thi, c.off_tlo, c.N, k0, nk, c.gsz, c.Kt / 32, 1, gps, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe};
+  }
+  return COp{c.off_hi, c.off_lo, c.N, k0, nk, c.kps, 0, 0, 1, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe};
 }
 
 // The per-tile GEMM program, walked identically by the producer and the MMA warp.  Every op with
-// commit_d is followed by exactly one epilogue of the tile body below (same order).
+// commit_d is followed by exactly one epilogue of the tile body below (same order, c_epi).
 //
-// Forward order: the encoder first (its input x_rel and the start point are staged at the START of a tile, before
-// any accumulator exists to wait for), its share of the heads kept aside, then the condition encoder, whose output
-// h_c stays in the A operand for the three products that read it (its share of the heads, and the h_c rows of the
-// first decoder layer, issued back to back); the reparameterisation runs on the CUDA cores UNDER the decoder
-// product and only adds the z rows afterwards.  No bias travels through the tensor cores: every epilogue adds its own.
-__host__ __device__ inline int chain_program(const Layout& lo, COp* ops, int stages) {
+// Forward order: the encoder first (its input x_rel is staged at the START of a tile, before any accumulator
+// exists to wait for), its share of the heads kept aside, then the condition encoder, whose output h_c stays in the
+// A operand for the three products that read it (its share of the heads, and the h_c rows of the first decoder
+// layer, issued back to back); the reparameterisation runs on the CUDA cores UNDER the decoder product and only adds
+// the z rows afterwards.  Backward: d/dz first, so that the reparameterisation backward runs under the decoder share of
+// d h_c.  No bias travels through the tensor cores: every epilogue adds its own.  "pipe" marks the layers whose
+// products overlap the epilogue before them (they write the other accumulator); cond1 and its data gradient cannot
+// (the idle accumulator holds the heads' small operands at that point) and wait for the whole epilogue.
+__host__ __device__ inline int chain_program(const Layout& lo, COp* ops) {
   const int zs = lo.Lp16 / 8;
-  const int pipe = stages >= 4 ? 1 : 0;   // a pipelined layer holds its four weight stages at once
+  const int A = (int)CT_AHI, Al = (int)CT_ALO, D0 = (int)CT_D0, D1 = (int)CT_D1;
   int n = 0;
-  auto fwd = [&](int t, int k0, int nk, int a_col, int d_col, int acc, int wait_a = 1, int commit_d = 1, int piped = 0) {
-    COp o = c_op(lo.tc[t], k0, nk, 0, a_col, d_col, acc, wait_a, commit_d);
-    o.pipe = piped && pipe;
-    ops[n++] = o;
+  auto fwd = [&](int t, int k0, int nk, int a_hi, int a_lo, int d_col, int acc, int wait_a, int commit_d, int pipe) {
+    ops[n++] = c_op(lo.tc[t], k0, nk, 0, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe);
   };
-  auto bwd = [&](int t, int k0, int nk, int a_col, int d_col, int acc, int wait_a = 1, int commit_d = 1, int piped = 0) {
-    COp o = c_op(lo.tc[t], k0, nk, 1, a_col, d_col, acc, wait_a, commit_d);
-    o.pipe = piped && pipe;
-    ops[n++] = o;
+  auto bwd = [&](int t, int k0, int nk, int a_hi, int a_lo, int d_col, int acc, int wait_a, int commit_d, int pipe) {
+    ops[n++] = c_op(lo.tc[t], k0, nk, 1, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe);
   };
-  fwd(TC_ENC0, 0, lo.Ip / 8, 0, CT_D, 0);           // x_rel -> e1
-  fwd(TC_ENC1, 0, 16, 0, CT_D, 0, 1, 1, 1);
-  fwd(TC_ENC2, 0, 16, 0, CT_D, 0, 1, 1, 1);
-  fwd(TC_ENC3, 0, 16, 0, CT_D, 0, 1, 1, 1);         // -> e4
-  fwd(TC_HEADS, 0, 16, 0, CT_DX, 0, 1, 0);          // h_traj share of the heads (kept aside, no epilogue)
-  fwd(TC_COND0, 0, 1, 0, CT_D, 0, 0, 1);            // start -> hc1 (bias row inside its K = 8)
-  ops[n - 1].a_hi = (int)CT_START_HI;
-  ops[n - 1].a_lo = (int)CT_START_LO;
-  fwd(TC_COND1, 0, 16, 0, CT_D, 0, 1, 1, 1);        // hc1 -> hc
-  fwd(TC_HEADS, 16, 16, 0, CT_DX, 1, 1, 1);         // + hc share -> mu, logvar: the reparameterisation epilogue
-  fwd(TC_DEC0, 0, 16, 0, CT_D, 0, 0, 0);            // hc rows of dec0, running under that epilogue
-  fwd(TC_DEC0, 16, zs, CT_X, CT_D, 1, 1, 1);        // + z rows -> d1
-  fwd(TC_DEC1, 0, 16, 0, CT_D, 0, 1, 1, 1);
-  fwd(TC_DEC2, 0, 16, 0, CT_D, 0, 1, 1, 1);
-  fwd(TC_DEC3, 0, 16, 0, CT_D, 0);                  // -> recon
-  bwd(TC_DEC3, 0, 4, 0, CT_D, 0);                   // d recon -> d d3 (4 slices of 32 columns)
-  bwd(TC_DEC2, 0, 4, 0, CT_D, 0, 1, 1, 1);
-  bwd(TC_DEC1, 0, 4, 0, CT_D, 0, 1, 1, 1);
-  bwd(TC_DEC0, 4, 1, 0, CT_DX, 0, 1, 1);            // d d1 -> d z (one slice) first: its epilogue (the reparameterisation
-                                                    // backward, CUDA cores) runs under the next product
-  bwd(TC_DEC0, 0, 4, 0, CT_D, 0, 0, 0);             //      -> d hc (decoder share), no epilogue of its own
-  bwd(TC_HEADS, 4, 4, CT_X, CT_D, 1);               // d (mu, logvar) -> + encoder share of d hc
-  bwd(TC_COND1, 0, 4, 0, CT_D, 0, 1, 1, 1);         // d hc -> d hc1
-  bwd(TC_HEADS, 0, 4, CT_X, CT_D, 0);               // d (mu, logvar) -> d e4
-  bwd(TC_ENC3, 0, 4, 0, CT_D, 0, 1, 1, 1);
-  bwd(TC_ENC2, 0, 4, 0, CT_D, 0, 1, 1, 1);
-  bwd(TC_ENC1, 0, 4, 0, CT_D, 0, 1, 1, 1);          // -> d e1
+  fwd(TC_ENC0, 0, lo.Ip / 8, A, Al, D0, 0, 1, 1, 0);                       // x_rel -> e1
+  fwd(TC_ENC1, 0, 16, A, Al, D1, 0, 1, 1, 1);
+  fwd(TC_ENC2, 0, 16, A, Al, D0, 0, 1, 1, 1);
+  fwd(TC_ENC3, 0, 16, A, Al, D1, 0, 1, 1, 1);                              // -> e4
+  fwd(TC_HEADS, 0, 16, A, Al, (int)CT_HEADS, 0, 1, 0, 0);                  // h_traj share of the heads (kept aside, no epilogue)
+  fwd(TC_COND0, 0, 1, (int)CT_START_HI, (int)CT_START_LO, D1, 0, 0, 1, 0); // start -> hc1 (bias row inside its K = 8)
+  fwd(TC_COND1, 0, 16, A, Al, D1, 0, 1, 1, 0);                             // hc1 -> hc
+  fwd(TC_HEADS, 16, 16, A, Al, (int)CT_HEADS, 1, 1, 1, 0);                 // + hc share -> mu, logvar: the reparameterisation epilogue
+  fwd(TC_DEC0, 0, 16, A, Al, D1, 0, 0, 0, 0);                              // hc rows of dec0, running under that epilogue
+  fwd(TC_DEC0, 16, zs, (int)CT_Z_HI, (int)CT_Z_LO, D1, 1, 1, 1, 0);        // + z rows -> d1
+  fwd(TC_DEC1, 0, 16, A, Al, D0, 0, 1, 1, 1);
+  fwd(TC_DEC2, 0, 16, A, Al, D1, 0, 1, 1, 1);
+  fwd(TC_DEC3, 0, 16, A, Al, D0, 0, 1, 1, 0);                              // -> recon
+  bwd(TC_DEC3, 0, 4, A, Al, D1, 0, 1, 1, 0);                               // d recon -> d d3 (4 slices of 32 columns)
+  bwd(TC_DEC2, 0, 4, A, Al, D0, 0, 1, 1, 1);
+  bwd(TC_DEC1, 0, 4, A, Al, D1, 0, 1, 1, 1);
+  bwd(TC_DEC0, 4, 1, A, Al, (int)CT_DZ, 0, 1, 1, 0);                       // d d1 -> d z (one slice): the reparameterisation backward
+  bwd(TC_DEC0, 0, 4, A, Al, D1, 0, 0, 0, 0);                               //      -> d hc (decoder share), under that epilogue
+  bwd(TC_HEADS, 4, 4, (int)CT_GML_HI, (int)CT_GML_LO, D1, 1, 1, 1, 0);     // d (mu, logvar) -> + encoder share of d hc
+  bwd(TC_COND1, 0, 4, A, Al, D1, 0, 1, 1, 0);                              // d hc -> d hc1
+  bwd(TC_HEADS, 0, 4, (int)CT_GML_HI, (int)CT_GML_LO, D1, 0, 1, 1, 0);     // d (mu, logvar) -> d e4
+  bwd(TC_ENC3, 0, 4, A, Al, D0, 0, 1, 1, 1);
+  bwd(TC_ENC2, 0, 4, A, Al, D1, 0, 1, 1, 1);
+  bwd(TC_ENC1, 0, 4, A, Al, D0, 0, 1, 1, 1);                               // -> d e1
   return n;
 }
 
-// relu' mask slots (two words per epilogue thread and slot, in shared memory)
+// relu' mask slots (CH_MW words per epilogue thread and slot, in shared memory)
 enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_D3, MK_COUNT };
 // The epilogues of a tile, in the order of the ops that signal them (chain_program).  The tile body is a
-// loop over this table rather than 22 inlined epilogues: the code stays small enough for the instruction
-// cache (the unrolled version spent as many issue slots waiting for instructions as for memory).
+// loop over this table rather than 21 inlined epilogues: the code stays small.
 enum EpiType { EP_HIDDEN = 0, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
 constexpr int CH_EPIS = 21;
 constexpr int CH_EPI_FIRST_DGRAD = 11;
-__constant__ int c_epi[CH_EPIS][5] = {
+__constant__ int c_epi[CH_EPIS][7] = {
     // type, mask slot, stash slot (the image the epilogue completes), write the A operand, layer whose bias the
-    // epilogue adds (-1: none - cond0 carries its bias row inside its K = 8)
-    {EP_HIDDEN, MK_E1, SX_E1, 1, L_ENC0},   {EP_HIDDEN, MK_E2, SX_E2, 1, L_ENC1},   {EP_HIDDEN, MK_E3, SX_E3, 1, L_ENC2},
-    {EP_HIDDEN, MK_E4, SX_E4, 1, L_ENC3},   {EP_HIDDEN, MK_HC1, SX_HC1, 1, -1},     {EP_HIDDEN, MK_HC, SX_HC, 1, L_COND1},
-    {EP_HEADS, 0, SX_Z, 0, -1},             {EP_HIDDEN, MK_D1, SX_D1, 1, L_DEC0},   {EP_HIDDEN, MK_D2, SX_D2, 1, L_DEC1},
-    {EP_HIDDEN, MK_D3, SX_D3, 1, L_DEC2},   {EP_LOSS, 0, SG_REC, 0, -1},
-    {EP_DGRAD, MK_D3, SG_D3, 1, -1},        {EP_DGRAD, MK_D2, SG_D2, 1, -1},        {EP_DGRAD, MK_D1, SG_D1, 1, -1},
-    {EP_BDEC0, 0, SG_ML, 0, -1},            {EP_DGRAD, MK_HC, SG_HC, 1, -1},        {EP_DGRAD, MK_HC1, SG_HC1, 0, -1},
-    {EP_DGRAD, MK_E4, SG_E4, 1, -1},        {EP_DGRAD, MK_E3, SG_E3, 1, -1},        {EP_DGRAD, MK_E2, SG_E2, 1, -1},
-    {EP_DGRAD, MK_E1, SG_E1, 0, -1},
+    // epilogue adds (-1: none - cond0 carries its bias row inside its K = 8), accumulator it reads, 1: it also writes
+    // the start-point columns (the A operand of cond0, which follows the encoder)
+    {EP_HIDDEN, MK_E1, SX_E1, 1, L_ENC0, CT_D0, 0},   {EP_HIDDEN, MK_E2, SX_E2, 1, L_ENC1, CT_D1, 0},
+    {EP_HIDDEN, MK_E3, SX_E3, 1, L_ENC2, CT_D0, 0},   {EP_HIDDEN, MK_E4, SX_E4, 1, L_ENC3, CT_D1, 1},
+    {EP_HIDDEN, MK_HC1, SX_HC1, 1, -1, CT_D1, 0},     {EP_HIDDEN, MK_HC, SX_HC, 1, L_COND1, CT_D1, 0},
+    {EP_HEADS, 0, SX_Z, 0, -1, CT_HEADS, 0},          {EP_HIDDEN, MK_D1, SX_D1, 1, L_DEC0, CT_D1, 0},
+    {EP_HIDDEN, MK_D2, SX_D2, 1, L_DEC1, CT_D0, 0},   {EP_HIDDEN, MK_D3, SX_D3, 1, L_DEC2, CT_D1, 0},
+    {EP_LOSS, 0, SG_REC, 0, -1, CT_D0, 0},
+    {EP_DGRAD, MK_D3, SG_D3, 1, -1, CT_D1, 0},        {EP_DGRAD, MK_D2, SG_D2, 1, -1, CT_D0, 0},
+    {EP_DGRAD, MK_D1, SG_D1, 1, -1, CT_D1, 0},        {EP_BDEC0, 0, SG_ML, 0, -1, CT_DZ, 0},
+    {EP_DGRAD, MK_HC, SG_HC, 1, -1, CT_D1, 0},        {EP_DGRAD, MK_HC1, SG_HC1, 0, -1, CT_D1, 0},
+    {EP_DGRAD, MK_E4, SG_E4, 1, -1, CT_D1, 0},        {EP_DGRAD, MK_E3, SG_E3, 1, -1, CT_D0, 0},
+    {EP_DGRAD, MK_E2, SG_E2, 1, -1, CT_D1, 0},        {EP_DGRAD, MK_E1, SG_E1, 0, -1, CT_D0, 0},
 };
 
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
   return (size_t)stages * STAGE_FLOATS + (size_t)lo.Ip * 128 /* recon scratch */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
-         (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * 2 * CH_EPI_THREADS /* masks */ +
+         (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * CH_MW * CH_EPI_THREADS /* masks */ +
          NUM_LAYERS * 128 /* biases */;
 }
 __host__ __device__ inline size_t chain_smem_bytes(const Layout& lo, int stages) {
   return chain_smem_floats(lo, stages) * 4 + 32 * 8 + 16 + 1024;
 }
+
+template <int N> struct TmemVec;
+template <> struct TmemVec<16> {
+  __device__ static __forceinline__ void ld(uint32_t t, uint32_t (&v)[16]) { tmem_ld16(t, v); }
+  __device__ static __forceinline__ void st(uint32_t t, const uint32_t (&v)[16]) { tmem_st16(t, v); }
+};
+template <> struct TmemVec<8> {
+  __device__ static __forceinline__ void ld(uint32_t t, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(t)
+                 : "memory");
+  }
+  __device__ static __forceinline__ void st(uint32_t t, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+  }
+};
 
 // cta / ncta: index of this CTA among the chain CTAs and their number (the whole grid for chain_kernel)
 __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a, const int cta, const int ncta,
@@ -210,11 +240,11 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   float *ring, *scratch, *xbuf, *mlb, *epb, *bias_s;
   uint32_t* masks;
   const COp* ops = a.ops;   // kernel parameter space: uniform reads by the producer and the MMA warp
-  // d_ready[n]: output half n of the accumulator is complete (MMA -> epilogue); a_ready[k]: quarter k of the A
-  // operand is written and quarter k of the accumulator has been read (epilogue -> MMA); a_free[k]: every MMA that
-  // reads quarter k of the A operand has completed (MMA -> epilogue)
-  // stash_done: every epilogue warp has issued the stash stores of the current epilogue (epilogue -> signal warp)
-  uint64_t *full, *empty, *d_ready, *a_ready, *a_free, *stash_done;
+  // d_ready: the accumulator of the op that commits is complete - and so is every product issued before it, so its A
+  // operand may be overwritten (MMA -> epilogue); a_ready[k]: quarter k of the A operand is written and quarter k
+  // of the accumulator has been read (epilogue -> MMA); stash_done: every epilogue warp has issued the stash stores
+  // of the current epilogue (epilogue -> signal warp)
+  uint64_t *full, *empty, *d_ready, *a_ready, *stash_done;
   uint32_t* tmem_slot;
   {
     const uint32_t base = smem_u32(smem_dyn);
@@ -225,13 +255,12 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     mlb = xbuf + round_up(128 * I, 4);
     epb = mlb + (size_t)NH * 128;
     masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
-    bias_s = reinterpret_cast<float*>(masks + MK_COUNT * 2 * CH_EPI_THREADS);
+    bias_s = reinterpret_cast<float*>(masks + MK_COUNT * CH_MW * CH_EPI_THREADS);
     full = reinterpret_cast<uint64_t*>(bias_s + NUM_LAYERS * 128);
     empty = full + 8;
     d_ready = empty + 8;
-    a_ready = d_ready + 2;
-    a_free = a_ready + 4;
-    stash_done = a_free + 4;
+    a_ready = d_ready + 1;
+    stash_done = a_ready + 4;
     tmem_slot = reinterpret_cast<uint32_t*>(stash_done + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,12 +273,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       mbar_init(&full[st], 1);
       mbar_init(&empty[st], 1);
     }
-    mbar_init(&d_ready[0], 1);
-    mbar_init(&d_ready[1], 1);
-    for (int k = 0; k < 4; ++k) {
-      mbar_init(&a_ready[k], CH_EPI_WARPS);
-      mbar_init(&a_free[k], 1);
-    }
+    mbar_init(d_ready, 1);
+    for (int k = 0; k < 4; ++k) mbar_init(&a_ready[k], CH_EPI_WARPS);
     mbar_init(stash_done, CH_EPI_WARPS);
     mbar_fence_init();
   }
@@ -282,13 +307,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           } else {
             const int ngroups = (op.N >> 3) / op.kps;
             const int fl = op.nk * op.kps * 256;       // nk slices x gsz steps x 1 KB, contiguous inside a group
-            for (int jg = 0; jg < ngroups; ++jg) {
-              const size_t src = (size_t)((jg * op.S + op.k0) * op.kps) * 256;
+            for (int jg = 0; jg < ngroups; jg += op.gps) {
               float* dst = ring + rs.stage * STAGE_FLOATS;
               mbar_wait(&empty[rs.stage], rs.phase ^ 1u);
-              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(2 * fl * 4));
-              tma_load_1d(dst, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
-              tma_load_1d(dst + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              mbar_arrive_expect_tx(&full[rs.stage], (uint32_t)(op.gps * 2 * fl * 4));
+              for (int g = 0; g < op.gps; ++g) {       // group g of the stage: [high plane][low plane]
+                const size_t src = (size_t)(((jg + g) * op.S + op.k0) * op.kps) * 256;
+                tma_load_1d(dst + (size_t)g * 2 * fl, pk + op.off_hi + src, (uint32_t)(fl * 4), &full[rs.stage]);
+                tma_load_1d(dst + (size_t)g * 2 * fl + fl, pk + op.off_lo + src, (uint32_t)(fl * 4), &full[rs.stage]);
+              }
               rs.advance();
             }
           }
@@ -302,111 +329,38 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
         const bool tr = a.trace != nullptr && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
-        if (op.pipe) {
-          // ---- a 128 x 128 layer in 2 x 4 blocks (output half n = 64 columns, contraction quarter k = one ring
-          // stage = 32 columns of the A operand).  Block (n, k) needs quarter k of A (a_ready[k]) and half n of
-          // the accumulator drained by the previous epilogue (a_ready[1] for n = 0, a_ready[3] for n = 1).  Order:
-          // (0,0) (0,1) (0,2) (0,3) -> d_ready[0] -> (1,0) .. (1,3), stage k and a_free[k] released after (1,k)
-          // -> d_ready[1]: the epilogue of the first half runs under the MMAs of the second, and the first blocks
-          // of the next layer under the second half of the epilogue.
-          int slot[4];
-          const uint32_t d = tmem + (uint32_t)op.d_col;
-          for (int nh = 0; nh < 2; ++nh) {
-            for (int k = 0; k < 4; ++k) {
-              if (nh == 0) {
-                if (k == 0) { mbar_wait(&a_ready[0], a_phase); mbar_wait(&a_ready[1], a_phase); }
-                else if (k >= 2) mbar_wait(&a_ready[k], a_phase);
-                slot[k] = rs.stage;
-                mbar_wait(&full[rs.stage], rs.phase);
-                rs.advance();
-                tc_fence_after();
-                if (tr && k == 0) { a.trace[o * 4 + 0] = clock64(); if (o == 0) a.trace[178] = global_ns(); }
-              }
-              const uint32_t b_hi = smem_u32(ring + slot[k] * STAGE_FLOATS);
-              const uint32_t a_hi0 = tmem + (uint32_t)(op.a_hi + 32 * k), a_lo0 = tmem + (uint32_t)(op.a_lo + 32 * k);
-              const uint32_t accf0 = (op.acc || k > 0) ? 1u : 0u;
-              if (!op.dgrad) {
-                // forward: stage = 4 K steps of the K-major planes [k-step][k-chunk][n-group of 8][8 n][4 k]; output
-                // half nh starts 8 n-groups (1 KB) into every k-chunk
-                const uint32_t unit_bytes = 128u * 32u;
-                const uint32_t b_lo = b_hi + 4u * unit_bytes;
-                const uint32_t idesc = umma_idesc_tf32(CH_M, 64);
-                const uint64_t dbits = umma_desc(0u, 128u * 16u, 128u);
-                uint64_t dh = dbits | (uint64_t)((b_hi + (uint32_t)nh * 1024u) >> 4), dl = dbits | (uint64_t)((b_lo + (uint32_t)nh * 1024u) >> 4);
-                if (elect_one()) {
-                  uint32_t a_hi = a_hi0, a_lo = a_lo0, accf = accf0;
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    umma_tf32_ts(d + 64u * nh, a_hi, dh, idesc, accf);
-                    umma_tf32_ts(d + 64u * nh, a_lo, dh, idesc, 1u);
-                    umma_tf32_ts(d + 64u * nh, a_hi, dl, idesc, 1u);
-                    accf = 1u;
-                    a_hi += 8u; a_lo += 8u; dh += (uint64_t)(unit_bytes >> 4); dl += (uint64_t)(unit_bytes >> 4);
-                  }
-                }
-              } else {
-                // data gradient: stage = one contraction group of gsz = 4 steps, planes [slice of 32 outputs][step]
-                // [two 512-byte atoms]; output half nh = slices 2 nh, 2 nh + 1
-                const uint32_t plane = 4u * 4u * 1024u;
-                const uint32_t idesc = umma_idesc_tf32(CH_M, 64, UMMA_B_MN);
-                const uint64_t dbits = umma_desc(0u, 4u * 1024u, 512u, 1u);
-                uint64_t dh = dbits | (uint64_t)((b_hi + (uint32_t)nh * 8192u) >> 4), dl = dbits | (uint64_t)((b_hi + plane + (uint32_t)nh * 8192u) >> 4);
-                if (elect_one()) {
-                  uint32_t a_hi = a_hi0, a_lo = a_lo0, accf = accf0;
-#pragma unroll
-                  for (int st = 0; st < 4; ++st) {
-                    umma_tf32_ts(d + 64u * nh, a_hi, dh, idesc, accf);
-                    umma_tf32_ts(d + 64u * nh, a_lo, dh, idesc, 1u);
-                    umma_tf32_ts(d + 64u * nh, a_hi, dl, idesc, 1u);
-                    accf = 1u;
-                    a_hi += 8u; a_lo += 8u; dh += 64u; dl += 64u;  // + 1024 bytes
-                  }
-                }
-              }
-              __syncwarp();
-              if (nh == 1) {
-                if (elect_one()) {
-                  umma_commit(&empty[slot[k]]);
-                  umma_commit(&a_free[k]);
-                }
-                __syncwarp();
-              }
-            }
-            if (elect_one()) umma_commit(&d_ready[nh]);
-            __syncwarp();
-          }
-          a_phase ^= 1u;
-          if (tr) a.trace[o * 4 + 1] = clock64();
-          continue;
-        }
-        if (op.wait_a) {
+        if (op.wait_a && !op.pipe) {
           for (int k = 0; k < 4; ++k) mbar_wait(&a_ready[k], a_phase);
-          a_phase ^= 1u;
         }
         tc_fence_after();
-        if (tr) a.trace[o * 4 + 0] = clock64();
-        if (tr && o == 0) a.trace[178] = global_ns();
+        const uint32_t d = tmem + (uint32_t)op.d_col;
         if (!op.dgrad) {
           const uint32_t unit_bytes = (uint32_t)op.N * 32u;  // one K step of a plane
-          for (int k = 0; k < op.nk; k += op.kps) {
+          // D[128 x N] (+)= A[:, 8 (k + ks) ..] x W^T, B K-major: LBO = chunk stride N*16, SBO = 128
+          const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
+          const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
+          const uint64_t dinc = (uint64_t)(unit_bytes >> 4);
+          int sidx = 0;
+          for (int k = 0; k < op.nk; k += op.kps, ++sidx) {
             const int nks = min(op.kps, op.nk - k);
+            if (op.pipe) {   // a pipelined layer has four stages: stage k reads quarter k of the A operand
+              mbar_wait(&a_ready[sidx], a_phase);
+              tc_fence_after();
+            }
             mbar_wait(&full[rs.stage], rs.phase);
             tc_fence_after();
+            if (tr && k == 0) { a.trace[o * 4 + 0] = clock64(); if (o == 0) a.trace[178] = global_ns(); }
             const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
             const uint32_t b_lo = b_hi + (uint32_t)nks * unit_bytes;
-            // D[128 x N] (+)= A[:, 8 (k + ks) ..] x W^T, B K-major: LBO = chunk stride N*16, SBO = 128
-            const uint32_t idesc = umma_idesc_tf32(CH_M, op.N);
-            const uint64_t dbits = umma_desc(0u, (uint32_t)op.N * 16u, 128u);
             uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)(b_lo >> 4);
-            const uint64_t dinc = (uint64_t)(unit_bytes >> 4);
             uint32_t a_hi = tmem + (uint32_t)(op.a_hi + 8 * k), a_lo = tmem + (uint32_t)(op.a_lo + 8 * k);
             uint32_t accf = (op.acc || k > 0) ? 1u : 0u;
             if (elect_one()) {
 #pragma unroll 4
               for (int ks = 0; ks < nks; ++ks) {
-                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_hi, dh, idesc, accf);
-                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_lo, dh, idesc, 1u);
-                umma_tf32_ts(tmem + (uint32_t)op.d_col, a_hi, dl, idesc, 1u);
+                umma_tf32_ts(d, a_hi, dh, idesc, accf);
+                umma_tf32_ts(d, a_lo, dh, idesc, 1u);
+                umma_tf32_ts(d, a_hi, dl, idesc, 1u);
                 accf = 1u;
                 a_hi += 8u; a_lo += 8u; dh += dinc; dl += dinc;
               }
@@ -423,45 +377,46 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           const uint32_t plane = (uint32_t)(op.nk * op.kps) * 1024u;
           const uint32_t idesc = umma_idesc_tf32(CH_M, 32 * op.nk, UMMA_B_MN);
           const uint64_t dbits = umma_desc(0u, (uint32_t)op.kps * 1024u, 512u, 1u);
-          const uint32_t d = tmem + (uint32_t)op.d_col;
-          uint32_t a_hi = tmem + (uint32_t)op.a_hi, a_lo = tmem + (uint32_t)op.a_lo;
           uint32_t accf = op.acc ? 1u : 0u;
-          for (int jg = 0; jg < ngroups; ++jg) {
+          for (int jg = 0; jg < ngroups; jg += op.gps) {
+            if (op.pipe) {   // four groups: group k reads quarter k of the A operand (gps == 1)
+              mbar_wait(&a_ready[jg], a_phase);
+              tc_fence_after();
+            }
             mbar_wait(&full[rs.stage], rs.phase);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(ring + rs.stage * STAGE_FLOATS);
-            uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)((b_hi + plane) >> 4);
+            if (tr && jg == 0) a.trace[o * 4 + 0] = clock64();
+            const uint32_t s0 = smem_u32(ring + rs.stage * STAGE_FLOATS);
             if (elect_one()) {
-              for (int st = 0; st < op.kps; ++st) {
-                umma_tf32_ts(d, a_hi, dh, idesc, accf);
-                umma_tf32_ts(d, a_lo, dh, idesc, 1u);
-                umma_tf32_ts(d, a_hi, dl, idesc, 1u);
-                accf = 1u;
-                a_hi += 8u; a_lo += 8u; dh += 64u; dl += 64u;  // + 1024 bytes
+              for (int g = 0; g < op.gps; ++g) {
+                const uint32_t b_hi = s0 + (uint32_t)g * 2u * plane;
+                uint64_t dh = dbits | (uint64_t)(b_hi >> 4), dl = dbits | (uint64_t)((b_hi + plane) >> 4);
+                uint32_t a_hi = tmem + (uint32_t)(op.a_hi + 8 * (jg + g) * op.kps);
+                uint32_t a_lo = tmem + (uint32_t)(op.a_lo + 8 * (jg + g) * op.kps);
+                for (int st = 0; st < op.kps; ++st) {
+                  umma_tf32_ts(d, a_hi, dh, idesc, accf);
+                  umma_tf32_ts(d, a_lo, dh, idesc, 1u);
+                  umma_tf32_ts(d, a_hi, dl, idesc, 1u);
+                  accf = 1u;
+                  a_hi += 8u; a_lo += 8u; dh += 64u; dl += 64u;  // + 1024 bytes
+                }
               }
               umma_commit(&empty[rs.stage]);
             }
             __syncwarp();
-            a_hi = tmem + (uint32_t)(op.a_hi + 8 * (jg + 1) * op.kps);
-            a_lo = tmem + (uint32_t)(op.a_lo + 8 * (jg + 1) * op.kps);
-            accf = 1u;
             rs.advance();
           }
         }
-        if (op.commit_d) {   // everything issued so far is complete: both halves of the accumulator, all of the A operand
-          if (elect_one()) {
-            umma_commit(&d_ready[0]);
-            umma_commit(&d_ready[1]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_commit(&a_free[k]);
-          }
+        if (op.wait_a) a_phase ^= 1u;   // this op consumed the a_ready phase of the epilogue before it
+        if (op.commit_d) {              // fires when everything issued so far is complete
+          if (elect_one()) umma_commit(d_ready);
           __syncwarp();
         }
         if (tr) a.trace[o * 4 + 1] = clock64();
       }
   } else if (warp == CH_SIGNAL_WARP) {
     // ===================== signal warp (fused launch only) ======================================
-    // Publishes the chain's progress to the weight-gradient CTAs: once all eight epilogue warps have issued the
+    // Publishes the chain's progress to the weight-gradient CTAs: once all epilogue warps have issued the
     // stash stores of an epilogue (their arrival on stash_done releases those stores to this thread), one thread
     // makes them visible device-wide - also to the bulk copies (async proxy) of the other CTAs - and bumps the
     // tile's counter.  The device-scope fence is cumulative over the stores it has observed through the barrier;
@@ -479,31 +434,27 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     }
   } else {
     // ===================== epilogue warps =======================================================
-    const int q = warp & 3, h = warp >> 2;   // tensor-memory lane quarter, column half
+    const int q = warp & 3, cp = warp >> 2;  // tensor-memory lane quarter, column part of a phase
     const int m = q * 32 + lane;             // row of the tile owned by this thread
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t d_phase = 0;
-    uint32_t* my_mask = masks + tid;   // [(slot * 2 + word) * 256 + tid]
+    uint32_t* my_mask = masks + tid;   // [(slot * CH_MW + word) * CH_EPI_THREADS + tid]
     float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float* my_ml = mlb + m;          // [n * 128 + m], h == 0 threads
+    float* my_ml = mlb + m;          // [n * 128 + m]
     float* my_ep = epb + m;
 
     int epi_no = 0;
     bool tr_tile = false;
-    // ---- hand-shakes with the MMA warp.  Every op that commits completes d_ready[0..1] and a_free[0..3] once, and
-    // every epilogue completes a_ready[0..3] once: one parity bit per direction.
-    auto wait_half = [&](int n) {          // output half n (64 columns) of the accumulator is complete
-      mbar_wait(&d_ready[n], d_phase);
+    // ---- hand-shakes with the MMA warp.  Every op that commits completes d_ready once, and every epilogue completes
+    // a_ready[0..3] once: one parity bit per direction.
+    auto wait_d = [&]() {                  // the accumulator is complete; every earlier product too (A may be overwritten)
+      mbar_wait(d_ready, d_phase);
       tc_fence_after();
-      if (n == 0 && tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
-    };
-    auto wait_free = [&](int k) {          // quarter k of the A operand is no longer read by any MMA
-      mbar_wait(&a_free[k], d_phase);
-      tc_fence_after();
+      if (tr_tile && tid == 0) a.trace[128 + epi_no * 2] = clock64();
     };
     // the warp's stash stores of this epilogue are issued: tell the signal warp.  Always BEFORE the warp's last
     // arrival on a_ready of the same epilogue, so that no warp can be an epilogue ahead of a warp that has not
-    // reported yet (the next epilogue starts only after all eight a_ready arrivals).
+    // reported yet (the next epilogue starts only after all a_ready arrivals).
     auto report_stash = [&]() {
       if (a.ready != nullptr) {
         __syncwarp();
@@ -516,12 +467,6 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_ready[k]);
-    };
-    auto wait_d = [&]() {                  // epilogues without phases: the whole accumulator, A free to overwrite
-      wait_half(0);
-      wait_half(1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) wait_free(k);
     };
     auto finish_epilogue = [&]() {
       d_phase ^= 1u;
@@ -546,10 +491,20 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
       return reinterpret_cast<float4*>(tile_stash + lo.slot_off[slot] + mn_image_index(4 * chunk, m, 128, lo.slot_w[slot] * 4));
     };
-    // start point of the tile's row -> the A columns of cond0, [x0, y0, 1, 0...], and the 16-wide stash image
+    // start point of the tile's row: the 16-wide stash image ([x0, y0, 1, 0...]; the same columns become the A operand
+    // of cond0 in the epilogue that precedes it, stage_start_cols)
     auto stage_start = [&](long long tile) {
-      if (h == 0) {
+      if (cp == 0) {
         const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];   // zeros past the batch end
+        float* ts = a.stash + (size_t)tile * lo.tile_stash;
+        *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
+#pragma unroll
+        for (int c = 1; c < 8; ++c) *stash_ptr(ts, SX_START, c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto stage_start_cols = [&]() {
+      if (cp == 0) {
+        const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];
         uint32_t xh, xl, yh, yl;
         split_tf32(sx, xh, xl);
         split_tf32(sy, yh, yl);
@@ -557,68 +512,60 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         tmem_st4(lane_base + CT_START_HI + 4, 0u, 0u, 0u, 0u);
         tmem_st4(lane_base + CT_START_LO, xl, yl, 0u, 0u);
         tmem_st4(lane_base + CT_START_LO + 4, 0u, 0u, 0u, 0u);
-        float* ts = a.stash + (size_t)tile * lo.tile_stash;
-        *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
-#pragma unroll
-        for (int c = 1; c < 8; ++c) *stash_ptr(ts, SX_START, c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     // encoder input of the tile's row: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
-    // -> the A operand of enc0 and the stash image.  Like the start point it is staged before the tile's first MMA.
+    // -> the A operand of enc0 and the stash image.  Staged before the tile's first MMA; the warps of a lane quarter
+    // share the 4-column chunks of a row.
     auto stage_xrel = [&](long long tile) {
-      if (h * 64 < Ip) {
-        float* ts = a.stash + (size_t)tile * lo.tile_stash;
-        const float* xr = xbuf + m * I;
-        const float sx = xr[1], sy = xr[2];
-        const int nc = min(Ip - h * 64, 64) >> 2;
-        for (int c4 = 0; c4 < nc; ++c4) {
-          float xv[4];
+      float* ts = a.stash + (size_t)tile * lo.tile_stash;
+      const float* xr = xbuf + m * I;
+      const float sx = xr[1], sy = xr[2];
+#pragma unroll 2
+      for (int c4 = cp; c4 < Ip / 4; c4 += CH_CP) {
+        float xv[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = h * 64 + c4 * 4 + i;
-            float val = 0.f;
-            if (n < I) {
-              val = xr[n];
-              const int d = n % 3;
-              if (d == 1) val = val - sx;
-              else if (d == 2) val = val - sy;
-            }
-            xv[i] = val;
+        for (int i = 0; i < 4; ++i) {
+          const int n = c4 * 4 + i;
+          float val = 0.f;
+          if (n < I) {
+            val = xr[n];
+            const int d = n % 3;
+            if (d == 1) val = val - sx;
+            else if (d == 2) val = val - sy;
           }
-          uint32_t hi[4], lw[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
-          tmem_st4(lane_base + CT_AHI + h * 64 + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
-          tmem_st4(lane_base + CT_ALO + h * 64 + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
-          *stash_ptr(ts, SX_X, h * 16 + c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+          xv[i] = val;
         }
+        uint32_t hi[4], lw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
+        tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+        tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+        *stash_ptr(ts, SX_X, c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
       }
     };
-
     // reparameterisation noise of the tile's row (injected, or Philox keyed by the global row index): nothing depends
     // on it before the heads epilogue, so it is drawn while the first encoder product runs
     auto stage_eps = [&](long long tile) {
-      if (h == 0) {
-        const long long row = tile * CH_M + m;
-        const bool row_ok = row < a.B;
+      const long long row = tile * CH_M + m;
+      const bool row_ok = row < a.B;
 #pragma unroll 1
-        for (int jb = 0; jb < Lp16 / 4; ++jb) {
-          float e4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (row_ok && jb * 4 < L) {
-            if (a.eps != nullptr) {
+      for (int jb = cp; jb < Lp16 / 4; jb += CH_CP) {
+        float e4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok && jb * 4 < L) {
+          if (a.eps != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
-            } else {
-              const unsigned long long step = a.step_dev != nullptr ? (unsigned long long)(*a.step_dev + 1) : a.step;
-              const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
-                                              (uint32_t)(step + 1));
-              e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
-            }
+            for (int i = 0; i < 4; ++i)
+              if (jb * 4 + i < L) e4[i] = __ldg(a.eps + row * L + jb * 4 + i);
+          } else {
+            const unsigned long long step = a.step_dev != nullptr ? (unsigned long long)(*a.step_dev + 1) : a.step;
+            const float4 r = philox_normal4(a.seed, a.sample_offset + (unsigned long long)row, (uint32_t)jb,
+                                            (uint32_t)(step + 1));
+            e4[0] = r.x; e4[1] = r.y; e4[2] = r.z; e4[3] = r.w;
           }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) my_ep[(jb * 4 + i) * 128] = jb * 4 + i < L ? e4[i] : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) my_ep[(jb * 4 + i) * 128] = jb * 4 + i < L ? e4[i] : 0.f;
       }
     };
 
@@ -654,34 +601,34 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       epi_no = 0;
       stage_eps(tile);   // under the first encoder product
 
-      // this thread's 64 features of a 128-wide stash image: base of its row, then per 4-feature chunk
-      // (mn_image_index with the row part hoisted; f = h*64 + c*16 + j4*4)
+      // this thread's features of a 128-wide stash image: base of its row, then per 8-feature unit
+      // (mn_image_index with the row part hoisted; f = c*32 + cp*CH_CPT + up*8)
       const int row_part = (m >> 2) * 512 + (m & 3) * 32;
       const int swz = m & 3;
-      // A 128-wide epilogue walks the accumulator in four phases of 32 columns (quarter c); the two warps of a lane
-      // quarter take 16 columns each: this thread's columns of phase c are c*32 + h*16 .. + 15.
-      auto unit_off = [&](int c, int up) -> int {   // 8 features c*32 + h*16 + up*8 ..: one swizzled 32-byte unit
-        return c * 128 + ((((h << 1) + up) ^ swz) << 3);
+      // A 128-wide epilogue walks the accumulator in four phases of 32 columns (quarter c); the warps of a lane
+      // quarter take CH_CPT columns each: this thread's columns of phase c are c*32 + cp*CH_CPT .. + CH_CPT - 1.
+      auto unit_off = [&](int c, int up) -> int {   // 8 features c*32 + cp*CH_CPT + up*8 ..: one swizzled 32-byte unit
+        return c * 128 + ((((cp * (CH_CPT / 8)) + up) ^ swz) << 3);
       };
-      // hidden layer: (+ bias) relu -> mask, stash image, A operand.  Phases 0, 1 need the first output half of
-      // the accumulator, phases 2, 3 the second; each phase hands its quarter of A (and of D) to the MMA warp.
-      // Mask word w holds the columns of phases 2 w, 2 w + 1, first column in the top bit.
-      auto epi_hidden = [&](int ms, int xslot, int bias_l) {
+      // hidden layer: + bias, relu -> mask, stash image, A operand.  Each phase hands its quarter of A (and of D) to
+      // the MMA warp.  A mask word holds 32 consecutive columns of the thread, first column in the top bit.
+      auto epi_hidden = [&](int ms, int xslot, int bias_l, uint32_t dcol, int with_start) {
         float* xs = ts + lo.slot_off[xslot] + row_part;
-        const float* bias = bias_l >= 0 ? bias_s + bias_l * 128 + h * 16 : nullptr;
-        // one phase: 16 accumulator values -> (+ bias) relu -> mask bits, stash image, quarter c of the A operand
-        auto phase = [&](const uint32_t (&v)[16], int c, uint32_t& mword) {
-          float bv[16];
+        const float* bias = bias_l >= 0 ? bias_s + bias_l * 128 + cp * CH_CPT : nullptr;
+        const uint32_t dbase = lane_base + dcol + cp * CH_CPT;
+        // one phase: CH_CPT accumulator values -> (+ bias) relu -> mask bits, stash image, quarter c of the A operand
+        auto phase = [&](const uint32_t (&v)[CH_CPT], int c, uint32_t& mword) {
+          float bv[CH_CPT];
           if (bias != nullptr) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
+            for (int j4 = 0; j4 < CH_CPT / 4; ++j4) {
               const float4 b4 = *(reinterpret_cast<const float4*>(bias + c * 32) + j4);
               bv[4 * j4] = b4.x; bv[4 * j4 + 1] = b4.y; bv[4 * j4 + 2] = b4.z; bv[4 * j4 + 3] = b4.w;
             }
           }
-          uint32_t hi[16], lw[16];
+          uint32_t hi[CH_CPT], lw[CH_CPT];
 #pragma unroll
-          for (int up = 0; up < 2; ++up) {
+          for (int up = 0; up < CH_CPT / 8; ++up) {
             float xv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -696,37 +643,37 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             }
             st_global_v8(xs + unit_off(c, up), xv);
           }
-          wait_free(c);
-          tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);
-          tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
-          arrive_q(c);   // (handing the quarter over one phase later, to hide the store latency, was measured slower)
+          TmemVec<CH_CPT>::st(lane_base + CT_AHI + c * 32 + cp * CH_CPT, hi);
+          TmemVec<CH_CPT>::st(lane_base + CT_ALO + c * 32 + cp * CH_CPT, lw);
+          arrive_q(c);
         };
-        // rolled over the two halves of the accumulator (half the code of the four-phase unrolled form: this body is
-        // fetched cold at least once per tile, see the once-per-tile epilogues)
+        wait_d();
+        if (with_start) stage_start_cols();
+        uint32_t mword = 0u;
+        // rolled over the two halves of the accumulator (half the code of the four-phase unrolled form)
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          uint32_t v0[16], v1[16];
-          uint32_t mword = 0u;
-          wait_half(half);
-          tmem_ld16(lane_base + CT_D + half * 64 + h * 16, v0);
+          uint32_t v0[CH_CPT], v1[CH_CPT];
+          TmemVec<CH_CPT>::ld(dbase + half * 64, v0);
           tmem_ld_wait();
-          tmem_ld16(lane_base + CT_D + half * 64 + 32 + h * 16, v1);
+          TmemVec<CH_CPT>::ld(dbase + half * 64 + 32, v1);
           phase(v0, 2 * half, mword);
           tmem_ld_wait();
           phase(v1, 2 * half + 1, mword);
-          my_mask[(ms * 2 + half) * CH_EPI_THREADS] = mword;
+          if (CH_MW == 2 || half == 1) my_mask[(ms * CH_MW + (CH_MW == 2 ? half : 0)) * CH_EPI_THREADS] = mword;
         }
         finish_epilogue();
       };
       // data gradient: D -> relu' mask of the layer input -> stash image (-> A operand); same four phases.
       // defer: the caller arrives for all four quarters itself (the last epilogue stages the next tile first)
-      auto epi_dgrad = [&](int ms, int gslot, bool write_a, bool defer) {
+      auto epi_dgrad = [&](int ms, int gslot, bool write_a, bool defer, uint32_t dcol) {
         float* gs = ts + lo.slot_off[gslot] + row_part;
-        auto phase = [&](const uint32_t (&v)[16], int c, uint32_t& mword) {
-          uint32_t hi[16], lw[16];
-          float gv[16];
+        const uint32_t dbase = lane_base + dcol + cp * CH_CPT;
+        auto phase = [&](const uint32_t (&v)[CH_CPT], int c, uint32_t& mword) {
+          uint32_t hi[CH_CPT], lw[CH_CPT];
+          float gv[CH_CPT];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < CH_CPT; ++j) {
             // all-ones / all-zeros from the top mask bit, then AND: no branch, no select on a predicate
             const uint32_t keep = (uint32_t)((int32_t)mword >> 31);
             mword <<= 1;
@@ -734,26 +681,26 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             split_tf32(gv[j], hi[j], lw[j]);
           }
 #pragma unroll
-          for (int up = 0; up < 2; ++up) {
+          for (int up = 0; up < CH_CPT / 8; ++up) {
             const float g8[8] = {gv[up * 8], gv[up * 8 + 1], gv[up * 8 + 2], gv[up * 8 + 3],
                                  gv[up * 8 + 4], gv[up * 8 + 5], gv[up * 8 + 6], gv[up * 8 + 7]};
             st_global_v8(gs + unit_off(c, up), g8);
           }
           if (write_a) {
-            wait_free(c);
-            tmem_st16(lane_base + CT_AHI + c * 32 + h * 16, hi);
-            tmem_st16(lane_base + CT_ALO + c * 32 + h * 16, lw);
+            TmemVec<CH_CPT>::st(lane_base + CT_AHI + c * 32 + cp * CH_CPT, hi);
+            TmemVec<CH_CPT>::st(lane_base + CT_ALO + c * 32 + cp * CH_CPT, lw);
           }
           if (!defer) arrive_q(c);
         };
+        wait_d();
+        uint32_t mword = 0u;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-          uint32_t v0[16], v1[16];
-          uint32_t mword = my_mask[(ms * 2 + half) * CH_EPI_THREADS];
-          wait_half(half);
-          tmem_ld16(lane_base + CT_D + half * 64 + h * 16, v0);
+          uint32_t v0[CH_CPT], v1[CH_CPT];
+          if (CH_MW == 2 || half == 0) mword = my_mask[(ms * CH_MW + (CH_MW == 2 ? half : 0)) * CH_EPI_THREADS];
+          TmemVec<CH_CPT>::ld(dbase + half * 64, v0);
           tmem_ld_wait();
-          tmem_ld16(lane_base + CT_D + half * 64 + 32 + h * 16, v1);
+          TmemVec<CH_CPT>::ld(dbase + half * 64 + 32, v1);
           phase(v0, 2 * half, mword);
           tmem_ld_wait();
           phase(v1, 2 * half + 1, mword);
@@ -761,60 +708,61 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       };
       auto epi_heads = [&]() {
       // heads: mu, logvar (Training_VAE.py:193-196); z = mu + eps * exp(0.5 logvar) (:199-206); z becomes the A
-      // operand (extra columns) of the z rows of dec0.  The h_c rows of dec0 are already running on the tensor
-      // cores (h_c is still the main A operand: this epilogue must not touch it).  The KLD term of the loss
-      // (:243) is summed here, where mu and logvar are at hand.
+      // operand of the z rows of dec0.  The h_c rows of dec0 are already running on the tensor cores (h_c is still
+      // the main A operand: this epilogue must not touch it).  The KLD term of the loss (:243) is summed here,
+      // where mu and logvar are at hand.  The warps of a lane quarter share the 4-latent blocks of a row.
       wait_d();
-      if (h == 0) {
+      if (cp == 0) {
         const float* bias = bias_s + L_HEADS * 128;
         for (int c = 0; c < NH / 16; ++c) {
           uint32_t v[16];
-          tmem_ld16(lane_base + CT_DX + c * 16, v);
+          tmem_ld16(lane_base + CT_HEADS + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) my_ml[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bias[c * 16 + j];
         }
-        if (tr_tile && tid == 0) a.trace[246] = clock64();
-        float s_k = 0.f;
-#pragma unroll 1
-        for (int jb = 0; jb < lo.slot_w[SX_Z] / 4; ++jb) {   // past Lp16 / 4: the zero padding of the stash image
-          float zv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = jb * 4 + i;
-            float z = 0.f;
-            if (j < L) {
-              const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128];
-              const float e_half = expf(0.5f * lv);          // exp(lv) = exp(lv / 2)^2: one exponential per element
-              z = fmaf(my_ep[j * 128], e_half, mu);
-              s_k += 1.f + lv - mu * mu - e_half * e_half;
-            }
-            zv[i] = z;
-          }
-          if (jb < Lp16 / 4) {
-            uint32_t hi[4], lw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split_tf32(zv[i], hi[i], lw[i]);
-            tmem_st4(lane_base + CT_AHI + CT_X + jb * 4, hi[0], hi[1], hi[2], hi[3]);
-            tmem_st4(lane_base + CT_ALO + CT_X + jb * 4, lw[0], lw[1], lw[2], lw[3]);
-          }
-          *stash_ptr(ts, SX_Z, jb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-        }
-        if (row_ok) loss_acc[1] += -0.5f * s_k * (a.inv_batch / (float)L);
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");   // mu, logvar of the row are in shared memory
+      if (tr_tile && tid == 0) a.trace[246] = clock64();
+      float s_k = 0.f;
+#pragma unroll 1
+      for (int jb = cp; jb < lo.slot_w[SX_Z] / 4; jb += CH_CP) {   // past Lp16 / 4: the zero padding of the stash image
+        float zv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = jb * 4 + i;
+          float z = 0.f;
+          if (j < L) {
+            const float mu = my_ml[j * 128], lv = my_ml[(L + j) * 128];
+            const float e_half = expf(0.5f * lv);          // exp(lv) = exp(lv / 2)^2: one exponential per element
+            z = fmaf(my_ep[j * 128], e_half, mu);
+            s_k += 1.f + lv - mu * mu - e_half * e_half;
+          }
+          zv[i] = z;
+        }
+        if (jb < Lp16 / 4) {
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(zv[i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_Z_HI + jb * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_Z_LO + jb * 4, lw[0], lw[1], lw[2], lw[3]);
+        }
+        *stash_ptr(ts, SX_Z, jb) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+      }
+      if (row_ok) loss_acc[1] += -0.5f * s_k * (a.inv_batch / (float)L);
       release_a();
       };
-      auto epi_loss = [&]() {
+      auto epi_loss = [&](uint32_t dcol) {
       // ---------------------------------- loss (Training_VAE.py:229-268) -----------------------
-      // recon -> the five terms and d(total)/d(recon), which becomes the A operand of dec3's
+      // recon -> the recon / start / time terms and d(total)/d(recon), which becomes the A operand of dec3's
       // data gradient; one thread per row walks the time steps in order
       wait_d();
-      if (h == 0) {
+      if (cp == 0) {
         float* rb = scratch + m;   // [n * 128 + m]
         const float* bias = bias_s + L_DEC3 * 128;
         for (int c = 0; c < Ip / 16; ++c) {
           uint32_t v[16];
-          tmem_ld16(lane_base + CT_D + c * 16, v);
+          tmem_ld16(lane_base + dcol + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) rb[(c * 16 + j) * 128] = __uint_as_float(v[j]) + bias[c * 16 + j];
@@ -887,22 +835,20 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       release_a();
       };
       auto epi_bdec0 = [&]() {
-      // dec0: d/dz is in the small accumulator; reparameterisation + KLD backward (Training_VAE.py:243):
+      // dec0: d/dz is in its small accumulator; reparameterisation + KLD backward (Training_VAE.py:243):
       //   d/dmu = w_k mu / (B L) + g_z ;  d/dlogvar = -0.5 w_k (1 - e^lv) / (B L) + 0.5 g_z eps e^(lv/2)
-      // -> the (mu, logvar) gradient becomes the A operand (extra columns) of the heads' data gradients.
-      // The decoder share of d/dhc stays in the main accumulator and is completed by the next op.
+      // -> the (mu, logvar) gradient becomes the A operand of the heads' data gradients (it replaces d/dz in the idle
+      // accumulator).  The decoder share of d/dhc is being computed into the other accumulator meanwhile.
       if (tr_tile && tid == 0) a.trace[240] = clock64();
       wait_d();
       if (tr_tile && tid == 0) a.trace[241] = clock64();
-      if (h == 0) {
+      if (cp == 0) {
         const float c_k = a.w_kld * a.inv_batch / (float)L;
-        // Rolled loops with small bodies on purpose: this code runs once per tile, long after its last use, so its
-        // instructions come from L2 every time - the fully unrolled version (600 instructions) spent ~8 000 cycles
-        // here, most of them waiting for instruction fetch.
+        // every thread first reads ALL of its row's d/dz (the gradient columns written below overlap them)
 #pragma unroll 1
         for (int jb = 0; jb < (L + 3) / 4; ++jb) {
           uint32_t v[4];
-          tmem_ld4(lane_base + CT_DX + jb * 4, v);
+          tmem_ld4(lane_base + CT_DZ + jb * 4, v);
           tmem_ld_wait();
           float gm[4], gl[4];
 #pragma unroll
@@ -937,8 +883,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             uint32_t hi[4], lw[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_tf32(gv[i], hi[i], lw[i]);
-            tmem_st4(lane_base + CT_AHI + CT_X + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
-            tmem_st4(lane_base + CT_ALO + CT_X + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+            tmem_st4(lane_base + CT_GML_HI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+            tmem_st4(lane_base + CT_GML_LO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
           }
           *stash_ptr(ts, SG_ML, c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
         }
@@ -952,11 +898,12 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll 1
       for (int e = 0; e < CH_EPIS; ++e) {
         const int ty = c_epi[e][0];
+        const uint32_t dcol = (uint32_t)c_epi[e][5];
         if (ty == EP_HIDDEN) {
-          epi_hidden(c_epi[e][1], c_epi[e][2], c_epi[e][4]);
+          epi_hidden(c_epi[e][1], c_epi[e][2], c_epi[e][4], dcol, c_epi[e][6]);
         } else if (ty == EP_DGRAD) {
           const bool last = e == CH_EPIS - 1;
-          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0, last);
+          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0, last, dcol);
           // after the first data gradient every warp is past the loss (that MMA could not finish before all of
           // them had released its A operand): the x tile can be replaced by the next tile's; after the last one
           // the next tile's start point and encoder input are staged, and only then is the A operand handed over
@@ -974,25 +921,22 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         } else if (ty == EP_HEADS) {
           epi_heads();
         } else if (ty == EP_LOSS) {
-          epi_loss();
+          epi_loss(dcol);
         } else {
           epi_bdec0();
         }
       }
     }
 
-
     if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[179] = global_ns();
-    // loss partials: fixed-order tree inside the warp, one slot per (CTA, row quarter)
-    if (h == 0) {
+    // loss partials: fixed-order tree inside the warp, one slot per (CTA, epilogue warp)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) loss_acc[t4] += __shfl_xor_sync(0xffffffffu, loss_acc[t4], o);
-      if (lane == 0) {
-        float* dst = a.loss_part + ((size_t)cta * 4 + q) * 4;
-        dst[0] = loss_acc[0]; dst[1] = loss_acc[1]; dst[2] = loss_acc[2]; dst[3] = loss_acc[3];
-      }
+      for (int t4 = 0; t4 < 4; ++t4) loss_acc[t4] += __shfl_xor_sync(0xffffffffu, loss_acc[t4], o);
+    if (lane == 0) {
+      float* dst = a.loss_part + ((size_t)cta * CH_EPI_WARPS + warp) * 4;
+      dst[0] = loss_acc[0]; dst[1] = loss_acc[1]; dst[2] = loss_acc[2]; dst[3] = loss_acc[3];
     }
   }
 
@@ -1662,9 +1606,9 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     }
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {
-    // the five loss terms: lanes stride the (CTA, row quarter) partials, fixed-order shuffle tree
+    // the five loss terms: lanes stride the (CTA, epilogue warp) partials, fixed-order shuffle tree
     float t[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = threadIdx.x; c < r.chain_grid * 4; c += 32) {
+    for (int c = threadIdx.x; c < r.chain_grid * CH_EPI_WARPS; c += 32) {
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) t[qd] += __ldcg(loss_part + (size_t)c * 4 + qd);
     }
@@ -1744,7 +1688,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   p.slab_stride = round_up(lo.n_params, 4);
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
   p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
-  p.loss_floats = (size_t)p.chain_grid * 16;
+  p.loss_floats = (size_t)p.chain_grid * CH_EPI_WARPS * 4;
   p.flag_floats = (p.overlap ? (size_t)round_up((int)p.n_tiles, 4) : 0) + 4;   // + the finished-block counter of the reduction
   return p;
 }
@@ -1761,7 +1705,7 @@ static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const Tra
   a.trace_tile = g_chain_trace_tile;
   a.ready = nullptr;
   for (int o = 0; o < CH_MAX_OPS; ++o) a.ops[o] = COp{};
-  a.n_ops = chain_program(lo, a.ops, plan.chain_stages);
+  a.n_ops = chain_program(lo, a.ops);
   return a;
 }
 static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs) {
