@@ -206,7 +206,7 @@ __constant__ int c_epi[CH_EPIS][7] = {
 };
 
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
-  return (size_t)stages * STAGE_FLOATS + (size_t)lo.Ip * 128 /* recon scratch */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
+  return (size_t)stages * STAGE_FLOATS + (size_t)(lo.Ip == 32 ? 0 : lo.Ip * 128) /* recon scratch of the wide-row loss */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
          (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * CH_MW * CH_EPI_THREADS /* masks */ +
          NUM_LAYERS * 128 /* biases */;
 }
@@ -244,14 +244,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   // operand may be overwritten (MMA -> epilogue); a_ready[k]: quarter k of the A operand is written and quarter k
   // of the accumulator has been read (epilogue -> MMA); stash_done: every epilogue warp has issued the stash stores
   // of the current epilogue (epilogue -> signal warp)
-  uint64_t *full, *empty, *d_ready, *a_ready, *stash_done;
+  // x_full: the tile's trajectories (and, for the first tile, the biases) have landed in shared memory (TMA -> epilogue)
+  uint64_t *full, *empty, *d_ready, *a_ready, *stash_done, *x_full;
   uint32_t* tmem_slot;
   {
     const uint32_t base = smem_u32(smem_dyn);
     unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
     ring = reinterpret_cast<float*>(p);
     scratch = ring + (size_t)a.stages * STAGE_FLOATS;
-    xbuf = scratch + (size_t)Ip * 128;
+    xbuf = scratch + (size_t)(Ip == 32 ? 0 : Ip * 128);
     mlb = xbuf + round_up(128 * I, 4);
     epb = mlb + (size_t)NH * 128;
     masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
@@ -261,7 +262,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     d_ready = empty + 8;
     a_ready = d_ready + 1;
     stash_done = a_ready + 4;
-    tmem_slot = reinterpret_cast<uint32_t*>(stash_done + 1);
+    x_full = stash_done + 1;
+    tmem_slot = reinterpret_cast<uint32_t*>(x_full + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
@@ -276,6 +278,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     mbar_init(d_ready, 1);
     for (int k = 0; k < 4; ++k) mbar_init(&a_ready[k], CH_EPI_WARPS);
     mbar_init(stash_done, CH_EPI_WARPS);
+    mbar_init(x_full, 1);
     mbar_fence_init();
   }
   if (warp == CH_PRODUCER_WARP) tmem_alloc(tmem_slot, CT_COLS);
@@ -572,21 +575,49 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     // the batch of this pass: the caller's, or the one the device-side step counter selects in a resident set
     const float* __restrict__ x_batch =
         a.x + (a.x_batches > 0 ? (size_t)((unsigned long long)(*a.step_dev) % (unsigned long long)a.x_batches) * (size_t)a.B * I : 0);
-    // the tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end
-    auto load_x = [&](long long tile) {
+    // The tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end.
+    // A full tile travels as ONE bulk copy issued by one thread (completion on x_full); a ragged or misaligned one is
+    // loaded by all threads, which then arrive on the same barrier, so that the wait below is the same either way.
+    uint32_t x_phase = 0;
+    auto load_x = [&](long long tile, bool with_biases) {
       const long long base = tile * CH_M * I;
       const long long left = a.B * I - base;
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
-      for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(x_batch + base + i) : 0.f;
+      const float* src = x_batch + base;
+      const bool bulk = nval == CH_M * I && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+      if (bulk) {
+        if (tid == 0) {
+          uint32_t bytes = (uint32_t)(CH_M * I * 4);
+          if (with_biases)
+            for (int l = 0; l < NUM_LAYERS; ++l) bytes += (uint32_t)(lo.Np[l] * 4);
+          fence_proxy_async_smem();   // earlier generic-proxy reads of the x tile are ordered before the copy overwrites it
+          mbar_arrive_expect_tx(x_full, bytes);
+          tma_load_1d(xbuf, src, (uint32_t)(CH_M * I * 4), x_full);
+          if (with_biases)
+            for (int l = 0; l < NUM_LAYERS; ++l) tma_load_1d(bias_s + l * 128, pk + lo.q_b[l], (uint32_t)(lo.Np[l] * 4), x_full);
+        }
+      } else {
+        for (int i = tid; i < CH_M * I; i += CH_EPI_THREADS) xbuf[i] = i < nval ? __ldg(x_batch + base + i) : 0.f;
+        if (with_biases)
+          for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS) {
+            const int l = i >> 7, n = i & 127;
+            if (n < lo.Np[l]) bias_s[i] = __ldg(pk + lo.q_b[l] + n);
+          }
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+        if (tid == 0) mbar_arrive(x_full);
+      }
+    };
+    auto wait_x = [&]() {
+      mbar_wait(x_full, x_phase);
+      x_phase ^= 1u;
     };
     if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[249] = global_ns();
-    load_x(cta);
-    // the (padded) biases of all layers: read by every epilogue, kept in shared memory for the whole launch
-    for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS) {
-      const int l = i >> 7, n = i & 127;
-      bias_s[i] = n < lo.Np[l] ? __ldg(pk + lo.q_b[l] + n) : 0.f;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+    // the (padded) biases of all layers are read by every epilogue and stay in shared memory for the whole launch:
+    // the padding is zeroed here, the values arrive with the first x tile
+    for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS)
+      if ((i & 127) >= lo.Np[i >> 7]) bias_s[i] = 0.f;
+    load_x(cta, true);
+    wait_x();
     if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[250] = global_ns();
     stage_start(cta);
     stage_xrel(cta);
@@ -755,9 +786,86 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       auto epi_loss = [&](uint32_t dcol) {
       // ---------------------------------- loss (Training_VAE.py:229-268) -----------------------
       // recon -> the recon / start / time terms and d(total)/d(recon), which becomes the A operand of dec3's
-      // data gradient; one thread per row walks the time steps in order
+      // data gradient; one thread per row walks the time steps in order.  Rows of up to 32 features (seq_len <= 10)
+      // stay in registers (compile-time feature indices); wider ones go through a scratch tile in shared memory.
       wait_d();
-      if (cp == 0) {
+      auto row_loss = [&](auto ip_tag) {
+        constexpr int IP = decltype(ip_tag)::value;
+        float r[IP];   // recon, overwritten in place by d(total)/d(recon) three features behind the walk
+        {
+          const float* bias = bias_s + L_DEC3 * 128;
+#pragma unroll
+          for (int c = 0; c < IP / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld16(lane_base + dcol + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = *(reinterpret_cast<const float4*>(bias + c * 16) + j4);
+              r[c * 16 + 4 * j4] = __uint_as_float(v[4 * j4]) + b4.x;
+              r[c * 16 + 4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) + b4.y;
+              r[c * 16 + 4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) + b4.z;
+              r[c * 16 + 4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) + b4.w;
+            }
+          }
+        }
+        if (tr_tile && tid == 0) a.trace[248] = clock64();
+        const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
+        const float c_start = a.w_start * a.inv_batch;
+        const float c_t0 = a.w_time * 2.f * a.inv_batch;
+        const float c_mono = T > 1 ? a.w_time * a.inv_batch / (float)(T - 1) : 0.f;
+        const float* xr = xbuf + m * I;
+        const float sx = xr[1], sy = xr[2];
+        float s_rec = 0.f, s_start = 0.f, s_t0 = 0.f, s_mono = 0.f;
+        // the gradient of feature n is final once feature n + 3 (the next time step of the same column) has been
+        // visited - the monotone-time term of step t + 1 adds to the time gradient of step t - and recon[n] is read
+        // for the last time there: three gradients wait in `pend` and replace recon three features behind
+        float pend[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int n = 0; n < IP; ++n) {
+          const int d = n % 3;                        // compile-time: 0 time, 1 x, 2 y
+          const bool on = n < I && row_ok;            // rows past the batch end carry no loss and no gradient
+          const float xv = n < I ? xr[n] : 0.f;
+          const float target = d == 0 ? xv : (d == 1 ? xv - sx : xv - sy);
+          const float diff = r[n] - target;
+          float gn = c_rec * diff;
+          if (on) s_rec = fmaf(diff, diff, s_rec);
+          if (n == 0) {
+            s_t0 = r[0] * r[0];
+            gn = fmaf(c_t0, r[0], gn);
+          } else if (d == 0) {
+            const float dt = r[n] - r[n - 3];
+            if (on && dt < 0.f) {   // relu'(0) = 0: strict
+              s_mono -= dt;
+              gn -= c_mono;
+              pend[0] += c_mono;
+            }
+          } else if (n < 3) {
+            if (on) s_start = fmaf(diff, diff, s_start);
+            gn = fmaf(c_start, diff, gn);
+          }
+          if (n >= 3) r[n - 3] = pend[d];
+          pend[d] = on ? gn : 0.f;
+        }
+#pragma unroll
+        for (int n = IP - 3; n < IP; ++n) r[n] = pend[n % 3];
+        if (row_ok) {
+          loss_acc[0] += s_rec * (a.inv_batch / (float)I);
+          loss_acc[2] += s_start * (a.inv_batch * 0.5f);
+          loss_acc[3] += s_t0 * a.inv_batch + (T > 1 ? s_mono * (a.inv_batch / (float)(T - 1)) : 0.f);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < IP / 4; ++c4) {
+          uint32_t hi[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_tf32(r[c4 * 4 + i], hi[i], lw[i]);
+          tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+          *stash_ptr(ts, SG_REC, c4) = make_float4(r[c4 * 4], r[c4 * 4 + 1], r[c4 * 4 + 2], r[c4 * 4 + 3]);
+        }
+      };
+      if (cp == 0 && Ip == 32) row_loss(std::integral_constant<int, 32>{});
+      if (cp == 0 && Ip != 32) {   // wider rows: through a scratch tile in shared memory
         float* rb = scratch + m;   // [n * 128 + m]
         const float* bias = bias_s + L_DEC3 * 128;
         for (int c = 0; c < Ip / 16; ++c) {
@@ -909,9 +1017,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
           // the next tile's start point and encoder input are staged, and only then is the A operand handed over
           if (next < n_tiles) {
             if (e == CH_EPI_FIRST_DGRAD) {
-              load_x(next);
+              asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");   // every warp is done with this tile's x
+              load_x(next, false);
             } else if (last) {
-              asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");   // the x tile is complete
+              wait_x();
               stage_start(next);
               stage_xrel(next);
             }
@@ -1651,7 +1760,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   TrainTcPlan p;
   p.n_tiles = (B + CH_M - 1) / CH_M;
   p.chain_grid = (int)(p.n_tiles < sm_count ? p.n_tiles : sm_count);
-  p.chain_stages = 4;
+  p.chain_stages = 5;   // one more than a 128 x 128 layer holds: the first stage of the next op is always in flight
   while (p.chain_stages > 2 && chain_smem_bytes(lo, p.chain_stages) > 232448) --p.chain_stages;
   p.chain_smem = chain_smem_bytes(lo, p.chain_stages);
   // Small batch: every tile gets a chain CTA and one weight-gradient CTA per role, all on their own SM in ONE launch
