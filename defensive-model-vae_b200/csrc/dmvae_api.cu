@@ -198,10 +198,10 @@ struct Workspace {
   float* slabs;
   float* stash;
 };
-// workspace = [grid slabs][stash units], both 16-byte aligned
+// workspace = [header][grid slabs][stash units], all 16-byte aligned (the header belongs to the tensor-core kernels)
 Workspace carve(void* ws, const dmvae::TrainPlan& p) {
   Workspace w;
-  w.slabs = static_cast<float*>(ws);
+  w.slabs = static_cast<float*>(ws) + dmvae::WS_HEADER_FLOATS;
   w.stash = w.slabs + (size_t)p.grid * p.slab_stride;
   return w;
 }
@@ -228,11 +228,11 @@ int64_t dmvae_train_workspace_bytes(const DmvaeCfg* cfg, int64_t B) {
   if (dmvae::train_tc_supported(lo)) {  // covers both implementations (dmvae_set_train_impl)
     for (int overlap = 0; overlap < 2; ++overlap) {   // either launch scheme (dmvae_set_train_impl 0 / 2)
       const dmvae::TrainTcPlan t = dmvae::plan_train_tc(lo, B > 0 ? B : 1, sms, overlap);
-      const size_t tc = t.stash_floats + t.slab_floats + t.loss_floats + t.flag_floats;
+      const size_t tc = t.stash_floats + t.slab_floats + t.loss_floats;
       if (tc > floats) floats = tc;
     }
   }
-  return (int64_t)(floats * sizeof(float));
+  return (int64_t)((floats + dmvae::WS_HEADER_FLOATS) * sizeof(float));
 }
 
 int64_t dmvae_stash_bytes(const DmvaeCfg* cfg, int64_t B) {
@@ -276,12 +276,11 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   if ((want_tc || step_dev != nullptr || dp != nullptr) && dmvae::train_tc_supported(lo)) {
     // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)
     const dmvae::TrainTcPlan tp = dmvae::plan_train_tc(lo, B, sms);
-    float* stash = static_cast<float*>(workspace);
+    // the header (zero at allocation) holds the per-tile counters and the finished-block counter: both reset themselves
+    int* flags = static_cast<int*>(workspace);
+    float* stash = static_cast<float*>(workspace) + dmvae::WS_HEADER_FLOATS;
     float* slabs = stash + tp.stash_floats;
     float* loss_part = slabs + tp.slab_floats;
-    int* flags = reinterpret_cast<int*>(loss_part + tp.loss_floats);
-    e = cudaMemsetAsync(flags, 0, tp.flag_floats * sizeof(int), st);
-    if (e != cudaSuccess) return cuda_fail(e, what);
     if (tp.overlap) {
       e = PROF(dmvae::K_TRAIN_TC_FUSED, st, dmvae::launch_chain_wgrad_fused(lo, tp, io, stash, slabs, loss_part, flags, st));
       if (e != cudaSuccess) return cuda_fail(e, what);
@@ -292,10 +291,10 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
       if (e != cudaSuccess) return cuda_fail(e, what);
     }
     // with the update, the reduction kernel also refreshes `packed` and advances the device-side step counter
-    unsigned int* done = reinterpret_cast<unsigned int*>(flags + tp.flag_floats - 4);
+    unsigned int* done = reinterpret_cast<unsigned int*>(flags + dmvae::WS_DONE_SLOT);
     e = PROF(dmvae::K_REDUCE_TC, st,
              dmvae::launch_reduce_tc(lo, tp, slabs, loss_part, wv, grads, adam, params, m, v, step_dev, packed_rw, step_dev, done,
-                                     dp, st));
+                                     dp, flags, st));
     if (e != cudaSuccess) return cuda_fail(e, what);
     return DMVAE_OK;
   } else {
@@ -479,7 +478,7 @@ int dmvae_backward(const DmvaeCfg* cfg, const float* packed, const float* g_reco
   const dmvae::TrainPlan plan = dmvae::plan_train(lo, B, sms, true);
   dmvae::TrainIO io;
   io.packed = packed; io.stash = const_cast<float*>(static_cast<const float*>(stash));
-  io.slabs = static_cast<float*>(workspace);
+  io.slabs = static_cast<float*>(workspace) + dmvae::WS_HEADER_FLOATS;
   io.g_recon = g_recon; io.g_mu = g_mu; io.g_logvar = g_logvar; io.g_hc = g_hc; io.B = B;
   io.inv_batch = 0.f;  // the KLD / loss seeds arrive through the upstream gradients
   cudaError_t e = PROF(dmvae::K_TRAIN_BWD, st, dmvae::launch_train(lo, plan, 2, io, st));

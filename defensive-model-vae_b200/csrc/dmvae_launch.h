@@ -55,6 +55,13 @@ struct TrainIO {
 // mode: 0 fused forward+loss+backward, 1 forward only, 2 backward only
 cudaError_t launch_train(const Layout& lo, const TrainPlan& plan, int mode, const TrainIO& io, cudaStream_t stream);
 
+// The first WS_HEADER_FLOATS floats of every training workspace are the library's persistent state: the per-tile
+// progress counters of train_tc_fused_kernel (reset by the reduction kernel that follows it) and the finished-block
+// counter of that reduction (self-resetting).  Zero at allocation (the caller's one duty), never touched by any other
+// kernel family, at the same place whatever the batch size or kernel selection - so that no step needs a memset.
+constexpr size_t WS_HEADER_FLOATS = 128;
+constexpr int WS_DONE_SLOT = 124;   // finished-block counter; the tile counters start at 0 (at most SMs / 4 <= 120 tiles)
+
 // Tensor-core training pass (dmvae_train_tc.cu): chain kernel -> weight-gradient kernel -> reduction.
 struct TrainTcPlan {
   long long n_tiles;          // 128-row tiles
@@ -65,10 +72,8 @@ struct TrainTcPlan {
   int unit_tiles[3], unit_count[3], unit_begin[3];  // tiles per unit, units (= partial slabs) per role, first slab
   int n_slabs;
   int slab_stride;
-  size_t stash_floats, slab_floats, loss_floats;   // workspace = [stash][slabs][loss partials][tile flags]
+  size_t stash_floats, slab_floats, loss_floats;   // workspace = [header][stash][slabs][loss partials]
   bool overlap;               // small batch: chain and weight-gradient CTAs side by side in one launch
-  size_t flag_floats;         // ints, zeroed before every pass: per-tile epilogue counters of that launch, then 4 for the
-                              // finished-block counter of the reduction
 };
 bool train_tc_supported(const Layout& lo);
 void set_chain_trace(long long* device_buffer, int tile = 0);  // development aid (256 int64), null = off; which of CTA 0's tiles
@@ -82,7 +87,7 @@ void set_train_tc_overlap(bool on);  // false: always the two-launch sequence (m
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
-                             const DmvaeDpPeers* dp, cudaStream_t stream);
+                             const DmvaeDpPeers* dp, int* tile_flags, cudaStream_t stream);
 inline int dp_exchange_stride(const Layout& lo) { return round_up(lo.n_params + 5, 4); }
 // inbox of a rank: [source | sum][step parity][stride] 8-byte words {step : value}, then 16 bytes whose first word is
 // the rank's status (0, or 0x80000000 | step once a thread timed out waiting for a peer)

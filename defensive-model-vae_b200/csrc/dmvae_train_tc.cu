@@ -1570,6 +1570,8 @@ struct ReduceTcArgs {
   float* packed;
   long long* step_inc;
   unsigned int* done;
+  int* tile_flags;            // per-tile progress counters of the fused launch before this kernel: reset here for the next pass
+  int n_tile_flags;
   // data parallel (dp.world > 1): the gradient exchange over peer memory runs inside this kernel, between the
   // slab sum and the update (dp_all_sum)
   DmvaeDpPeers dp;
@@ -1659,6 +1661,7 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
                                  float* __restrict__ grads, float* __restrict__ p, float* __restrict__ m,
                                  float* __restrict__ v) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < r.n_tile_flags) r.tile_flags[e] = 0;   // every CTA of the fused launch has exited: its counters start over
   __shared__ AdamScalarsTc hs;
   __shared__ unsigned int epoch_s;
   const bool tr = r.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -1684,7 +1687,8 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
     const int role = r.tensor_role[t];
     const float* src = slabs + (size_t)r.role_begin[role] * r.slab_stride + e;
     const int n = r.role_count[role];
-#pragma unroll 8
+    // fixed order; 16 loads in flight per thread (the sum stays one sequential chain of adds)
+#pragma unroll 16
     for (int c = 0; c < n; ++c) s += __ldcg(src + (size_t)c * r.slab_stride);
     if (tr) r.trace[231] = global_ns();
     if (dp_on) s = dp_all_sum(r.dp, r.dp_stride, e, s, epoch_s, r.dp_ctl);
@@ -1798,7 +1802,7 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
   p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
   p.loss_floats = (size_t)p.chain_grid * CH_EPI_WARPS * 4;
-  p.flag_floats = (p.overlap ? (size_t)round_up((int)p.n_tiles, 4) : 0) + 4;   // + the finished-block counter of the reduction
+  if (p.overlap && p.n_tiles > WS_DONE_SLOT) p.overlap = false;   // the tile counters live in the workspace header
   return p;
 }
 
@@ -1879,8 +1883,10 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
 cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const float* slabs, const float* loss_part,
                              const float w[4], float* grads, const DmvaeAdam* adam, float* p, float* m, float* v,
                              const long long* step_dev, float* packed, long long* step_inc, unsigned int* done,
-                             const DmvaeDpPeers* dp, cudaStream_t stream) {
+                             const DmvaeDpPeers* dp, int* tile_flags, cudaStream_t stream) {
   ReduceTcArgs r;
+  r.tile_flags = tile_flags;
+  r.n_tile_flags = (tile_flags != nullptr && plan.overlap) ? (int)plan.n_tiles : 0;
   if (dp != nullptr) r.dp = *dp;
   else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
   r.dp_stride = dp_exchange_stride(lo);

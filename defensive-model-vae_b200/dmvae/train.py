@@ -69,7 +69,7 @@ class FusedTrainer:
         if ws is None:
             with torch.cuda.device(self.device):
                 nbytes = check(self.lib.dmvae_train_workspace_bytes(self._cfg_ref, B), "dmvae_train_workspace_bytes")
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)   # zero once: self-resetting counters in its header
             self._ws = {B: ws}       # keep only the latest size
         return ws
 

@@ -145,7 +145,9 @@ int dmvae_decode_from_condition(const DmvaeCfg* cfg, const float* packed, const 
  *                   (key `seed`, counter = sample_offset + row, stream = step + 1)
  *   inv_batch       1 / (global batch size): the loss is a mean over the
  *                   GLOBAL batch, so data-parallel ranks pass the global size
- *   workspace       dmvae_train_workspace_bytes(cfg, B) bytes, 16-byte aligned
+ *   workspace       dmvae_train_workspace_bytes(cfg, B) bytes, 16-byte aligned, ZERO-FILLED once when it is allocated:
+ *                   its first 512 bytes are counters that the kernels reset themselves (no step issues a memset);
+ *                   the caller never writes to it afterwards and uses one workspace per stream
  *   grads           out: dmvae_grad_count(cfg) = param_count + 5 floats: the
  *                   gradient of the total loss in state_dict order, then
  *                   [total, recon, kld, start, time] (this rank's share of the
