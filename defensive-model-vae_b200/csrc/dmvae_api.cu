@@ -250,7 +250,8 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
                         uint64_t sample_offset, uint64_t step, const DmvaeLossWeights* w, float inv_batch, int64_t B,
                         void* workspace, float* grads, const DmvaeAdam* adam, float* params, float* m, float* v,
                         float* packed_rw, void* stream, const char* what, long long* step_dev = nullptr,
-                        const DmvaeDpPeers* dp = nullptr, int64_t x_batches = 0) {
+                        const DmvaeDpPeers* dp = nullptr, int64_t x_batches = 0, int x_shuffle = 0,
+                        uint64_t x_shuffle_seed = 0) {
   dmvae::Layout lo;
   int rc = layout_or_fail(cfg, &lo);
   if (rc != DMVAE_OK) return rc;
@@ -264,6 +265,7 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   dmvae::TrainIO io;
   io.packed = packed; io.x = x; io.eps = eps; io.x_batches = x_batches;
+  io.x_shuffle = x_shuffle; io.x_shuffle_seed = x_shuffle_seed;
   io.seed = seed; io.sample_offset = sample_offset; io.step = step; io.step_dev = step_dev; io.B = B;
   io.w_recon = w->recon; io.w_kld = w->kld; io.w_start = w->start; io.w_time = w->time; io.inv_batch = inv_batch;
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
@@ -372,19 +374,28 @@ int dmvae_train_step_dp(const DmvaeCfg* cfg, float* params, float* packed, float
                       reinterpret_cast<long long*>(step_dev), peers);
 }
 
+int64_t dmvae_resident_row(uint64_t shuffle_seed, int64_t epoch, int64_t pos, int64_t n_rows) {
+  if (n_rows < 1 || n_rows > 0xffffffffll || pos < 0 || pos >= n_rows || epoch < 0)
+    return fail(DMVAE_ERR_ARG, "resident_row: need 0 <= pos < n_rows <= 2^32 - 1 and epoch >= 0");
+  return (int64_t)dmvae::resident_row(shuffle_seed, (uint64_t)epoch, (uint32_t)pos, (uint32_t)n_rows);
+}
+
 int dmvae_train_step_resident(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v, const float* x_set,
-                              int64_t n_batches, uint64_t seed, uint64_t sample_offset, const DmvaeLossWeights* w,
+                              int64_t n_batches, int shuffle, uint64_t shuffle_seed, uint64_t seed, uint64_t sample_offset,
+                              const DmvaeLossWeights* w,
                               float inv_batch, int64_t B, const DmvaeAdam* adam, int64_t* step_dev, void* workspace,
                               float* grads, const DmvaeDpPeers* peers, void* stream) {
   if (!adam || !step_dev || !packed) return fail(DMVAE_ERR_ARG, "train_step_resident: adam, step_dev or packed is null");
   if (n_batches < 1) return fail(DMVAE_ERR_ARG, "train_step_resident: the resident set holds at least one batch");
+  if (shuffle && (n_batches > 0xffffffffll / (B > 0 ? B : 1)))
+    return fail(DMVAE_ERR_ARG, "train_step_resident: a shuffled set holds at most 2^32 - 1 rows");
   if (peers) {
     const int prc = check_peers(peers, "train_step_resident");
     if (prc != DMVAE_OK) return prc;
   }
   return train_common(cfg, packed, x_set, nullptr, seed, sample_offset, 0, w, inv_batch, B, workspace, grads, adam, params, m, v,
                       packed, stream, "train_step_resident", reinterpret_cast<long long*>(step_dev),
-                      (peers && peers->world > 1) ? peers : nullptr, n_batches);
+                      (peers && peers->world > 1) ? peers : nullptr, n_batches, shuffle ? 1 : 0, shuffle_seed);
 }
 
 int dmvae_train_fwd_bwd(const DmvaeCfg* cfg, const float* packed, const float* x, const float* eps, uint64_t seed,
@@ -575,6 +586,15 @@ int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream)
   if (rc != DMVAE_OK) return rc;
   const cudaError_t e = dmvae::launch_ffma_probe(iters, sink, sms, flop_out, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "ffma_probe");
+}
+
+int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream) {
+  if (!sink || iters < 1 || (mode != 0 && mode != 1)) return fail(DMVAE_ERR_ARG, "tf32_probe: null sink, iters < 1 or mode not 0 / 1");
+  int sms = 0;
+  const int rc = require_device(&sms);
+  if (rc != DMVAE_OK) return rc;
+  const cudaError_t e = dmvae::launch_tf32_probe(iters, mode, sink, sms, flop_out, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "tf32_probe");
 }
 
 }  // extern "C"

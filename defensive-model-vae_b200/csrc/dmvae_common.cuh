@@ -421,4 +421,42 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample,
   return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
 }
 
+
+// --------------------------------------------------------------------------------------
+// Shuffled walk over a resident data set (the reference's DataLoader(shuffle=True), Training_VAE.py:327)
+// --------------------------------------------------------------------------------------
+// pi_{seed, epoch}: a bijection of [0, n) evaluated per element, so that a kernel can pick the rows of its batch
+// without any permutation array: a keyed mixing function that is a bijection of k-bit words (k = bits of n - 1:
+// xor-shift, multiplication by an odd constant and key addition are each one), cycle-walked until the value falls
+// inside [0, n) (fewer than two evaluations on average).  Position p of epoch e reads row resident_row(seed, e, p, n);
+// every row is read exactly once per epoch and the order changes with the epoch.  Host and device evaluate the same code.
+__host__ __device__ inline uint32_t resident_mix(uint32_t x, uint32_t mask, int k, uint32_t k0, uint32_t k1) {
+  const int s1 = (k + 1) / 2, s2 = (k + 2) / 3 > 0 ? (k + 2) / 3 : 1;
+  x = (x + k0) & mask;
+  x ^= x >> s1;
+  x = (x * 0x9E3779B1u) & mask;
+  x ^= x >> s2;
+  x = (x + k1) & mask;
+  x = (x * 0x85EBCA6Bu) & mask;
+  x ^= x >> s1;
+  x = (x * 0xC2B2AE35u) & mask;
+  x ^= x >> s2;
+  return x;
+}
+__host__ __device__ inline uint32_t resident_row(uint64_t seed, uint64_t epoch, uint32_t pos, uint32_t n) {
+  if (n <= 1u) return 0u;
+  int k = 1;
+  while (k < 32 && (1u << k) < n) ++k;
+  const uint32_t mask = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+  // two key words from (seed, epoch): one splitmix64 step each
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (epoch + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const uint32_t k0 = (uint32_t)z, k1 = (uint32_t)(z >> 32);
+  uint32_t x = pos;
+  do { x = resident_mix(x, mask, k, k0, k1); } while (x >= n);
+  return x;
+}
+
 }  // namespace dmvae

@@ -41,6 +41,8 @@ struct TrainIO {
   const float* packed = nullptr;
   const float* x = nullptr;
   long long x_batches = 0;   // tensor-core path with step_dev: x is a resident set of this many batches (0: one batch)
+  int x_shuffle = 0;         // resident set: rows are picked through the per-epoch permutation resident_row (else in storage order)
+  unsigned long long x_shuffle_seed = 0;
   const float* start = nullptr;
   const float* eps = nullptr;
   float* stash = nullptr;

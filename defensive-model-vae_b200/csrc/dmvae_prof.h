@@ -29,5 +29,7 @@ void profile_enable(int on);
 cudaError_t profile_collect(double* ms, long long* launches, int n);
 long long launch_count(int kernel);
 cudaError_t launch_ffma_probe(long long iters, float* sink, int sm_count, double* flop, cudaStream_t stream);
+// dense tcgen05.mma kind::tf32 issue rate (dmvae_probe_tc.cu); mode 0: operands in shared memory, N = 256; 1: A in tensor memory, N = 128
+cudaError_t launch_tf32_probe(long long iters, int mode, float* sink, int sm_count, double* flop, cudaStream_t stream);
 
 }  // namespace dmvae

@@ -101,6 +101,8 @@ struct ChainArgs {
   const float* packed;
   const float* x;     // (B, T, 3) absolute; with x_batches > 0: a resident set of x_batches such batches, back to back
   long long x_batches;   // resident set: the pass reads batch (*step_dev mod x_batches) - no per-step copy or host work
+  int x_shuffle;         // resident set: position p of epoch e = *step_dev / x_batches reads row resident_row(seed, e, p, rows)
+  unsigned long long x_shuffle_seed;
   const float* eps;   // (B, L) or null (Philox)
   float* stash;       // [n_tiles][tile_stash]
   float* loss_part;   // [grid][epilogue warps][4 terms]
@@ -573,8 +575,11 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     };
 
     // the batch of this pass: the caller's, or the one the device-side step counter selects in a resident set
-    const float* __restrict__ x_batch =
-        a.x + (a.x_batches > 0 ? (size_t)((unsigned long long)(*a.step_dev) % (unsigned long long)a.x_batches) * (size_t)a.B * I : 0);
+    const unsigned long long x_step = a.x_batches > 0 ? (unsigned long long)(*a.step_dev) : 0ull;
+    const unsigned long long x_b = a.x_batches > 0 ? x_step % (unsigned long long)a.x_batches : 0ull;
+    const unsigned long long x_epoch = a.x_batches > 0 ? x_step / (unsigned long long)a.x_batches : 0ull;
+    const bool shuffled = a.x_batches > 0 && a.x_shuffle != 0;
+    const float* __restrict__ x_batch = a.x + (shuffled ? 0 : (size_t)x_b * (size_t)a.B * I);
     // The tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end.
     // A full tile travels as ONE bulk copy issued by one thread (completion on x_full); a ragged or misaligned one is
     // loaded by all threads, which then arrive on the same barrier, so that the wait below is the same either way.
@@ -584,8 +589,36 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       const long long left = a.B * I - base;
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
       const float* src = x_batch + base;
-      const bool bulk = nval == CH_M * I && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-      if (bulk) {
+      const bool bulk = !shuffled && nval == CH_M * I && (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+      if (shuffled) {
+        // the rows of this tile are scattered over the resident set: position p = batch * B + row of the epoch's
+        // permutation (the reference's DataLoader(shuffle=True) draws a new row order per epoch, Training_VAE.py:327).
+        // Two threads per row; all loads of a thread are issued before its first store.
+        const int r = tid >> 1, half = tid & 1;
+        const long long row = tile * CH_M + r;
+        const int n0 = half * ((I + 1) / 2), n1 = half ? I : (I + 1) / 2;
+        float v[32];
+        if (row < a.B) {
+          const uint32_t src_row = resident_row(a.x_shuffle_seed, x_epoch, (uint32_t)(x_b * (unsigned long long)a.B + (unsigned long long)row),
+                                                (uint32_t)(a.x_batches * a.B));
+          const float* sp = a.x + (size_t)src_row * I;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = n0 + j < n1 ? __ldg(sp + n0 + j) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < n1) xbuf[r * I + n0 + j] = v[j];
+        if (with_biases)
+          for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS) {
+            const int l = i >> 7, n = i & 127;
+            if (n < lo.Np[l]) bias_s[i] = __ldg(pk + lo.q_b[l] + n);
+          }
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+        if (tid == 0) mbar_arrive(x_full);
+      } else if (bulk) {
         if (tid == 0) {
           uint32_t bytes = (uint32_t)(CH_M * I * 4);
           if (with_biases)
@@ -1810,6 +1843,8 @@ static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const Tra
   ChainArgs a;
   a.packed = io.packed; a.x = io.x; a.eps = io.eps; a.stash = stash; a.loss_part = loss_part;
   a.x_batches = io.step_dev != nullptr ? io.x_batches : 0;
+  a.x_shuffle = io.x_shuffle;
+  a.x_shuffle_seed = io.x_shuffle_seed;
   a.seed = io.seed; a.sample_offset = io.sample_offset; a.step = io.step; a.B = io.B;
   a.w_recon = io.w_recon; a.w_kld = io.w_kld; a.w_start = io.w_start; a.w_time = io.w_time; a.inv_batch = io.inv_batch;
   a.stages = plan.chain_stages;

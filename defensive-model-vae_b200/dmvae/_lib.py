@@ -60,7 +60,8 @@ SIGNATURES = {
                                  c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P]),
     "dmvae_train_step_dev": (c_int, [_CFG, _P, _P, _P, _P, _P, _P, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                      c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, _P]),
-    "dmvae_train_step_resident": (c_int, [_CFG, _P, _P, _P, _P, _P, c_int64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
+    "dmvae_resident_row": (c_int64, [c_uint64, c_int64, c_int64, c_int64]),
+    "dmvae_train_step_resident": (c_int, [_CFG, _P, _P, _P, _P, _P, c_int64, c_int, c_uint64, c_uint64, c_uint64, POINTER(DmvaeLossWeights),
                                           c_float, c_int64, POINTER(DmvaeAdam), _P, _P, _P, POINTER(DmvaeDpPeers), _P]),
     "dmvae_train_fwd_bwd_dev": (c_int, [_CFG, _P, _P, _P, c_uint64, c_uint64, _P, POINTER(DmvaeLossWeights),
                                         c_float, c_int64, _P, _P, _P]),
@@ -84,6 +85,7 @@ SIGNATURES = {
     "dmvae_profile_begin": (c_int, []),
     "dmvae_profile_end": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
+    "dmvae_tf32_probe": (c_int, [c_int64, c_int, _P, POINTER(ctypes.c_double), _P]),
 }
 KERNEL_COUNT = 16
 ABI_VERSION = 2

@@ -193,16 +193,18 @@ class DataParallelTrainer:
         self.engine.apply()
         return self.engine.grad_buf[self.engine.n_params:]
 
-    def capture(self, local_rows: int, host_batch=None, host_losses=None, dataset=None):
+    def capture(self, local_rows: int, host_batch=None, host_losses=None, dataset=None, shuffle=False, shuffle_seed=0):
         """The whole data-parallel step for ``local_rows`` rows per rank as one CUDA graph on every rank:
         fused forward+loss+backward, the SUM all-reduce of [gradients | losses] (NCCL, captured), Adam,
         repack (engine = ``FusedTrainer``; equal shards).  Returns the engine's ``GraphStep``."""
         B, offset = self.global_batch_layout(int(local_rows), True)
         if self.peers is not None:
             return self.engine.capture(int(local_rows), host_batch=host_batch, host_losses=host_losses, sample_offset=offset,
-                                       global_batch=B, peers=self.peers, peers_reset=self._reset_flags, dataset=dataset)
+                                       global_batch=B, peers=self.peers, peers_reset=self._reset_flags, dataset=dataset,
+                                       shuffle=shuffle, shuffle_seed=shuffle_seed)
         if dataset is not None and self.world == 1:
-            return self.engine.capture(int(local_rows), host_losses=host_losses, dataset=dataset)
+            return self.engine.capture(int(local_rows), host_losses=host_losses, dataset=dataset, shuffle=shuffle,
+                                       shuffle_seed=shuffle_seed)
         if dataset is not None:
             raise ValueError("a resident dataset needs the peer exchange (exchange='peer') when there is more than one rank")
         reduce_fn = None

@@ -96,11 +96,12 @@ class FusedTrainer:
 
     def capture(self, B: int, host_batch: Optional[torch.Tensor] = None, host_losses: Optional[torch.Tensor] = None,
                 sample_offset: int = 0, all_reduce=None, global_batch: Optional[int] = None, peers=None,
-                peers_reset=None, dataset: Optional[torch.Tensor] = None) -> "GraphStep":
+                peers_reset=None, dataset: Optional[torch.Tensor] = None, shuffle: bool = False,
+                shuffle_seed: int = 0) -> "GraphStep":
         """The whole step for batch size ``B`` as one CUDA graph (host-driven ``step()`` / ``apply()`` calls may
         be mixed in: ``replay()`` re-synchronises the device-side step counter when needed)."""
         return GraphStep(self, B, host_batch, host_losses, sample_offset, all_reduce, global_batch, peers, peers_reset,
-                         dataset)
+                         dataset, shuffle, shuffle_seed)
 
     # ------------------------------------------------------------------ passes
     def loss_and_grads(self, batch: torch.Tensor, eps: Optional[torch.Tensor] = None,
@@ -188,14 +189,16 @@ class GraphStep:
     def __init__(self, trainer: "FusedTrainer", B: int, host_batch: Optional[torch.Tensor] = None,
                  host_losses: Optional[torch.Tensor] = None, sample_offset: int = 0,
                  all_reduce=None, global_batch: Optional[int] = None, peers=None, peers_reset=None,
-                 dataset: Optional[torch.Tensor] = None):
+                 dataset: Optional[torch.Tensor] = None, shuffle: bool = False, shuffle_seed: int = 0):
         """``all_reduce``: data-parallel ranks pass a callable that SUM-all-reduces a tensor in place (captured
         in the graph between the fused pass and the Adam update) and ``global_batch`` / ``sample_offset`` =
         the global batch size and this rank's row offset.  ``peers`` (a ``DmvaeDpPeers``) instead selects the
         step whose update kernel exchanges the gradients over peer memory itself (``dmvae_train_step_dp``).
         ``dataset``: a device tensor ``(n_batches * B, T, 3)`` that stays resident; update t then reads batch
         ``(t - 1) mod n_batches`` of it, selected in the kernel from the device-side step counter
-        (``dmvae_train_step_resident``): replaying the graph walks the set with no per-step copy (``batch`` is unused)."""
+        (``dmvae_train_step_resident``): replaying the graph walks the set with no per-step copy (``batch`` is unused).
+        ``shuffle``: the rows of every epoch are picked through a new permutation keyed by ``(shuffle_seed, epoch)``, like
+        the reference's ``DataLoader(shuffle=True)`` (``resident_order`` returns the same permutation on the host)."""
         model = trainer.model
         self.trainer = trainer
         self.B = int(B)
@@ -232,7 +235,8 @@ class GraphStep:
                 self.batch.copy_(host_batch, non_blocking=True)
             if dataset is not None:
                 check(lib.dmvae_train_step_resident(trainer._cfg_ref, ptr(arena), ptr(packed), ptr(trainer.m), ptr(trainer.v),
-                                                    ptr(dataset), self.n_batches, ctypes.c_uint64(trainer.seed),
+                                                    ptr(dataset), self.n_batches, int(bool(shuffle)),
+                                                    ctypes.c_uint64(int(shuffle_seed)), ctypes.c_uint64(trainer.seed),
                                                     ctypes.c_uint64(sample_offset), trainer._w_ref, ctypes.c_float(inv), B,
                                                     byref(hyper), ptr(trainer.step_dev), ptr(ws), ptr(trainer.grad_buf),
                                                     byref(peers) if peers is not None else None, stream_ptr()),
@@ -296,6 +300,14 @@ class GraphStep:
         tr._dev_t = tr.t
         tr.model.mark_packed_current()
         return tr.losses
+
+
+def resident_order(n_rows: int, epoch: int, shuffle_seed: int = 0):
+    """The row order of one epoch of a shuffled resident set, as a list: position p reads row ``order[p]``
+    (``dmvae_resident_row``, the function the kernel evaluates per row)."""
+    lib = _lib.lib()
+    return [check(lib.dmvae_resident_row(ctypes.c_uint64(int(shuffle_seed)), int(epoch), p, int(n_rows)), "dmvae_resident_row")
+            for p in range(int(n_rows))]
 
 
 class LossMeter:

@@ -190,13 +190,21 @@ int dmvae_train_step_dev(const DmvaeCfg* cfg, float* params, float* packed, floa
                          const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
                          int64_t* step_dev, void* workspace, float* grads, void* stream);
 /* dmvae_train_step_dev over a data set that is resident in device memory (the reference's
- * DataLoader hands out one batch per step on the host): x_set holds n_batches batches of B rows back to back
- * and update t reads batch (t - 1) mod n_batches, selected in the kernel from the device-side step counter -
- * an epoch is n_batches replays of one captured graph with no per-step copy or host work.  Shuffle by
- * permuting the set between epochs.  peers: NULL, or the data-parallel peers of dmvae_train_step_dp (every
- * rank walks its own resident shard).  Tensor-core path only. */
+ * DataLoader hands out one batch per step on the host, reshuffled every epoch, Training_VAE.py:327): x_set holds
+ * n_batches batches of B rows back to back; update t belongs to epoch e = (t - 1) / n_batches and is batch
+ * b = (t - 1) mod n_batches of it, both derived in the kernel from the device-side step counter - an epoch is
+ * n_batches replays of one captured graph with no per-step copy or host work.
+ *   shuffle == 0   batch b is rows [b B, (b + 1) B) of the set, every epoch;
+ *   shuffle != 0   row r of batch b is row pi(b B + r) of the set, pi = the permutation of [0, n_batches B) keyed
+ *                  by (shuffle_seed, e): every row exactly once per epoch, a new order every epoch, no permutation
+ *                  array anywhere (dmvae_resident_row evaluates the same function on the host).
+ * peers: NULL, or the data-parallel peers of dmvae_train_step_dp (every rank walks its own resident shard with the
+ * same function of (shuffle_seed, epoch, position): the order does not depend on the rank or the world size).
+ * Tensor-core path only. */
+int64_t dmvae_resident_row(uint64_t shuffle_seed, int64_t epoch, int64_t pos, int64_t n_rows);
 int dmvae_train_step_resident(const DmvaeCfg* cfg, float* params, float* packed, float* m, float* v,
-                              const float* x_set, int64_t n_batches, uint64_t seed, uint64_t sample_offset,
+                              const float* x_set, int64_t n_batches, int shuffle, uint64_t shuffle_seed,
+                              uint64_t seed, uint64_t sample_offset,
                               const DmvaeLossWeights* w, float inv_batch, int64_t B, const DmvaeAdam* adam,
                               int64_t* step_dev, void* workspace, float* grads, const DmvaeDpPeers* peers,
                               void* stream);
@@ -286,6 +294,11 @@ int dmvae_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n);
  * by the caller (or through the profile calls) it yields the FFMA peak the fused
  * kernels are measured against.  sink: any device float. */
 int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream);
+/* Tensor-core roofline probe: every SM issues iters x 16 dense tcgen05.mma kind::tf32 products (M = 128, K = 8 per
+ * instruction) on resident operands; *flop_out receives the FLOPs.  mode 0: both operands in shared memory, N = 256;
+ * mode 1: A in tensor memory, N = 128 (the shape the training chain issues).  Timed by the caller it yields the
+ * MEASURED dense TF32 rate; the fp32-equivalent ceiling of the 3xTF32 kernels is one third of it. */
+int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,3 +91,18 @@ def test_compute_calls_fail_loudly_without_a_device(lib):
     with pytest.raises(Exception) as err:
         model.generate(torch.zeros(1, 2), n=4)
     assert "oracle" not in str(err.value).lower()
+
+
+def test_resident_row_is_a_permutation_per_epoch(lib):
+    """dmvae_resident_row (host evaluation of the function the kernel uses to pick the rows of a shuffled resident
+    set): a bijection of [0, n) for every epoch, different between epochs and seeds, and loud on bad arguments."""
+    for n in (1, 2, 3, 255, 256, 257, 5000):
+        for epoch in (0, 1, 1000):
+            order = [lib.dmvae_resident_row(7, epoch, p, n) for p in range(n)]
+            assert sorted(order) == list(range(n)), (n, epoch)
+    a = [lib.dmvae_resident_row(7, 0, p, 5000) for p in range(5000)]
+    b = [lib.dmvae_resident_row(7, 1, p, 5000) for p in range(5000)]
+    c = [lib.dmvae_resident_row(8, 0, p, 5000) for p in range(5000)]
+    assert a != b and a != c and sum(x == y for x, y in zip(a, b)) < 50
+    assert sum(x == i for i, x in enumerate(a)) < 50              # not the identity
+    assert lib.dmvae_resident_row(7, 0, 5, 5) < 0 and lib.dmvae_resident_row(7, -1, 0, 5) < 0

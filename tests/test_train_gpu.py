@@ -396,3 +396,50 @@ def test_resident_dataset_graph_walks_the_set_in_step_order():
         np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-6)
     assert rel_inf(mb.flat_parameters().cpu().numpy(), ma.flat_parameters().cpu().numpy()) < 1e-6
     assert int(tb.step_dev.item()) == 2 * nb + 1
+
+
+def test_shuffled_resident_set_reads_every_row_once_per_epoch_in_a_new_order():
+    """dmvae_train_step_resident(shuffle=1): the reference reshuffles its DataLoader every epoch (Training_VAE.py:327);
+    here row r of batch b of epoch e is row pi_{seed,e}(b B + r) of the resident set.  The kernel's picks are checked
+    against host-driven steps on the batches that dmvae_resident_row (the same function on the host) names; the
+    permutation itself against its invariants (a bijection per epoch, a new order per epoch, a function of
+    (seed, epoch, position) only)."""
+    from dmvae.train import FusedTrainer, resident_order
+    T, L, B, nb = 10, 8, 384, 3
+    n = B * nb
+    orders = [resident_order(n, e, shuffle_seed=99) for e in range(3)]
+    for o in orders:
+        assert sorted(o) == list(range(n))                      # every row exactly once per epoch
+    assert orders[0] != orders[1] and orders[1] != orders[2]    # a new order every epoch
+    assert resident_order(n, 1, shuffle_seed=99) == orders[1] and resident_order(n, 1, shuffle_seed=98) != orders[1]
+    p = O.init_params(T, L, seed=13)
+    data = torch.cat([synth_batch(B, T, seed=170 + i) for i in range(nb)], 0).cuda()
+    ma, mb = make_model(p, T, L), make_model(p, T, L)
+    ta, tb = FusedTrainer(ma, lr=1e-3, seed=5), FusedTrainer(mb, lr=1e-3, seed=5)
+    gs = tb.capture(B, dataset=data, shuffle=True, shuffle_seed=99)
+    for t in range(2 * nb + 2):                     # two epochs and a bit
+        e, b = divmod(t, nb)
+        idx = torch.tensor(orders[e][b * B:(b + 1) * B], device="cuda")
+        la = ta.step(data[idx]).clone()
+        lb = gs.replay().clone()
+        np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-6)
+    assert rel_inf(mb.flat_parameters().cpu().numpy(), ma.flat_parameters().cpu().numpy()) < 1e-6
+
+
+def test_shuffled_resident_set_with_a_ragged_last_tile():
+    """Batch size that is not a multiple of the 128-row tile: rows past the batch end carry nothing."""
+    from dmvae.train import FusedTrainer, resident_order
+    T, L, B, nb = 10, 8, 300, 2
+    n = B * nb
+    p = O.init_params(T, L, seed=14)
+    data = torch.cat([synth_batch(B, T, seed=270 + i) for i in range(nb)], 0).cuda()
+    ma, mb = make_model(p, T, L), make_model(p, T, L)
+    ta, tb = FusedTrainer(ma, lr=1e-3, seed=6), FusedTrainer(mb, lr=1e-3, seed=6)
+    gs = tb.capture(B, dataset=data, shuffle=True, shuffle_seed=3)
+    for t in range(nb + 1):
+        e, b = divmod(t, nb)
+        order = resident_order(n, e, shuffle_seed=3)
+        idx = torch.tensor(order[b * B:(b + 1) * B], device="cuda")
+        la = ta.step(data[idx]).clone()
+        lb = gs.replay().clone()
+        np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-6)
