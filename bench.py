@@ -53,6 +53,13 @@ WEIGHTS = (0.1, 0.1, 1.0, 1.0)            # Training_VAE.py:300-306
 LR = 1e-3                                 # Training_VAE.py:279
 METRIC = "vae_train_samples_per_sec"
 UNIT = "samples/s"
+# the same description in both arms (the driver compares the `config` objects of the two lines)
+WORKLOAD = ("configs[1]: four scenarios jointly, batch 4096 per GPU, full train step (offset transform + forward + "
+            "5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128")
+
+
+def workload_config(batch_per_gpu: int) -> dict:
+    return {"workload": WORKLOAD, "batch_per_gpu": batch_per_gpu, "seq_len": T, "latent_dim": L, "hidden_dim": H}
 
 # per-scenario start boxes of the shipped datasets and direction of travel
 SCENARIOS = (
@@ -248,6 +255,90 @@ def cpu_decode_rate(rows: int, budget_s: float):
     return n * rows / dt, n, dt
 
 
+def reference_config_legs(gpu: bool) -> dict:
+    """BASELINE configs[0] (the reference's own configuration): training on the shipped
+    StaticBlindTown05 set with batch 38 = the whole set (Training_VAE.py:275-280: one step per epoch), and the
+    generate helper at batch 1, with and without the checkpoint load the reference repeats on every call
+    (Tools.py:39-41).  gpu: this repo's drop-in modules; else the oracle port on the host."""
+    import tempfile
+
+    import numpy as np
+    from oracle import vae_oracle as O
+    gold = os.path.join(ROOT, "tests", "golden")
+    data = np.load(os.path.join(gold, "data_sce1_cond.npy")).astype(np.float32)        # (38, 10, 3)
+    ck = np.load(os.path.join(gold, "ckpt_sce1_cond.npz"))
+    out = {"train": {"batch": int(data.shape[0]), "data": "tests/golden/data_sce1_cond.npy (the shipped trajectory_sce1_cond.npy)"},
+           "decode_b1": {"checkpoint": "the shipped vae_offset_sce1_cond_ld8_epoch3000.pth (tests/golden/ckpt_sce1_cond.npz)"}}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "vae_offset_sce1_cond_ld8_epoch3000.pth")
+        torch.save({k: torch.from_numpy(ck[k]) for k in ck.files}, path)
+        sx, sy = float(data[0, 0, 1]), float(data[0, 0, 2])
+        if gpu:
+            import Tools
+            from dmvae import ConditionalTrajectoryVAE
+            from dmvae.train import FusedTrainer
+            torch.manual_seed(0)
+            model = ConditionalTrajectoryVAE(T, D, L).to("cuda")
+            tr = FusedTrainer(model, lr=LR, weights=WEIGHTS, seed=0)
+            batch = torch.from_numpy(data).cuda()
+            for _ in range(20):
+                tr.step(batch)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 400
+            for _ in range(n):
+                float(tr.step(batch)[0])              # the loop reads its loss every step (Training_VAE.py:366-370)
+            dt = time.perf_counter() - t0
+            out["train"].update(steps_per_s=n / dt, samples_per_s=n * data.shape[0] / dt,
+                                how="FusedTrainer.step per epoch + one loss read per step, host-driven launches (FFMA kernels: batches "
+                                    "of at most 128 rows), wall clock")
+            for tag, clear, n in (("cached_checkpoint", False, 300), ("with_checkpoint_load", True, 30)):
+                Tools.load_model_and_generate_trajectory(path, sx, sy, T, D, L)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    if clear:
+                        Tools._MODEL_CACHE.clear()
+                    Tools.load_model_and_generate_trajectory(path, sx, sy, T, D, L)
+                out["decode_b1"][tag + "_calls_per_s"] = n / (time.perf_counter() - t0)
+            out["decode_b1"]["how"] = ("Tools.load_model_and_generate_trajectory, one trajectory per call, result on the host; the drop-in "
+                                       "caches the checkpoint by (path, mtime, size) - with_checkpoint_load clears that cache before every call")
+        else:
+            torch.set_num_threads(os.cpu_count() or 1)
+            p = O.init_params(T, L, seed=0)
+            adam = O.AdamState(p, lr=LR)
+            batch = torch.from_numpy(data)
+
+            def step():
+                _, grads, _ = O.loss_and_grads(p, batch, torch.randn(batch.shape[0], L), WEIGHTS)
+                adam.step(p, grads)
+
+            for _ in range(5):
+                step()
+            t0 = time.perf_counter()
+            n = 0
+            while time.perf_counter() - t0 < 3.0:
+                step()
+                n += 1
+            dt = time.perf_counter() - t0
+            out["train"].update(steps_per_s=n / dt, samples_per_s=n * data.shape[0] / dt,
+                                how=f"oracle port of Training_VAE.py:345-363, {torch.get_num_threads()} threads, wall clock")
+            params = {k: torch.from_numpy(ck[k]) for k in ck.files}
+            start = torch.tensor([[sx, sy]], dtype=torch.float32)
+            for tag, load, budget in (("cached_checkpoint", False, 2.0), ("with_checkpoint_load", True, 3.0)):
+                t0 = time.perf_counter()
+                n = 0
+                while time.perf_counter() - t0 < budget:
+                    if load:                                         # Tools.py:39-41: module construction + torch.load per call
+                        O.init_params(T, L)
+                        params = torch.load(path, map_location="cpu")
+                    O.generate(params, torch.randn(1, L), start)
+                    n += 1
+                out["decode_b1"][tag + "_calls_per_s"] = n / (time.perf_counter() - t0)
+            out["decode_b1"]["how"] = "oracle port of Tools.py:18-65 on the host; with_checkpoint_load = what the reference does on every call"
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port:
     the reference is a flat directory of Python scripts, not installable, and does not travel
@@ -288,14 +379,15 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": min(args.warmup, 5), "ms_per_step": 1e3 * dt / done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: four scenarios jointly, batch 4096, full train step (offset transform + "
-                               "forward + 5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128",
-                   "batch_per_step": B, "device": "host CPU, torch %s, %d threads" % (torch.__version__, torch.get_num_threads())},
+        "config": {**workload_config(B), "device": "host CPU, torch %s, %d threads" % (torch.__version__, torch.get_num_threads()),
+                   "what": "the oracle port of the reference's PyTorch-CPU path (the reference is a flat directory of scripts: "
+                           "not installable, and /root/reference does not exist on the GPU box)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{done} steps x {B} rows of the same workload"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "decode": {"metric": "decoded_trajectories_per_sec", "value": dec_rate, "unit": "trajectories/s",
                    "sample": f"{dec_n} x {1 << 18} rows, shared start, host randn + cond-encoder + decoder + offset add"},
+        "reference_config": reference_config_legs(gpu=False),
         "gpu_launches": 0,
     }
     emit(line)
@@ -334,6 +426,46 @@ def ffma_peak_tflops(lib) -> float:
     return best
 
 
+def tf32_peak_tflops(lib) -> dict:
+    """Dense tcgen05.mma kind::tf32 rate measured with dmvae_tf32_probe: operands in shared memory (N = 256) and A in
+    tensor memory with N = 128 (the shape the training chain issues)."""
+    from dmvae import _lib
+    sink = torch.zeros(4, device="cuda")
+    out = {}
+    for mode, key in ((0, "ss_n256"), (1, "ts_n128")):
+        flop = ctypes.c_double(0.0)
+        best = 0.0
+        iters = 4000 if mode == 0 else 8000        # ~1 ms
+        for rep in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.dmvae_tf32_probe(iters, mode, _lib.ptr(sink), ctypes.byref(flop), _lib.stream_ptr()), "dmvae_tf32_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        out[key] = best
+    return out
+
+
+def bind_to_gpu_numa_node(index: int) -> str:
+    """Pins this process to the CPUs next to its GPU (NVML's affinity mask) BEFORE any pinned host buffer is
+    allocated, so that first-touch places those buffers on the GPU's own NUMA node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs next to GPU {index}"
+        return "NVML affinity mask empty"
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation only
+        return f"unchanged ({type(e).__name__})"
+
+
 def run_cuda(args):
     import torch.distributed as dist
     from dmvae import ConditionalTrajectoryVAE, _lib
@@ -346,6 +478,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -665,20 +798,58 @@ def run_cuda(args):
     d1.record()
     barrier()
     pr_ms = max_over_ranks(d0.elapsed_time(d1)) / Kd
-    # e2e decode: public API, results land in pinned host memory
-    host_out = torch.empty(R, T, 3, dtype=torch.float32).pin_memory()
+    # e2e decode: public API, results land in pinned host memory.  Two device buffers and two pinned host buffers:
+    # launch s + 1 decodes into the other buffer while launch s travels device -> host on a copy stream.
+    host_outs = [torch.empty(R, T, 3, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h_stream = torch.cuda.Stream()
+    dec_done = [torch.cuda.Event() for _ in range(2)]     # decode into device buffer j finished
+    d2h_done = [torch.cuda.Event() for _ in range(2)]     # device buffer j (and host buffer j) free again
+    for ev in d2h_done:
+        ev.record(torch.cuda.current_stream())
+    n_e2e = max(2, Kd // 4) * 4
+
+    def decode_e2e_pass(count):
+        cur = torch.cuda.current_stream()
+        for i in range(count):
+            j, sc = i % 2, i % 4
+            cur.wait_event(d2h_done[j])                                  # its previous copy has left the buffer
+            model.generate(starts[sc], n=R, seed=sc, sample_offset=rank * R, out=outs[j])
+            dec_done[j].record(cur)
+            d2h_stream.wait_event(dec_done[j])
+            with torch.cuda.stream(d2h_stream):
+                host_outs[j].copy_(outs[j], non_blocking=True)
+                d2h_done[j].record(d2h_stream)
+        d2h_stream.synchronize()
+
+    decode_e2e_pass(2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(max(2, Kd // 4)):
-        for s in range(4):
-            model.generate(starts[s], n=R, seed=s, sample_offset=rank * R, out=outs[s])
-            host_out.copy_(outs[s], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    decode_e2e_pass(n_e2e)
     barrier()
     dec_e2e_dt = max_over_ranks(time.perf_counter() - t0)
-    dec_e2e = max(2, Kd // 4) * 4 * R * world / dec_e2e_dt
+    dec_e2e = n_e2e * R * world / dec_e2e_dt
+
+    # the reference shuffles its data set every epoch (Training_VAE.py:327): the same resident step with the rows of
+    # every epoch picked through the keyed permutation (dmvae_train_step_resident, shuffle = 1)
+    shuffled = None
+    if resident and gstep is not None:
+        gsh = trainer.capture(B, dataset=data, shuffle=True, shuffle_seed=7) if world == 1 else \
+            dp.capture(B, dataset=data, shuffle=True, shuffle_seed=7)
+        for i in range(W):
+            gsh.replay()
+        barrier()
+        f0.record()
+        for i in range(K):
+            gsh.replay()
+        f1.record()
+        barrier()
+        sh_ms = max_over_ranks(f0.elapsed_time(f1))
+        shuffled = {"value": K * Bg / (sh_ms * 1e-3), "unit": UNIT, "ms_per_step": sh_ms / K,
+                    "note": "rows of every epoch picked in the kernel through a keyed permutation of the resident set "
+                            "(scattered 120-byte reads instead of one bulk copy per tile)"}
 
     peak_ffma = ffma_peak_tflops(lib)
+    tf32 = tf32_peak_tflops(lib)
     clk = clocks.stop(t_mark0, time.perf_counter()) if clocks is not None else None
     # every rank applied the same updates to the same bits (collective: all ranks take part)
     replicas_identical = dp.parameter_checksum(model.flat_parameters()) if world > 1 else None
@@ -707,6 +878,12 @@ def run_cuda(args):
         dec_cpu_obj = {"value": drate, "unit": "trajectories/s", "cores": cores, "kind": "port",
                        "sample": f"{dn} x {1 << 18} rows in {ddt:.1f} s (oracle generate: host randn + cond-encoder + decoder + offset add)"}
 
+    ref_cfg = None
+    if world == 1:
+        ref_cfg = {"b200": reference_config_legs(gpu=True)}
+        if not args.no_cpu:
+            ref_cfg["host_cpu_port"] = reference_config_legs(gpu=False)
+
     ach = kernel_flop[dominant] / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     tensor_burst = float(peaks.get("bf16_tflops", 1682.8 if not peaks else tensor_peak))
     on_tensor = dominant in ("chain_kernel", "wgrad_kernel", "train_tc_fused_kernel")
@@ -716,10 +893,9 @@ def run_cuda(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 (3xTF32 on tcgen05: tf32 hi/lo split operands, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": "configs[1]: four scenarios jointly, batch 4096 per GPU, fused train step (offset "
-                               "transform + forward + 5-term loss + backward + Adam), seq_len 10, latent 8, hidden 128",
-                   "batch_per_gpu": B, "global_batch": Bg, "parallelism": f"dp{world}",
-                   "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows,
+        "config": {**workload_config(B), "global_batch": Bg, "parallelism": f"dp{world}",
+                   "eps": "in-kernel Philox4x32-10", "dataset_rows_per_gpu": rows, "dataset_rows_total": rows * world,
+                   "host_placement": numa_note,
                    "launch": ("one CUDA graph per step, batch picked in the kernel from the resident set (device-side step counter" if resident else
                               "one CUDA graph per step (device-side Adam step counter") + (
                               ("; the NCCL all-reduce is captured in it)" if dp.exchange == "nccl" else ")")) if gstep is not None else "host-driven launches",
@@ -735,12 +911,17 @@ def run_cuda(args):
                      "peak_source": ("dmvae_ffma_probe measured in this run (FP32 FFMA, all SMs)" if not on_tensor else
                                      "MEASURED_PEAKS.json bf16_tflops (dense bf16, burst: the kernel is timed alone)" if peaks
                                      else "fallback 1682.8 TFLOP/s: MEASURED_PEAKS.json absent"),
-                     "tf32x3_ceiling": tensor_burst / 6.0,
-                     "frac_of_tf32x3_ceiling": ach / (tensor_burst / 6.0) if on_tensor else None,
-                     "note": "3xTF32: TF32 issues at half the bf16 rate and every product takes three passes, so "
-                             "fp32-equivalent work tops out at peak / 6; the chain walks 128-row tiles and at batch 4096 "
-                             "there are only 32 of them for 148 SMs, so train_tc_fused_kernel runs the 32 chain CTAs and "
-                             "96 weight-gradient CTAs side by side in one launch (per-tile ready counters)",
+                     "tf32_dense_measured": tf32,
+                     "tf32x3_ceiling": max(tf32.values()) / 3.0,
+                     "frac_of_tf32x3_ceiling": ach / (max(tf32.values()) / 3.0) if on_tensor and max(tf32.values()) > 0 else None,
+                     "tf32x3_ceiling_assumed_from_bf16": tensor_burst / 6.0,
+                     "note": "3xTF32: every fp32-class product takes three TF32 passes, so fp32-equivalent work tops out at one "
+                             "third of the dense TF32 rate, which dmvae_tf32_probe MEASURES in this run (tf32_dense_measured: "
+                             "operands in shared memory with N = 256, and A in tensor memory with N = 128 - the shape the chain "
+                             "issues); frac stays against the measured bf16 peak as the contract asks.  The chain walks 128-row "
+                             "tiles and at batch 4096 there are only 32 of them for 148 SMs, so train_tc_fused_kernel runs the 32 "
+                             "chain CTAs and 96 weight-gradient CTAs side by side in one launch (per-tile ready counters): the "
+                             "launch is bound by the latency of one tile's 24-product chain, not by issue rate",
                      "flop_per_launch": kernel_flop[dominant], "kernel_ms": dom_ms, "kernel_us": per_kernel_us,
                      "kernel_share_of_step": shares, "step_kernel_ms_sum": step_kernel_ms,
                      "step_tflops": B * fl["train"] / (step_kernel_ms * 1e-3) / 1e12 if step_kernel_ms else None,
@@ -749,6 +930,8 @@ def run_cuda(args):
                      "ffma_kernels_value": ffma_value, "tensor_peak_sustained": tensor_peak,
                      "tensor_peak_source": peak_src},
         "large_batch": big,
+        "shuffled_resident_set": shuffled,
+        "reference_config": ref_cfg,
         "cpu_baseline": cpu_obj,
         "e2e": e2e_obj,
         "gpu_launches": int(launches),
@@ -769,7 +952,9 @@ def run_cuda(args):
                          "traffic_source": (traffic_from_profile("decode_tc_kernel") or {}).get("source"),
                          "traffic_note": "captured by scripts/gpu_check.sh at 262144 rows per launch (31 MB of output, which "
                                          "stays in the 126 MB L2 for the length of the kernel); the algorithmic bytes are 120 B per row",
-                         "tf32x3_ceiling": tensor_burst / 6.0, "frac_of_tf32x3_ceiling": dach / (tensor_burst / 6.0),
+                         "tf32_dense_measured": tf32, "tf32x3_ceiling": max(tf32.values()) / 3.0,
+                         "frac_of_tf32x3_ceiling": dach / (max(tf32.values()) / 3.0) if max(tf32.values()) > 0 else None,
+                         "tf32x3_ceiling_assumed_from_bf16": tensor_burst / 6.0,
                          "ffma_peak_tflops": peak_ffma,
                          "flop_per_launch": R * fl["decode_shared_start"], "kernel_ms": dec_kernel_ms,
                          "hbm_gbs_achieved": R * T * 3 * 4 / (dec_kernel_ms * 1e-3) / 1e9 if dec_kernel_ms else None,
@@ -791,7 +976,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--dataset-rows", type=int, default=1 << 21)
+    ap.add_argument("--dataset-rows", type=int, default=1 << 23,
+                    help="rows per GPU of the resident set: 2^23 = 1.0 GB per GPU, 64 M rows on eight GPUs (BASELINE configs[3])")
     ap.add_argument("--big-batch", type=int, default=1 << 16, help="rows per GPU of the large-batch throughput leg")
     ap.add_argument("--decode-rows", type=int, default=1 << 20)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
