@@ -588,6 +588,52 @@ int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream)
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "ffma_probe");
 }
 
+// ---------------------------------------------------------------------------- validation metrics
+static int check_traj(const float* traj, int64_t n, int32_t T, int32_t layout, const char* what) {
+  if (!traj || n < 1 || T < 2 || T > 400 || (layout != 0 && layout != 1))
+    return fail(DMVAE_ERR_ARG, "%s: need trajectories (n >= 1, 2 <= seq_len <= 400, 3) and layout 0 ([t, x, y]) or 1 ([x, y, t])", what);
+  return DMVAE_OK;
+}
+
+int dmvae_waypoint_speeds(const float* traj, int64_t n, int32_t seq_len, int32_t layout, float* speeds, float* minmax, void* stream) {
+  int rc = check_traj(traj, n, seq_len, layout, "waypoint_speeds");
+  if (rc != DMVAE_OK) return rc;
+  if (!speeds || !minmax) return fail(DMVAE_ERR_ARG, "waypoint_speeds: null output");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_SPEEDS, st, dmvae::launch_speeds(traj, n, seq_len, layout, speeds, minmax, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "waypoint_speeds");
+}
+
+int dmvae_histogram(const float* values, int64_t m, const double* edges, int32_t n_bins, uint64_t* counts, void* stream) {
+  if (!values || !edges || !counts || m < 0 || n_bins < 1 || n_bins > 256)
+    return fail(DMVAE_ERR_ARG, "histogram: null pointer, negative size or n_bins outside 1..256");
+  for (int i = 0; i < n_bins; ++i)
+    if (!(edges[i] <= edges[i + 1])) return fail(DMVAE_ERR_ARG, "histogram: edges must increase monotonically");
+  int sms = 0;
+  const int rc = require_device(&sms);
+  if (rc != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_HISTOGRAM, st,
+                             dmvae::launch_histogram(values, m, edges, n_bins, reinterpret_cast<unsigned long long*>(counts), sms, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "histogram");
+}
+
+int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, int32_t layout, double x0, double x_step, int32_t nx_edges,
+                                double y0, double y_step, int32_t ny_edges, uint64_t* counts, void* stream) {
+  int rc = check_traj(traj, n, seq_len, layout, "trajectories_per_cell");
+  if (rc != DMVAE_OK) return rc;
+  if (!counts || nx_edges < 2 || ny_edges < 2 || !(x_step > 0.0) || !(y_step > 0.0) || (int64_t)(nx_edges - 1) * (ny_edges - 1) > (1 << 24))
+    return fail(DMVAE_ERR_ARG, "trajectories_per_cell: null counts, fewer than two edges, non-positive step or more than 2^24 cells");
+  int sms = 0;
+  if ((rc = require_device(&sms)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_CELLS, st,
+                             dmvae::launch_cells(traj, n, seq_len, layout, x0, x_step, nx_edges, y0, y_step, ny_edges,
+                                                 reinterpret_cast<unsigned long long*>(counts), sms, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "trajectories_per_cell");
+}
+
 int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream) {
   if (!sink || iters < 1 || (mode != 0 && mode != 1)) return fail(DMVAE_ERR_ARG, "tf32_probe: null sink, iters < 1 or mode not 0 / 1");
   int sms = 0;

@@ -108,4 +108,11 @@ cudaError_t launch_loss_grad(const Layout& lo, long long B, const float* recon, 
                              const float* logvar, const float w[4], const float* g_out, float* g_recon, float* g_mu,
                              float* g_logvar, cudaStream_t stream);
 
+// validation metrics over waypoint trajectories (dmvae_metrics.cu); layout 0 = [t, x, y], 1 = [x, y, t]
+cudaError_t launch_speeds(const float* traj, long long n, int T, int layout, float* vel, float* minmax, cudaStream_t stream);
+cudaError_t launch_histogram(const float* values, long long m, const double* edges, int nb, unsigned long long* counts, int sm_count,
+                             cudaStream_t stream);
+cudaError_t launch_cells(const float* traj, long long n, int T, int layout, double x0, double xstep, int nx, double y0, double ystep,
+                         int ny, unsigned long long* counts, int sm_count, cudaStream_t stream);
+
 }  // namespace dmvae

@@ -80,6 +80,10 @@ SIGNATURES = {
     "dmvae_decode_from_condition": (c_int, [_CFG, _P, _P, _P, _P, c_int64, _P]),
     "dmvae_set_decode_impl": (c_int, [c_int]),
     "dmvae_set_train_impl": (c_int, [c_int]),
+    "dmvae_waypoint_speeds": (c_int, [_P, c_int64, c_int32, c_int32, _P, _P, _P]),
+    "dmvae_histogram": (c_int, [_P, c_int64, POINTER(ctypes.c_double), c_int32, _P, _P]),
+    "dmvae_trajectories_per_cell": (c_int, [_P, c_int64, c_int32, c_int32, ctypes.c_double, ctypes.c_double, c_int32,
+                                            ctypes.c_double, ctypes.c_double, c_int32, _P, _P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),
@@ -87,7 +91,7 @@ SIGNATURES = {
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
     "dmvae_tf32_probe": (c_int, [c_int64, c_int, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 16
+KERNEL_COUNT = 19
 ABI_VERSION = 2
 # include/dmvae_debug.h (development aids, outside the drop-in boundary)
 DEBUG_SIGNATURES = {

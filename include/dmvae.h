@@ -272,6 +272,28 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
                         const float* logvar, const DmvaeLossWeights* w, int64_t B, const float* g_out,
                         float* g_recon, float* g_mu, float* g_logvar, void* stream);
 
+/* ---- validation metrics over generated waypoint trajectories -------------------
+ * The reference compares generated with human trajectories through two distributions: waypoint
+ * speeds (Distribution.py:248-296) summarised as a Jensen-Shannon divergence over 50 common histogram edges (:309-331),
+ * and the number of trajectories that visit each cell of a scenario grid (Spatial_Distribution.py:387-431) summarised as
+ * an RMSE (:434-493).  These are the per-trajectory passes for the 10^6 trajectories the generation kernel produces; the
+ * final arithmetic on 49 counts / one count map is the caller's (dmvae/validation.py).
+ *   traj      (n, seq_len, 3) fp32, layout 0 = [t, x, y] (what dmvae_decode writes), 1 = [x, y, t] (the reference's order)
+ * dmvae_waypoint_speeds: speeds (n * seq_len): per trajectory the speed of every step, the last point repeating the last
+ *   step; a step whose time difference is not above 1e-6 repeats the value before it in the flattened array (0 at the very
+ *   beginning) - the reference's loop, evaluated without its sequential dependency.  minmax (2 floats, device): the
+ *   smallest and largest speed.  fp32 arithmetic as the reference's NumPy scalars (within one unit in the last place).
+ * dmvae_histogram: np.histogram(values, bins=edges) for n_bins <= 256 increasing edges (host array of n_bins + 1
+ *   doubles); counts (device, n_bins x uint64) is overwritten.
+ * dmvae_trajectories_per_cell: edges x0 + i * x_step (i < nx_edges, np.arange) and likewise in y; counts (device,
+ *   (ny_edges - 1) x (nx_edges - 1) uint64, row = y cell) is overwritten with the number of trajectories that have at
+ *   least one point in the cell; points outside the grid fall into its border cells (np.clip, as the reference). */
+int dmvae_waypoint_speeds(const float* traj, int64_t n, int32_t seq_len, int32_t layout, float* speeds, float* minmax,
+                          void* stream);
+int dmvae_histogram(const float* values, int64_t m, const double* edges, int32_t n_bins, uint64_t* counts, void* stream);
+int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, int32_t layout, double x0, double x_step,
+                                int32_t nx_edges, double y0, double y_step, int32_t ny_edges, uint64_t* counts, void* stream);
+
 /* ---- instrumentation -------------------------------------------------------
  * Nothing in the reference corresponds to these: they let bench.py report what the
  * library launched and how long the dominant kernel ran inside the timed region.
@@ -279,8 +301,8 @@ int dmvae_loss_backward(const DmvaeCfg* cfg, const float* recon, const float* x,
  * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe,
  * 11 decode (tensor cores), 12 train chain (tensor cores), 13 weight gradients (tensor
  * cores), 14 partial-slab reduction (+ Adam), 15 chain + weight gradients in one launch
- * (small batches). */
-#define DMVAE_KERNEL_COUNT 16
+ * (small batches), 16 waypoint speeds, 17 histogram, 18 trajectories per grid cell. */
+#define DMVAE_KERNEL_COUNT 19
 const char* dmvae_kernel_name(int kernel);
 /* Kernels launched by this process since the library was loaded (kernel < 0: all). */
 int64_t dmvae_launch_count(int kernel);
