@@ -829,6 +829,46 @@ def run_cuda(args):
     dec_e2e_dt = max_over_ranks(time.perf_counter() - t0)
     dec_e2e = n_e2e * R * world / dec_e2e_dt
 
+    # validation metrics over one launch's worth of decoded trajectories: three HBM-bound scans,
+    # timed with CUDA events around the C ABI calls (dmvae/validation.py adds a small device -> host read per call)
+    from dmvae import validation as V
+    metrics = None
+    if rank == 0:
+        import numpy as np
+        tr_m = outs[0]                                          # (R, T, 3) [t, x, y], left there by the decode legs
+        v_m, (v_lo, v_hi) = V.waypoint_speeds(tr_m)
+        edges_m = np.ascontiguousarray(np.linspace(v_lo, v_hi, 50))
+        h_m = V.histogram(v_m, edges_m)
+        H_m = V.trajectories_per_cell(tr_m, "vae_offset_sce4_cond")
+        gx0, gnx, gy0, gny = V.grid_edges("vae_offset_sce4_cond")
+        mm_d = torch.empty(2, device=dev)
+        cnt_d = torch.empty(49, dtype=torch.int64, device=dev)
+        cells_d = torch.empty((gnx - 1) * (gny - 1), dtype=torch.int64, device=dev)
+        calls = (
+            ("waypoint_speeds", R * T * 3 * 4 + R * T * 4,
+             lambda: lib.dmvae_waypoint_speeds(_lib.ptr(tr_m), R, T, 0, _lib.ptr(v_m), _lib.ptr(mm_d), _lib.stream_ptr())),
+            ("histogram_49_bins", R * T * 4,
+             lambda: lib.dmvae_histogram(_lib.ptr(v_m), R * T, edges_m.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 49,
+                                         _lib.ptr(cnt_d), _lib.stream_ptr())),
+            ("trajectories_per_cell", R * T * 3 * 4,
+             lambda: lib.dmvae_trajectories_per_cell(_lib.ptr(tr_m), R, T, 0, gx0, 1.0, gnx, gy0, 1.0, gny, _lib.ptr(cells_d),
+                                                     _lib.stream_ptr())))
+        metrics = {"trajectories": R, "note": "CUDA events around 20 back-to-back calls of the C entry point; algorithmic bytes: 120 B "
+                                              "read per trajectory and pass (+ 40 B of speeds written / read); peak = measured HBM copy rate"}
+        for name, nbytes, call in calls:
+            _lib.check(call(), name)
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(20):
+                call()
+            m1.record()
+            torch.cuda.synchronize()
+            ms_call = m0.elapsed_time(m1) / 20
+            metrics[name] = {"ms": ms_call, "gbs": nbytes / ms_call / 1e6, "frac_of_hbm_peak": nbytes / ms_call / 1e6 / hbm_peak}
+        metrics["check"] = {"histogram_total": int(h_m.sum()), "expected": R * T, "cells_max": int(H_m.max()),
+                            "cells_equal_wrapper": bool((cells_d.cpu().numpy().reshape(H_m.shape) == H_m).all())}
+
     # the reference shuffles its data set every epoch (Training_VAE.py:327): the same resident step with the rows of
     # every epoch picked through the keyed permutation (dmvae_train_step_resident, shuffle = 1)
     shuffled = None
@@ -931,6 +971,7 @@ def run_cuda(args):
                      "tensor_peak_source": peak_src},
         "large_batch": big,
         "shuffled_resident_set": shuffled,
+        "validation_metrics": metrics,
         "reference_config": ref_cfg,
         "cpu_baseline": cpu_obj,
         "e2e": e2e_obj,
