@@ -1199,13 +1199,21 @@ __device__ inline int slot_epilogue(int slot) {
   return CH_EPIS - 1;
 }
 // spin (one lane) until the chain has completed epilogue `epi` of a tile, then order the bulk copies behind it
+// The chain CTAs come first in the grid and never wait, so the counter always moves; should it not (a fault in the chain
+// body), the launch must end with an error instead of hanging the GPU: after two seconds the waiting thread traps.
 __device__ __forceinline__ void wait_tile_ready(const int* flag, int epi) {
   const int need = (epi + 1) * CH_EPI_WARPS;
-  for (;;) {
+  long long t0 = 0;
+  for (int spin = 0;; ++spin) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     if (v >= need) break;
     __nanosleep(100);
+    if ((spin & 1023) == 1023) {
+      const long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ll) __trap();
+    }
   }
   fence_proxy_async_global();
 }
@@ -1693,6 +1701,8 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
                                  const float* __restrict__ loss_part, const __grid_constant__ ReduceTcArgs r,
                                  float* __restrict__ grads, float* __restrict__ p, float* __restrict__ m,
                                  float* __restrict__ v) {
+  // One thread per parameter.  (Four lanes per parameter, each summing a quarter of the slabs, was measured at twice
+  // the time: the update and the scatter then run with a quarter of the lanes on four times the warps.)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < r.n_tile_flags) r.tile_flags[e] = 0;   // every CTA of the fused launch has exited: its counters start over
   __shared__ AdamScalarsTc hs;
