@@ -635,7 +635,7 @@ int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, i
 }
 
 int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream) {
-  if (!sink || iters < 1 || (mode != 0 && mode != 1)) return fail(DMVAE_ERR_ARG, "tf32_probe: null sink, iters < 1 or mode not 0 / 1");
+  if (!sink || iters < 1 || mode < 0 || mode > 3) return fail(DMVAE_ERR_ARG, "tf32_probe: null sink, iters < 1 or mode not 0..3");
   int sms = 0;
   const int rc = require_device(&sms);
   if (rc != DMVAE_OK) return rc;

@@ -318,7 +318,8 @@ int dmvae_profile_end(double* ms_by_kernel, int64_t* launches_by_kernel, int n);
 int dmvae_ffma_probe(int64_t iters, float* sink, double* flop_out, void* stream);
 /* Tensor-core roofline probe: every SM issues iters x 16 dense tcgen05.mma kind::tf32 products (M = 128, K = 8 per
  * instruction) on resident operands; *flop_out receives the FLOPs.  mode 0: both operands in shared memory, N = 256;
- * mode 1: A in tensor memory, N = 128 (the shape the training chain issues).  Timed by the caller it yields the
+ * mode 1: A in tensor memory, N = 128 (the shape the training chain issues); modes 2 / 3: one M = 128, N = 128 product
+ * per PAIR of CTAs (cta_group::2, 64 rows per SM) with A in tensor / shared memory.  Timed by the caller it yields the
  * MEASURED dense TF32 rate; the fp32-equivalent ceiling of the 3xTF32 kernels is one third of it. */
 int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream);
 
