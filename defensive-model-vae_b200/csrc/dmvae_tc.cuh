@@ -132,6 +132,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// The split the tensor core makes by itself: it reads only the TF32 bits of an fp32 word (sign, exponent, ten mantissa
+// bits - the word is CUT, not rounded), so a raw fp32 operand already is its own high half  hi = cut(x);  what remains,
+// x - cut(x), is exact in fp32 and is rounded to TF32 here so that the cut leaves it alone.  One shared-memory image
+// less to write than split_tf32 needs (the raw operand stays in place).
+__device__ __forceinline__ float tf32_cut_low(float x) {
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xffffe000u);
+}
 // the same split in two instructions (cvt.rna rounds to nearest, ties away from zero)
 __device__ __forceinline__ void split_tf32_cvt(float x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));

@@ -1105,7 +1105,8 @@ constexpr int WG_ROWS = 16;                 // batch rows per ring stage (two 8-
 constexpr int WG_STAGE_FLOATS = 8192;       // [A_hi 2048][B_hi <= 2048][A_lo 2048][B_lo <= 2048]
 constexpr int WG_MAX_OPS = 6;
 constexpr int WG_ROLES = 3;
-constexpr int WG_STAGES = 6;
+constexpr int WG_STAGES = 6;                // even: the work warps split alternate stages in two groups
+constexpr int WG_SPLIT_THREADS = WG_WORK_THREADS / 2;
 
 enum WKind { WK_COND0 = 0, WK_COND1, WK_ENC0, WK_ENC1, WK_ENC2, WK_ENC3, WK_HEADS_E, WK_HEADS_C, WK_DEC0_C, WK_DEC0_Z,
              WK_DEC1, WK_DEC2, WK_DEC3 };
@@ -1257,7 +1258,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     if (a.trace != nullptr && my_index == 0) a.trace[180 + role * 16] = global_ns();
     for (int st = 0; st < WG_STAGES; ++st) {
       mbar_init(&raw_full[st], 1);
-      mbar_init(&split_full[st], WG_WORK_WARPS);
+      mbar_init(&split_full[st], WG_WORK_WARPS / 2);
       mbar_init(&empty[st], 1);
     }
     mbar_init(d_done, 1);
@@ -1514,21 +1515,29 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile)
       for (int o = 0; o < n_ops; ++o) {
         const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
-        for (int c = 0; c < chunks; ++c) {
+        for (int c = 0; c < chunks; ++c, rs.advance()) {
+          // the two halves of the work warps take alternate stages (the ring depth is even, so a stage always has the
+          // same half): two stages are being split at any time, which hides the shared-memory round trip, the proxy
+          // fence and the hand-over of one behind the other
+          if ((rs.stage & 1) != (warp >> 2)) continue;
           float4* st4 = reinterpret_cast<float4*>(ring + rs.stage * WG_STAGE_FLOATS);
           mbar_wait(&raw_full[rs.stage], rs.phase);
-          for (int i = tid; i < 512 + nB4; i += WG_WORK_THREADS) {
-            const int idx = i;  // A part [0,512), B part [512, 512 + nB4)
-            const float4 x = st4[idx];
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            split_tf32(x.x, h0, l0); split_tf32(x.y, h1, l1); split_tf32(x.z, h2, l2); split_tf32(x.w, h3, l3);
-            st4[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-            st4[idx + 1024] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          const int n4 = 512 + nB4;   // A part [0, 512), B part [512, 512 + nB4)
+          for (int i0 = tid & (WG_SPLIT_THREADS - 1); i0 < n4; i0 += 4 * WG_SPLIT_THREADS) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)   // all loads of a batch are issued before the first store
+              if (i0 + u * WG_SPLIT_THREADS < n4) x[u] = st4[i0 + u * WG_SPLIT_THREADS];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = i0 + u * WG_SPLIT_THREADS;
+              if (idx < n4)   // the raw words stay where they are: they ARE the high halves (split_tf32_cut)
+                st4[idx + 1024] = make_float4(tf32_cut_low(x[u].x), tf32_cut_low(x[u].y), tf32_cut_low(x[u].z), tf32_cut_low(x[u].w));
+            }
           }
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&split_full[rs.stage]);
-          rs.advance();
         }
         if (per_op) {
           mbar_wait(d_done, done_phase);
