@@ -75,7 +75,8 @@ struct TrainTcPlan {
   int n_slabs;
   int slab_stride;
   size_t stash_floats, slab_floats, loss_floats;   // workspace = [header][stash][slabs][loss partials]
-  bool overlap;               // small batch: chain and weight-gradient CTAs side by side in one launch
+  bool overlap;               // chain and weight-gradient CTAs side by side in one launch (at most SMs / 2 tiles)
+  bool streamed;              // ... with fewer weight-gradient CTAs than tiles x roles: each follows several tiles
 };
 bool train_tc_supported(const Layout& lo);
 void set_chain_trace(long long* device_buffer, int tile = 0);  // development aid (256 int64), null = off; which of CTA 0's tiles

@@ -1239,8 +1239,8 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     raw_full = reinterpret_cast<uint64_t*>(wo_stage + WG_WO_FLOATS);
     split_full = raw_full + 8;
     empty = split_full + 8;
-    d_done = empty + 8;
-    d_free = d_done + 1;
+    d_done = empty + 8;     // two, used alternately: the work warps may be one write-out behind the MMA warp
+    d_free = d_done + 2;
     tmem_slot = reinterpret_cast<uint32_t*>(d_free + 1);
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1261,7 +1261,8 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
       mbar_init(&split_full[st], WG_WORK_WARPS / 2);
       mbar_init(&empty[st], 1);
     }
-    mbar_init(d_done, 1);
+    mbar_init(&d_done[0], 1);
+    mbar_init(&d_done[1], 1);
     mbar_init(d_free, WG_WORK_WARPS);
     mbar_fence_init();
   }
@@ -1283,15 +1284,22 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   // Next to a running chain (one tile per unit) every op is written out as soon as its own products are complete,
   // while the CTA waits for the chain to finish the images of its next op; otherwise once per unit.
   const bool per_op = a.ready != nullptr && ut == 1;
+  // Several tiles per unit next to a running chain: op by op over the unit's tiles (the early images of ALL its tiles
+  // before the late images of the first), so that only the last ops are left when the chain ends.  After a chain
+  // kernel: tile by tile (the next tile's images are being prefetched meanwhile).
+  const bool op_major = a.ready != nullptr && !per_op;
   constexpr int chunks = CH_M / WG_ROWS;  // 8 ring stages per (tile, op)
 
   if (warp == WG_PRODUCER_WARP) {
     if (lane == 0) {
       RingStateRt rs(WG_STAGES);
-      for (long long unit = my_index; unit < n_units; unit += role_ctas)
-      for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile) {
-        const float* ts = a.stash + (size_t)tile * lo.tile_stash;
-        for (int o = 0; o < n_ops; ++o) {
+      for (long long unit = my_index; unit < n_units; unit += role_ctas) {
+        const long long t0 = unit * ut;
+        const int nt = (int)(min((unit + 1) * ut, a.n_tiles) - t0);
+        for (int it = 0; it < nt * n_ops; ++it) {
+          const int o = op_major ? it / nt : it % n_ops;
+          const long long tile = t0 + (op_major ? it % nt : it / n_ops);
+          const float* ts = a.stash + (size_t)tile * lo.tile_stash;
           const WOp op = ops[o];
           const float* srcA = ts + lo.slot_off[op.slotA];
           const float* srcB = ts + lo.slot_off[op.slotB];
@@ -1307,7 +1315,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             long long tn = tile;
             if (on == n_ops) {
               on = 0;
-              tn = tile + 1 < min((unit + 1) * ut, a.n_tiles) ? tile + 1 : (unit + role_ctas) * ut;
+              tn = tile + 1 < t0 + nt ? tile + 1 : (unit + role_ctas) * ut;
             }
             if (tn < a.n_tiles) {
               const float* tsn = a.stash + (size_t)tn * lo.tile_stash;
@@ -1329,15 +1337,18 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   } else if (warp == WG_MMA_WARP) {
     RingStateRt rs(WG_STAGES);
     uint32_t free_phase = 0;
+    uint32_t n_commit = 0;   // completions signalled so far: number k goes to d_done[k & 1]
     for (long long unit = my_index; unit < n_units; unit += role_ctas) {
-     if (unit != my_index) {  // the previous unit's accumulators have been read out
-       mbar_wait(d_free, free_phase);
-       free_phase ^= 1u;
-       tc_fence_after();
-     }
-     bool first_tile = true;
-     for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile) {
-      for (int o = 0; o < n_ops; ++o) {
+      if (unit != my_index) {  // the previous unit's accumulators have been read out
+        mbar_wait(d_free, free_phase);
+        free_phase ^= 1u;
+        tc_fence_after();
+      }
+      const long long t0 = unit * ut;
+      const int nt = (int)(min((unit + 1) * ut, a.n_tiles) - t0);
+      for (int it = 0; it < nt * n_ops; ++it) {
+        const int o = op_major ? it / nt : it % n_ops;
+        const bool first_tile = (op_major ? it % nt : it / n_ops) == 0;
         const WOp op = ops[o];
         const uint32_t idesc = umma_idesc_tf32(128, op.FB, UMMA_A_MN | UMMA_B_MN);
         const uint32_t idesc_b1 = umma_idesc_tf32(128, 16, UMMA_A_MN | UMMA_B_MN);
@@ -1374,22 +1385,27 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           __syncwarp();
           rs.advance();
         }
-        if (per_op) {   // this op's accumulator is final (one tile per unit): the work warps write it out right away
-          if (elect_one()) umma_commit(d_done);
+        if (per_op) {   // this op's accumulator is final (one tile per unit): the work warps write it out while the
+          if (elect_one()) umma_commit(&d_done[n_commit & 1u]);   // next op's products run
           __syncwarp();
+          ++n_commit;
         }
       }
-      first_tile = false;
-     }
-     if (!per_op) {
-       if (elect_one()) umma_commit(d_done);
-       __syncwarp();
-     }
+      if (!per_op) {
+        if (elect_one()) umma_commit(&d_done[n_commit & 1u]);
+        __syncwarp();
+        ++n_commit;
+      }
     }
   } else if (warp < WG_WORK_WARPS) {
     // ===================== work warps: TF32 split of the raw stages, then the final write-out ======
     RingStateRt rs(WG_STAGES);
-    uint32_t done_phase = 0;
+    uint32_t n_done = 0;     // completions consumed so far (the MMA warp's n_commit)
+    auto wait_done = [&]() {
+      mbar_wait(&d_done[n_done & 1u], (n_done >> 1) & 1u);
+      ++n_done;
+      tc_fence_after();
+    };
     // one op's accumulator -> the unit's partial slab
     auto write_op = [&](int o, long long unit) {
     const int q = warp & 3, hh = warp >> 2;
@@ -1512,8 +1528,11 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
         }
     };
     for (long long unit = my_index; unit < n_units; unit += role_ctas) {
-    for (long long tile = unit * ut; tile < min((unit + 1) * ut, a.n_tiles); ++tile)
-      for (int o = 0; o < n_ops; ++o) {
+    const int nt = (int)(min((unit + 1) * ut, a.n_tiles) - unit * ut);
+    int pending = -1;   // per_op: the op whose accumulator is complete (or about to be) and not yet written out
+    for (int it = 0; it < nt * n_ops; ++it) {
+      {
+        const int o = op_major ? it / nt : it % n_ops;
         const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
         for (int c = 0; c < chunks; ++c, rs.advance()) {
           // the two halves of the work warps take alternate stages (the ring depth is even, so a stage always has the
@@ -1540,19 +1559,26 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           if (lane == 0) mbar_arrive(&split_full[rs.stage]);
         }
         if (per_op) {
-          mbar_wait(d_done, done_phase);
-          done_phase ^= 1u;
-          tc_fence_after();
-          if (a.trace != nullptr && unit == 0 && tid == 0 && o == n_ops - 1) a.trace[180 + role * 16 + 8] = global_ns();
-          write_op(o, unit);
+          // the stages of op o are split and on their way through the tensor cores: meanwhile the accumulator of the
+          // op before it (complete by now, or soon) goes to the slab - a write-out costs almost as much as the
+          // products of an op, and the accumulators of a role do not share columns
+          if (pending >= 0) {
+            wait_done();
+            write_op(pending, unit);
+          }
+          pending = o;
         }
       }
+    }
+    if (per_op && pending >= 0) {
+      wait_done();
+      if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
+      write_op(pending, unit);
+    }
 
     // ---- write-out: accumulators -> the unit's partial slab (torch layout of each tensor) ----------
     if (!per_op) {
-      mbar_wait(d_done, done_phase);
-      done_phase ^= 1u;
-      tc_fence_after();
+      wait_done();
       if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
       for (int o = 0; o < n_ops; ++o) write_op(o, unit);
     }
@@ -1819,19 +1845,30 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   p.chain_stages = 5;   // one more than a 128 x 128 layer holds: the first stage of the next op is always in flight
   while (p.chain_stages > 2 && chain_smem_bytes(lo, p.chain_stages) > 232448) --p.chain_stages;
   p.chain_smem = chain_smem_bytes(lo, p.chain_stages);
-  // Small batch: every tile gets a chain CTA and one weight-gradient CTA per role, all on their own SM in ONE launch
-  // (train_tc_fused_kernel); the weight gradients then overlap the second half of the chain.
-  p.overlap = (overlap < 0 ? g_tc_overlap : overlap != 0) && (long long)(1 + WG_ROLES) * p.n_tiles <= sm_count;
+  // Chain and weight-gradient CTAs side by side in ONE launch (train_tc_fused_kernel), every CTA on its own SM, a
+  // chain CTA per tile:
+  //   up to a quarter of the SMs in tiles: one weight-gradient CTA per tile and role; the weight gradients overlap the
+  //     second half of the chain;
+  //   up to 68 tiles on 148 SMs ("streamed"): the other SMs are divided between the roles, and a weight-gradient CTA
+  //     follows a unit of several tiles op by op (+14..18 % at batch 4864 .. 8192 over the two kernels, whose chain
+  //     leaves more than half of the GPU idle; break-even at 74 tiles).  More tiles than that and a chain CTA would
+  //     have to walk several tiles while the weight gradients (which cost an SM as much as the chain does) pile up
+  //     behind it: measured slower than the two kernels with chain CTAs of 2..8 tiles at batch 12 288 .. 65 536.
+  const bool want = overlap < 0 ? g_tc_overlap : overlap != 0;
+  p.overlap = want && (long long)(1 + WG_ROLES) * p.n_tiles <= sm_count;
+  p.streamed = want && !p.overlap && 2 * p.n_tiles <= sm_count - 12 && p.n_tiles <= WS_DONE_SLOT;
+  if (p.streamed) p.overlap = true;
   // CTAs per role in proportion to the accumulator columns (= MMA time per tile), at most one per tile.
   // Tiles are grouped into units of at most 4 (64 K steps: bounds the tensor-memory accumulation depth);
   // every unit writes its own partial slab.
   int cols[WG_ROLES], total = 0;
   for (int r = 0; r < WG_ROLES; ++r) { cols[r] = wgrad_role_cols(lo, r); total += cols[r]; }
+  const int wg_sms = p.streamed ? sm_count - p.chain_grid : sm_count;
   int used = 0, slabs = 0;
   for (int r = 0; r < WG_ROLES; ++r) {
-    long long n = (long long)sm_count * cols[r] / total;
+    long long n = (long long)wg_sms * cols[r] / total;
     if (n < 1) n = 1;
-    if (n > p.n_tiles || p.overlap) n = p.n_tiles;
+    if (n > p.n_tiles || (p.overlap && !p.streamed)) n = p.n_tiles;
     p.role_count[r] = (int)n;
     p.role_begin[r] = used;
     used += (int)n;
@@ -1854,7 +1891,6 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
   p.stash_floats = (size_t)p.n_tiles * lo.tile_stash;
   p.slab_floats = (size_t)p.n_slabs * p.slab_stride;
   p.loss_floats = (size_t)p.chain_grid * CH_EPI_WARPS * 4;
-  if (p.overlap && p.n_tiles > WS_DONE_SLOT) p.overlap = false;   // the tile counters live in the workspace header
   return p;
 }
 
@@ -1940,7 +1976,7 @@ cudaError_t launch_reduce_tc(const Layout& lo, const TrainTcPlan& plan, const fl
                              const DmvaeDpPeers* dp, int* tile_flags, cudaStream_t stream) {
   ReduceTcArgs r;
   r.tile_flags = tile_flags;
-  r.n_tile_flags = (tile_flags != nullptr && plan.overlap) ? (int)plan.n_tiles : 0;
+  r.n_tile_flags = (tile_flags != nullptr && plan.overlap) ? (int)plan.n_tiles : 0;   // n_tiles < n_params always (one thread each)
   if (dp != nullptr) r.dp = *dp;
   else { r.dp = DmvaeDpPeers{}; r.dp.world = 1; }
   r.dp_stride = dp_exchange_stride(lo);

@@ -14,6 +14,8 @@ from dmvae import ConditionalTrajectoryVAE, _lib  # noqa: E402
 from dmvae.train import FusedTrainer  # noqa: E402
 
 lib = _lib.lib()
+IMPL = int(os.environ.get("IMPL", "0"))     # dmvae_set_train_impl: 0 default, 2 tensor cores with two launches, 3 tensor cores always
+_lib.check(lib.dmvae_set_train_impl(IMPL), "dmvae_set_train_impl")
 sizes = [int(a) for a in sys.argv[1:]] or [4096, 65536]
 for B in sizes:
     torch.manual_seed(0)
