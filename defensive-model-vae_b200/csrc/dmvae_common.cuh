@@ -109,6 +109,10 @@ struct Layout {
   // is cut into NC64 chunks of 64 outputs, each with its own forward image (high plane, then low plane, 8192
   // floats each: [k-step][k-chunk of 4][n-group of 8][8 n][4 k] with N = 64, no bias row)
   int NC64, d3c_off;
+  // ... and TRAINING on the tensor cores cuts the last decoder layer into NC chunks of 128 outputs, each a 128 x 128
+  // layer of its own: [forward high plane][forward low plane][data-gradient high][data-gradient low], 16384 floats each
+  // (no bias step: the loss epilogue adds the bias); zero beyond output I
+  int d3t_off;
   TcLayer tc[NUM_TC];
   int slot_off[NUM_SLOTS];  // float offset of a stash slot inside a tile's stash
   int slot_w[NUM_SLOTS];    // features per row of the slot in memory (multiple of 32)
@@ -174,13 +178,13 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   for (int t = 0; t < NUM_TC; ++t) {
     TcLayer& c = l.tc[t];
     c.K = H; c.N = H;
-    if (l.NC > 1 && (t == TC_ENC0 || t == TC_ENC1 || t == TC_ENC2 || t == TC_ENC3 || t == TC_HEADS || t == TC_DEC3)) {
-      // long trajectories train on the FFMA kernels (no encoder / heads images); dec3 is chunked (below)
+    if (l.NC > 1 && t == TC_DEC3) {
+      // long trajectories: dec3 is chunked (d3c images for generation, d3t images for training, below)
       c.K = 0; c.Kb = 0; c.N = 16; c.kps = 32; c.off_hi = c.off_lo = q; c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
       continue;
     }
     if (t == TC_COND0) c.K = 8;
-    else if (t == TC_ENC0) c.K = l.Ip;
+    else if (t == TC_ENC0) c.K = l.Ipt;   // long trajectories: NC x 128 contraction rows, walked chunk by chunk
     else if (t == TC_HEADS) { c.K = 2 * H; c.N = l.NH; }
     else if (t == TC_DEC0) c.K = H + l.Lp16;
     else if (t == TC_DEC3) c.N = l.Ip;
@@ -191,7 +195,7 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
     c.off_hi = q; q += c.Kb * c.N;
     c.off_lo = q; q += c.Kb * c.N;
     c.off_thi = c.off_tlo = -1; c.Kt = 0; c.gsz = 0;
-    if (t != TC_COND0 && t != TC_ENC0 && l.NC == 1) {
+    if (t != TC_COND0 && t != TC_ENC0) {
       c.Kt = (t == TC_DEC0) ? H + round_up(l.L, 32) : c.K;
       c.gsz = c.N / 8 < 4 ? c.N / 8 : 4;
       c.off_thi = q; q += c.Kt * c.N;
@@ -205,12 +209,14 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
     c.K = H; c.Kb = 0; c.N = 64; c.kps = 8; c.off_hi = q; c.off_lo = q + 8192;
     q += l.NC64 * 16384;
   }
+  l.d3t_off = q;
+  if (l.NC > 1) q += l.NC * 65536;
   {
     int o = 0;
     for (int sl = 0; sl < NUM_SLOTS; ++sl) {
       int w = H;
       if (sl == SX_START) w = 16;
-      else if (sl == SX_X || sl == SG_REC) w = l.Ip;
+      else if (sl == SX_X || sl == SG_REC) w = l.Ipt;   // long trajectories: NC images of 128 features, back to back
       else if (sl == SX_Z) w = l.Lp16;
       else if (sl == SG_ML) w = l.NH;
       l.slot_off[sl] = o; l.slot_n[sl] = w; l.slot_w[sl] = round_up(w, 32);
@@ -220,6 +226,16 @@ inline int make_layout(const DmvaeCfg* c, Layout* lo) {
   }
   l.n_packed = round_up(q, 4);
   return DMVAE_OK;
+}
+
+// The last decoder layer as the training chain sees it: chunk c of 128 outputs as a 128 x 128 layer (one chunk - the
+// layer's own images - up to 128 features).
+__host__ __device__ inline TcLayer dec3_chunk_layer(const Layout& lo, int c) {
+  if (lo.NC == 1) return lo.tc[TC_DEC3];
+  TcLayer t;
+  t.off_hi = lo.d3t_off + c * 65536; t.off_lo = t.off_hi + 16384; t.off_thi = t.off_hi + 32768; t.off_tlo = t.off_hi + 49152;
+  t.K = H; t.Kb = H; t.N = H; t.kps = STAGE_FLOATS / (16 * H); t.Kt = H; t.gsz = 4;
+  return t;
 }
 
 // --------------------------------------------------------------------------------------

@@ -78,7 +78,7 @@ __host__ __device__ inline float tc_weight(const Layout& lo, const float* __rest
 }
 
 // The arena is cut into segments (one per image / bias row); element idx of a segment:
-enum PackSeg { PS_FW = 0, PS_FB, PS_RW, PS_RW_HEADS, PS_RW_DEC0C, PS_RW_DEC0Z, PS_TC, PS_TT, PS_D3C };
+enum PackSeg { PS_FW = 0, PS_FB, PS_RW, PS_RW_HEADS, PS_RW_DEC0C, PS_RW_DEC0Z, PS_TC, PS_TT, PS_D3C, PS_D3T };
 
 // index of (k, n) inside a tensor-core forward plane: [k-step][k-chunk of 4][n-group of 8][8 n][4 k]
 __host__ __device__ inline int tc_plane_index(const TcLayer& c, int k, int n) {
@@ -148,6 +148,20 @@ __host__ __device__ inline void pack_element(const Layout& lo, int type, int l, 
       q[lo.d3c_off + c * 16384 + 8192 + r] = tf32_rn(w - hi);
       break;
     }
+    case PS_D3T: {
+      // last decoder layer of a long trajectory, training: per chunk of 128 outputs a forward image and a
+      // data-gradient image of a 128 x 128 layer (dec3_chunk_layer); idx walks (chunk, k, n)
+      const int c = idx >> 14, r = idx & 16383;
+      const int k = r >> 7, n = r & 127;
+      const int ng = c * 128 + n;
+      const float w = ng < lo.I ? p[lo.p_w[L_DEC3] + ng * H + k] : 0.f;
+      const float hi = tf32_rn(w), lw = tf32_rn(w - hi);
+      const TcLayer t = dec3_chunk_layer(lo, c);
+      const int fi = tc_plane_index(t, k, n), ti = tc_tplane_index(t, k, n);
+      q[t.off_hi + fi] = hi; q[t.off_lo + fi] = lw;
+      q[t.off_thi + ti] = hi; q[t.off_tlo + ti] = lw;
+      break;
+    }
     default: {
       // data-gradient planes: [group of gsz steps of n][slice of 32 k][step][2 atoms][4 n][32 k, 32-byte units
       // swizzled by n % 4]
@@ -197,6 +211,7 @@ inline PackPlan make_pack_plan(const Layout& lo) {
     if (lo.tc[t].off_thi >= 0) add(PS_TT, t, lo.tc[t].Kt * lo.tc[t].N);
   }
   if (lo.NC > 1) add(PS_D3C, 0, lo.NC64 * 8192);
+  if (lo.NC > 1) add(PS_D3T, 0, lo.NC * 16384);
   plan.block0[plan.n] = blocks;
   return plan;
 }
@@ -250,6 +265,10 @@ __host__ __device__ inline void scatter_param(const Layout& lo, int e, float val
     const int idx = (k >> 3) * 512 + ((k >> 2) & 1) * 256 + ((n & 63) >> 3) * 32 + (n & 7) * 4 + (k & 3);
     q[lo.d3c_off + (n >> 6) * 16384 + idx] = hi;
     q[lo.d3c_off + (n >> 6) * 16384 + 8192 + idx] = lw;
+    const TcLayer t = dec3_chunk_layer(lo, n >> 7);   // ... and the training images of the same chunk
+    const int fi = tc_plane_index(t, k, n & 127), ti = tc_tplane_index(t, k, n & 127);
+    q[t.off_hi + fi] = hi; q[t.off_lo + fi] = lw;
+    q[t.off_thi + ti] = hi; q[t.off_tlo + ti] = lw;
     return;
   }
   if (!tc) return;

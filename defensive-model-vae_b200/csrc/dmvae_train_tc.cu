@@ -67,7 +67,7 @@ constexpr int CH_MMA_WARP = CH_EPI_WARPS + 1;
 constexpr int CH_SIGNAL_WARP = CH_EPI_WARPS + 2;   // publishes the per-tile progress counter of the fused launch
 constexpr int CH_THREADS = (CH_SIGNAL_WARP + 1) * 32;
 constexpr int CH_M = 128;
-constexpr int CH_MAX_OPS = 28;
+constexpr int CH_MAX_OPS = 56;            // 24 + 3 per extra 128-feature chunk of a long trajectory (at most 10 chunks)
 // Tensor-memory columns: TWO accumulators and the A operand (TF32 high and low halves, 128 columns each).  Consecutive
 // 128 x 128 layers alternate between the accumulators, so the products of layer l + 1 (into the other accumulator) run
 // while the epilogue warps still read layer l's.  The small operands and accumulators of the odd-shaped steps (heads,
@@ -111,8 +111,10 @@ struct ChainArgs {
   long long B;
   float w_recon, w_kld, w_start, w_time, inv_batch;
   int stages;
-  COp ops[CH_MAX_OPS];   // the per-tile GEMM program (chain_program, built on the host)
+  COp ops[CH_MAX_OPS];   // the per-tile GEMM program (chain_program / chain_program_long, built on the host)
   int n_ops;
+  int n_chunks;          // 0: trajectories of up to 64 floats (3 T <= 64); else their 128-feature chunks (chain_program_long)
+  int n_epis;            // epilogues per tile: CH_EPIS + 3 (n_chunks - 1)
   long long* trace;   // development aid: clock64 stamps of CTA 0, one of its tiles (null in production)
   int trace_tile;     // which of CTA 0's tiles (0 = its first)
   int* ready;         // when set: per-tile counter, + (epilogue warps) per epilogue, once the stash images of that
@@ -183,11 +185,66 @@ __host__ __device__ inline int chain_program(const Layout& lo, COp* ops) {
   return n;
 }
 
+// Trajectories of more than 64 floats (3 T > 64): the first encoder layer contracts over NC chunks of 128 features and
+// the last decoder layer produces NC chunks of 128 outputs - each chunk a 128 x 128 product of its own (dec3_chunk_layer),
+// with the A operand re-staged between chunks by an epilogue of its own:
+//   enc0 chunk c     D0 (+)= x_rel[:, chunk c] W0[chunk c]      then: stage x_rel chunk c + 1 (last chunk: the usual epilogue)
+//   dec3 chunk c     D0   = d3 W3[chunk c]                      then: the loss over these 128 features (carrying the time
+//                                                                     walk from chunk to chunk); the gradient goes to the stash
+//   b_dec3 chunk c   D1 (+)= g_rec[:, chunk c] W3[chunk c]^T    then: stage g_rec chunk c + 1 from the stash (last: usual)
+// Everything between is the program of chain_program.
+__host__ __device__ inline int chain_program_long(const Layout& lo, COp* ops) {
+  const int zs = lo.Lp16 / 8, NC = lo.NC;
+  const int A = (int)CT_AHI, Al = (int)CT_ALO, D0 = (int)CT_D0, D1 = (int)CT_D1;
+  int n = 0;
+  auto fwd = [&](const TcLayer& c, int k0, int nk, int a_hi, int a_lo, int d_col, int acc, int wait_a, int commit_d, int pipe) {
+    ops[n++] = c_op(c, k0, nk, 0, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe);
+  };
+  auto bwd = [&](const TcLayer& c, int k0, int nk, int a_hi, int a_lo, int d_col, int acc, int wait_a, int commit_d, int pipe) {
+    ops[n++] = c_op(c, k0, nk, 1, a_hi, a_lo, d_col, acc, wait_a, commit_d, pipe);
+  };
+  for (int c = 0; c < NC; ++c) fwd(lo.tc[TC_ENC0], 16 * c, 16, A, Al, D0, c > 0, 1, 1, 0);
+  fwd(lo.tc[TC_ENC1], 0, 16, A, Al, D1, 0, 1, 1, 1);
+  fwd(lo.tc[TC_ENC2], 0, 16, A, Al, D0, 0, 1, 1, 1);
+  fwd(lo.tc[TC_ENC3], 0, 16, A, Al, D1, 0, 1, 1, 1);
+  fwd(lo.tc[TC_HEADS], 0, 16, A, Al, (int)CT_HEADS, 0, 1, 0, 0);
+  fwd(lo.tc[TC_COND0], 0, 1, (int)CT_START_HI, (int)CT_START_LO, D1, 0, 0, 1, 0);
+  fwd(lo.tc[TC_COND1], 0, 16, A, Al, D1, 0, 1, 1, 0);
+  fwd(lo.tc[TC_HEADS], 16, 16, A, Al, (int)CT_HEADS, 1, 1, 1, 0);
+  fwd(lo.tc[TC_DEC0], 0, 16, A, Al, D1, 0, 0, 0, 0);
+  fwd(lo.tc[TC_DEC0], 16, zs, (int)CT_Z_HI, (int)CT_Z_LO, D1, 1, 1, 1, 0);
+  fwd(lo.tc[TC_DEC1], 0, 16, A, Al, D0, 0, 1, 1, 1);
+  fwd(lo.tc[TC_DEC2], 0, 16, A, Al, D1, 0, 1, 1, 1);
+  for (int c = 0; c < NC; ++c) fwd(dec3_chunk_layer(lo, c), 0, 16, A, Al, D0, 0, 1, 1, 0);
+  for (int c = 0; c < NC; ++c) bwd(dec3_chunk_layer(lo, c), 0, 4, A, Al, D1, c > 0, 1, 1, 0);
+  bwd(lo.tc[TC_DEC2], 0, 4, A, Al, D0, 0, 1, 1, 1);
+  bwd(lo.tc[TC_DEC1], 0, 4, A, Al, D1, 0, 1, 1, 1);
+  bwd(lo.tc[TC_DEC0], 4, 1, A, Al, (int)CT_DZ, 0, 1, 1, 0);
+  bwd(lo.tc[TC_DEC0], 0, 4, A, Al, D1, 0, 0, 0, 0);
+  bwd(lo.tc[TC_HEADS], 4, 4, (int)CT_GML_HI, (int)CT_GML_LO, D1, 1, 1, 1, 0);
+  bwd(lo.tc[TC_COND1], 0, 4, A, Al, D1, 0, 1, 1, 0);
+  bwd(lo.tc[TC_HEADS], 0, 4, (int)CT_GML_HI, (int)CT_GML_LO, D1, 0, 1, 1, 0);
+  bwd(lo.tc[TC_ENC3], 0, 4, A, Al, D0, 0, 1, 1, 1);
+  bwd(lo.tc[TC_ENC2], 0, 4, A, Al, D1, 0, 1, 1, 1);
+  bwd(lo.tc[TC_ENC1], 0, 4, A, Al, D0, 0, 1, 1, 1);
+  return n;
+}
+// Epilogue e of a tile with nc chunks (nc = 1: the list c_epi itself) -> its row of c_epi, or one of the chunk
+// epilogues: EP_STAGE_X / EP_LOSS / EP_STAGE_G with the chunk they work on
+enum EpiType { EP_HIDDEN = 0, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0, EP_STAGE_X, EP_STAGE_G };
+struct EpiRef { int type, row, chunk; };
+__host__ __device__ inline EpiRef epi_at(int e, int nc) {
+  if (e < nc - 1) return EpiRef{EP_STAGE_X, -1, e + 1};
+  if (e < nc + 9) return EpiRef{-1, e - (nc - 1), 0};                    // rows 0..9: E1 .. D3
+  if (e < 2 * nc + 9) return EpiRef{EP_LOSS, 10, e - (nc + 9)};
+  if (e < 3 * nc + 8) return EpiRef{EP_STAGE_G, -1, e - (2 * nc + 9) + 1};
+  return EpiRef{-1, 11 + e - (3 * nc + 8), 0};                            // rows 11..20: the data gradients
+}
+
 // relu' mask slots (CH_MW words per epilogue thread and slot, in shared memory)
 enum MaskSlot { MK_HC1 = 0, MK_HC, MK_E1, MK_E2, MK_E3, MK_E4, MK_D1, MK_D2, MK_D3, MK_COUNT };
 // The epilogues of a tile, in the order of the ops that signal them (chain_program).  The tile body is a
 // loop over this table rather than 21 inlined epilogues: the code stays small.
-enum EpiType { EP_HIDDEN = 0, EP_HEADS, EP_LOSS, EP_DGRAD, EP_BDEC0 };
 constexpr int CH_EPIS = 21;
 constexpr int CH_EPI_FIRST_DGRAD = 11;
 __constant__ int c_epi[CH_EPIS][7] = {
@@ -207,8 +264,13 @@ __constant__ int c_epi[CH_EPIS][7] = {
     {EP_DGRAD, MK_E2, SG_E2, 1, -1, CT_D1, 0},        {EP_DGRAD, MK_E1, SG_E1, 0, -1, CT_D0, 0},
 };
 
+// trajectories of more than 64 floats: chunks of 128 features (chain_program_long); nothing of x or recon is kept in
+// shared memory then
+__host__ __device__ inline bool chain_long(const Layout& lo) { return lo.Ip > 64; }
+__host__ __device__ inline size_t chain_scratch_floats(const Layout& lo) { return (lo.Ip == 32 || chain_long(lo)) ? 0 : (size_t)lo.Ip * 128; }
+__host__ __device__ inline size_t chain_x_floats(const Layout& lo) { return chain_long(lo) ? 0 : (size_t)round_up(128 * lo.I, 4); }
 __host__ __device__ inline size_t chain_smem_floats(const Layout& lo, int stages) {
-  return (size_t)stages * STAGE_FLOATS + (size_t)(lo.Ip == 32 ? 0 : lo.Ip * 128) /* recon scratch of the wide-row loss */ + (size_t)round_up(128 * lo.I, 4) /* x tile */ +
+  return (size_t)stages * STAGE_FLOATS + chain_scratch_floats(lo) /* recon scratch of the wide-row loss */ + chain_x_floats(lo) /* x tile */ +
          (size_t)lo.NH * 128 /* mu, logvar */ + (size_t)lo.Lp16 * 128 /* eps */ + MK_COUNT * CH_MW * CH_EPI_THREADS /* masks */ +
          NUM_LAYERS * 128 /* biases */;
 }
@@ -254,8 +316,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     unsigned char* p = smem_dyn + ((1024u - (base & 1023u)) & 1023u);
     ring = reinterpret_cast<float*>(p);
     scratch = ring + (size_t)a.stages * STAGE_FLOATS;
-    xbuf = scratch + (size_t)(Ip == 32 ? 0 : Ip * 128);
-    mlb = xbuf + round_up(128 * I, 4);
+    xbuf = scratch + chain_scratch_floats(lo);
+    mlb = xbuf + chain_x_floats(lo);
     epb = mlb + (size_t)NH * 128;
     masks = reinterpret_cast<uint32_t*>(epb + (size_t)Lp16 * 128);
     bias_s = reinterpret_cast<float*>(masks + MK_COUNT * CH_MW * CH_EPI_THREADS);
@@ -270,6 +332,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
   const long long n_tiles = (a.B + CH_M - 1) / CH_M;
+  const bool lng = a.n_chunks > 0;          // trajectories of more than 64 floats, walked in chunks of 128 features
+  const int NCK = lng ? a.n_chunks : 1;
 
   if (tid == 0) {
     if (a.trace != nullptr && cta == 0) a.trace[176] = global_ns();
@@ -333,7 +397,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     for (long long tile = cta; tile < n_tiles; tile += ncta)
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
-        const bool tr = a.trace != nullptr && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
+        const bool tr = a.trace != nullptr && !lng && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
         if (op.wait_a && !op.pipe) {
           for (int k = 0; k < 4; ++k) mbar_wait(&a_ready[k], a_phase);
         }
@@ -429,7 +493,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     if (lane == 0 && a.ready != nullptr) {
       uint32_t phase = 0;
       for (long long tile = cta; tile < n_tiles; tile += ncta)
-        for (int e = 0; e < CH_EPIS; ++e) {
+        for (int e = 0; e < a.n_epis; ++e) {
           mbar_wait(stash_done, phase);
           phase ^= 1u;
           fence_proxy_async_global();
@@ -496,11 +560,34 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     auto stash_ptr = [&](float* tile_stash, int slot, int chunk) -> float4* {
       return reinterpret_cast<float4*>(tile_stash + lo.slot_off[slot] + mn_image_index(4 * chunk, m, 128, lo.slot_w[slot] * 4));
     };
+    // the batch of this pass: the caller's, or the one the device-side step counter selects in a resident set
+    const unsigned long long x_step = a.x_batches > 0 ? (unsigned long long)(*a.step_dev) : 0ull;
+    const unsigned long long x_b = a.x_batches > 0 ? x_step % (unsigned long long)a.x_batches : 0ull;
+    const unsigned long long x_epoch = a.x_batches > 0 ? x_step / (unsigned long long)a.x_batches : 0ull;
+    const bool shuffled = a.x_batches > 0 && a.x_shuffle != 0;
+    const float* __restrict__ x_batch = a.x + (shuffled ? 0 : (size_t)x_b * (size_t)a.B * I);
+    // long trajectories: a thread reads its row of the tile straight from global memory (the tile does not fit shared
+    // memory); null past the batch end
+    const float* xrow = nullptr;
+    auto set_row = [&](long long tile) {
+      const long long row = tile * CH_M + m;
+      xrow = nullptr;
+      if (row < a.B) {
+        if (shuffled) {
+          const uint32_t src_row = resident_row(a.x_shuffle_seed, x_epoch, (uint32_t)(x_b * (unsigned long long)a.B + (unsigned long long)row),
+                                                (uint32_t)(a.x_batches * a.B));
+          xrow = a.x + (size_t)src_row * I;
+        } else {
+          xrow = x_batch + (size_t)row * I;
+        }
+      }
+    };
+    auto x_at = [&](int n) -> float { return lng ? (xrow != nullptr ? __ldg(xrow + n) : 0.f) : xbuf[m * I + n]; };
     // start point of the tile's row: the 16-wide stash image ([x0, y0, 1, 0...]; the same columns become the A operand
     // of cond0 in the epilogue that precedes it, stage_start_cols)
     auto stage_start = [&](long long tile) {
       if (cp == 0) {
-        const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];   // zeros past the batch end
+        const float sx = x_at(1), sy = x_at(2);   // zeros past the batch end
         float* ts = a.stash + (size_t)tile * lo.tile_stash;
         *stash_ptr(ts, SX_START, 0) = make_float4(sx, sy, 1.0f, 0.f);
 #pragma unroll
@@ -509,7 +596,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     };
     auto stage_start_cols = [&]() {
       if (cp == 0) {
-        const float sx = xbuf[m * I + 1], sy = xbuf[m * I + 2];
+        const float sx = x_at(1), sy = x_at(2);
         uint32_t xh, xl, yh, yl;
         split_tf32(sx, xh, xl);
         split_tf32(sy, yh, yl);
@@ -522,19 +609,21 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     // encoder input of the tile's row: x_rel = x - start on the x, y columns (Training_VAE.py:345-348), zero beyond I
     // -> the A operand of enc0 and the stash image.  Staged before the tile's first MMA; the warps of a lane quarter
     // share the 4-column chunks of a row.
-    auto stage_xrel = [&](long long tile) {
+    // chunk: long trajectories, the 128 features [128 chunk, 128 chunk + 128) and their own stash image
+    auto stage_xrel = [&](long long tile, int chunk) {
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
-      const float* xr = xbuf + m * I;
-      const float sx = xr[1], sy = xr[2];
+      const float sx = x_at(1), sy = x_at(2);
+      const int width = lng ? 128 : Ip, n0 = chunk * 128;
+      float* img = ts + lo.slot_off[SX_X] + (size_t)chunk * (128 * 128);
 #pragma unroll 2
-      for (int c4 = cp; c4 < Ip / 4; c4 += CH_CP) {
+      for (int c4 = cp; c4 < width / 4; c4 += CH_CP) {
         float xv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int n = c4 * 4 + i;
+          const int n = n0 + c4 * 4 + i;
           float val = 0.f;
           if (n < I) {
-            val = xr[n];
+            val = x_at(n);
             const int d = n % 3;
             if (d == 1) val = val - sx;
             else if (d == 2) val = val - sy;
@@ -546,7 +635,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
         for (int i = 0; i < 4; ++i) split_tf32(xv[i], hi[i], lw[i]);
         tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
         tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
-        *stash_ptr(ts, SX_X, c4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        *reinterpret_cast<float4*>(img + mn_image_index(4 * c4, m, 128, width * 4)) = make_float4(xv[0], xv[1], xv[2], xv[3]);
       }
     };
     // reparameterisation noise of the tile's row (injected, or Philox keyed by the global row index): nothing depends
@@ -574,17 +663,21 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       }
     };
 
-    // the batch of this pass: the caller's, or the one the device-side step counter selects in a resident set
-    const unsigned long long x_step = a.x_batches > 0 ? (unsigned long long)(*a.step_dev) : 0ull;
-    const unsigned long long x_b = a.x_batches > 0 ? x_step % (unsigned long long)a.x_batches : 0ull;
-    const unsigned long long x_epoch = a.x_batches > 0 ? x_step / (unsigned long long)a.x_batches : 0ull;
-    const bool shuffled = a.x_batches > 0 && a.x_shuffle != 0;
-    const float* __restrict__ x_batch = a.x + (shuffled ? 0 : (size_t)x_b * (size_t)a.B * I);
     // The tile's trajectories (128 x I floats, contiguous in global memory) -> shared memory, zero past the batch end.
     // A full tile travels as ONE bulk copy issued by one thread (completion on x_full); a ragged or misaligned one is
     // loaded by all threads, which then arrive on the same barrier, so that the wait below is the same either way.
     uint32_t x_phase = 0;
     auto load_x = [&](long long tile, bool with_biases) {
+      if (lng) {   // long trajectories are read from global memory row by row (set_row): only the biases come here
+        if (with_biases)
+          for (int i = tid; i < NUM_LAYERS * 128; i += CH_EPI_THREADS) {
+            const int l = i >> 7, n = i & 127;
+            if (n < lo.Np[l]) bias_s[i] = __ldg(pk + lo.q_b[l] + n);
+          }
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+        if (tid == 0) mbar_arrive(x_full);
+        return;
+      }
       const long long base = tile * CH_M * I;
       const long long left = a.B * I - base;
       const int nval = (int)(left < (long long)CH_M * I ? left : (long long)CH_M * I);
@@ -652,8 +745,9 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     load_x(cta, true);
     wait_x();
     if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[250] = global_ns();
+    set_row(cta);
     stage_start(cta);
-    stage_xrel(cta);
+    stage_xrel(cta, 0);
     arrive_all(false);   // not an epilogue: the staged images are covered by the report of the tile's first epilogue
     if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[251] = global_ns();
 
@@ -661,8 +755,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       const long long row = tile * CH_M + m;
       const bool row_ok = row < a.B;
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
-      tr_tile = a.trace != nullptr && cta == 0 && tile == cta + (long long)a.trace_tile * ncta;
+      tr_tile = a.trace != nullptr && !lng && cta == 0 && tile == cta + (long long)a.trace_tile * ncta;
       epi_no = 0;
+      float lw_prev[16], lw_sum[4], lw_rt;   // state of the chunked loss walk (epi_loss_chunk)
+      int lw_pos;
       stage_eps(tile);   // under the first encoder product
 
       // this thread's features of a 128-wide stash image: base of its row, then per 8-feature unit
@@ -1035,27 +1131,149 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       if (tr_tile && tid == 0) a.trace[245] = clock64();
       };
 
+      // ---- long trajectories: the chunk epilogues --------------------------------------------------------------
+      // x_rel chunk c -> the A operand of the first encoder layer's next product (the previous one has completed: wait_d)
+      auto epi_stage_x = [&](int c) {
+        wait_d();
+        stage_xrel(tile, c);
+        release_a();
+      };
+      // the recon gradient of chunk c, back from the stash -> the A operand of the last decoder layer's data gradient
+      auto stage_g = [&](int c) {
+        const float* img = ts + lo.slot_off[SG_REC] + (size_t)c * (128 * 128);
+#pragma unroll 2
+        for (int c4 = cp; c4 < 32; c4 += CH_CP) {
+          const float4 g = *reinterpret_cast<const float4*>(img + mn_image_index(4 * c4, m, 128, 512));
+          uint32_t hi[4], lw[4];
+          split_tf32(g.x, hi[0], lw[0]); split_tf32(g.y, hi[1], lw[1]); split_tf32(g.z, hi[2], lw[2]); split_tf32(g.w, hi[3], lw[3]);
+          tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+          tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+        }
+      };
+      auto epi_stage_g = [&](int c) {
+        wait_d();
+        stage_g(c);
+        release_a();
+      };
+      // The loss (Training_VAE.py:229-268) over the 128 recon features of chunk c: one thread per row walks them in
+      // groups of 16 straight from tensor memory.  The walk's state lives in the thread from chunk to chunk: the
+      // sums, the previous time value, and the gradients of the last finished group - a time step whose successor runs
+      // backwards gets c_mono added three features later, possibly from the next group or chunk, so a group is written
+      // to the stash only when the next one has been walked.
+      auto epi_loss_chunk = [&](int c, uint32_t dcol) {
+        wait_d();
+        if (cp == 0) {
+          const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
+          const float c_start = a.w_start * a.inv_batch;
+          const float c_t0 = a.w_time * 2.f * a.inv_batch;
+          const float c_mono = T > 1 ? a.w_time * a.inv_batch / (float)(T - 1) : 0.f;
+          const float sx = x_at(1), sy = x_at(2);
+          const float* bias = pk + lo.q_b[L_DEC3];
+          float* img0 = ts + lo.slot_off[SG_REC];
+          auto write_group = [&](int pos, const float (&g)[16]) {   // pos = 8 chunk + group
+            float* img = img0 + (size_t)(pos >> 3) * (128 * 128);
+            const int c4 = (pos & 7) * 4;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<float4*>(img + mn_image_index(4 * (c4 + q4), m, 128, 512)) =
+                  make_float4(g[4 * q4], g[4 * q4 + 1], g[4 * q4 + 2], g[4 * q4 + 3]);
+          };
+          if (c == 0) {
+            lw_sum[0] = lw_sum[1] = lw_sum[2] = lw_sum[3] = 0.f;
+            lw_rt = 0.f;
+            lw_pos = -1;
+          }
+#pragma unroll 1
+          for (int grp = 0; grp < 8; ++grp) {
+            const int nb = c * 128 + grp * 16;
+            uint32_t v[16];
+            tmem_ld16(lane_base + dcol + grp * 16, v);
+            tmem_ld_wait();
+            float gcur[16];
+            const int ph = nb % 3;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = nb + j;
+              int d = ph + (j % 3);
+              d = d >= 3 ? d - 3 : d;                       // n % 3: 0 time, 1 x, 2 y
+              const bool inside = n < I;
+              const bool on = inside && row_ok;
+              const float r = __uint_as_float(v[j]) + (inside ? __ldg(bias + n) : 0.f);
+              const float xv = inside ? x_at(n) : 0.f;
+              const float target = d == 0 ? xv : (d == 1 ? xv - sx : xv - sy);
+              const float diff = r - target;
+              float gn = c_rec * diff;
+              if (on) lw_sum[0] = fmaf(diff, diff, lw_sum[0]);
+              if (d == 0) {
+                if (n == 0) {
+                  if (on) lw_sum[2] = r * r;
+                  gn = fmaf(c_t0, r, gn);
+                } else {
+                  const float dt = r - lw_rt;
+                  if (on && dt < 0.f) {   // relu'(0) = 0: strict
+                    lw_sum[3] -= dt;
+                    gn -= c_mono;
+                    if (j >= 3) gcur[j >= 3 ? j - 3 : 0] += c_mono;
+                    else lw_prev[13 + j] += c_mono;
+                  }
+                }
+                lw_rt = r;
+              } else if (n < 3) {
+                if (on) lw_sum[1] = fmaf(diff, diff, lw_sum[1]);
+                gn = fmaf(c_start, diff, gn);
+              }
+              gcur[j] = on ? gn : 0.f;
+            }
+            if (lw_pos >= 0) write_group(lw_pos, lw_prev);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lw_prev[j] = gcur[j];
+            lw_pos = c * 8 + grp;
+          }
+          if (c == NCK - 1) {
+            write_group(lw_pos, lw_prev);
+            if (row_ok) {
+              loss_acc[0] += lw_sum[0] * (a.inv_batch / (float)I);
+              loss_acc[2] += lw_sum[1] * (a.inv_batch * 0.5f);
+              loss_acc[3] += lw_sum[2] * a.inv_batch + (T > 1 ? lw_sum[3] * (a.inv_batch / (float)(T - 1)) : 0.f);
+            }
+          }
+        }
+        if (c == NCK - 1) {
+          // every product of the last decoder layer is complete: its input d3 may go.  The first chunk of the gradient
+          // comes back from the stash (the other half of the row was written by this lane quarter's first warp)
+          asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
+          stage_g(0);
+        }
+        release_a();
+      };
+
       const long long next = tile + ncta;
 #pragma unroll 1
-      for (int e = 0; e < CH_EPIS; ++e) {
-        const int ty = c_epi[e][0];
-        const uint32_t dcol = (uint32_t)c_epi[e][5];
+      for (int e = 0; e < a.n_epis; ++e) {
+        const EpiRef er = epi_at(e, NCK);
+        if (er.type == EP_STAGE_X) { epi_stage_x(er.chunk); continue; }
+        if (er.type == EP_STAGE_G) { epi_stage_g(er.chunk); continue; }
+        const int er_row = er.row;
+        const int ty = c_epi[er_row][0];
+        const uint32_t dcol = (uint32_t)c_epi[er_row][5];
+        if (ty == EP_LOSS && lng) { epi_loss_chunk(er.chunk, dcol); continue; }
         if (ty == EP_HIDDEN) {
-          epi_hidden(c_epi[e][1], c_epi[e][2], c_epi[e][4], dcol, c_epi[e][6]);
+          epi_hidden(c_epi[er_row][1], c_epi[er_row][2], c_epi[er_row][4], dcol, c_epi[er_row][6]);
         } else if (ty == EP_DGRAD) {
-          const bool last = e == CH_EPIS - 1;
-          epi_dgrad(c_epi[e][1], c_epi[e][2], c_epi[e][3] != 0, last, dcol);
+          const bool last = e == a.n_epis - 1;
+          epi_dgrad(c_epi[er_row][1], c_epi[er_row][2], c_epi[er_row][3] != 0, last, dcol);
           // after the first data gradient every warp is past the loss (that MMA could not finish before all of
           // them had released its A operand): the x tile can be replaced by the next tile's; after the last one
           // the next tile's start point and encoder input are staged, and only then is the A operand handed over
           if (next < n_tiles) {
-            if (e == CH_EPI_FIRST_DGRAD) {
+            if (er_row == CH_EPI_FIRST_DGRAD && !lng) {
               asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");   // every warp is done with this tile's x
               load_x(next, false);
             } else if (last) {
-              wait_x();
+              if (!lng) wait_x();
+              set_row(next);
               stage_start(next);
-              stage_xrel(next);
+              stage_xrel(next, 0);
             }
           }
           if (last) arrive_all();
@@ -1103,7 +1321,7 @@ constexpr int WG_MMA_WARP = WG_WORK_WARPS + 1;
 constexpr int WG_THREADS = (WG_MMA_WARP + 2) * 32;   // + one idle warp: the fused launch runs both bodies with the chain's block size
 constexpr int WG_ROWS = 16;                 // batch rows per ring stage (two 8-deep contraction steps)
 constexpr int WG_STAGE_FLOATS = 8192;       // [A_hi 2048][B_hi <= 2048][A_lo 2048][B_lo <= 2048]
-constexpr int WG_MAX_OPS = 6;
+constexpr int WG_MAX_OPS = 16;   // long trajectories: one op per 128-feature chunk of enc0 / dec3
 constexpr int WG_ROLES = 3;
 constexpr int WG_STAGES = 6;                // even: the work warps split alternate stages in two groups
 constexpr int WG_SPLIT_THREADS = WG_WORK_THREADS / 2;
@@ -1119,6 +1337,7 @@ struct WOp {
   int bias;          // 0 none; 1: A x ones -> column 0 of a 16-wide accumulator (lane = feature);
                      // 2: ones x B -> lane 0 of an FB-wide accumulator
   int d_col_b;
+  int chunk;         // long trajectories: the 128-feature chunk of x_rel / the recon gradient this op reads (B side), else -1
 };
 
 // Layer groups whose accumulators fit tensor memory together; 128-wide layers are spread so that
@@ -1133,7 +1352,7 @@ __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* op
   auto add = [&](int kind, int sa, int sb, int FB, int bias) {
     WOp w;
     w.kind = kind; w.slotA = sa; w.slotB = sb; w.FB = FB; w.d_col = col; col += FB;
-    w.bias = bias; w.d_col_b = col;
+    w.bias = bias; w.d_col_b = col; w.chunk = -1;
     if (bias == 1) col += 16;
     else if (bias == 2) col += FB;
     ops[n++] = w;
@@ -1163,8 +1382,47 @@ __host__ __device__ inline int wgrad_program(const Layout& lo, int role, WOp* op
   }
   return n;
 }
+// Long trajectories (chain_program_long): enc0 and dec3 become one op per 128-feature chunk, more accumulators than
+// tensor memory holds.  Every op is written out (added to the CTA's slab) as soon as it is complete, and the ops
+// alternate between two column sets, so that the write-out of one runs under the products of the next.
+__host__ __device__ inline int wgrad_program_long(const Layout& lo, int role, WOp* ops) {
+  int n = 0;
+  auto add = [&](int kind, int sa, int sb, int FB, int bias, int chunk) {
+    WOp w;
+    w.kind = kind; w.slotA = sa; w.slotB = sb; w.FB = FB; w.d_col = (n & 1) * 256; w.bias = bias; w.d_col_b = w.d_col + 128;
+    w.chunk = chunk;
+    ops[n++] = w;
+  };
+  const bool enc2_in_role2 = wgrad_enc2_in_role2(lo);
+  if (role == 0) {
+    add(WK_COND1, SG_HC, SX_HC1, H, 1, -1);
+    add(WK_COND0, SG_HC1, SX_START, 16, 0, -1);
+    if (!enc2_in_role2) add(WK_ENC2, SG_E3, SX_E2, H, 1, -1);
+    add(WK_ENC1, SG_E2, SX_E1, H, 1, -1);
+  } else if (role == 1) {
+    add(WK_DEC2, SG_D3, SX_D2, H, 1, -1);
+    add(WK_DEC1, SG_D2, SX_D1, H, 1, -1);
+    add(WK_ENC3, SG_E4, SX_E3, H, 1, -1);
+    for (int c = 0; c < lo.NC; ++c) add(WK_ENC0, SG_E1, SX_X, H, c == 0 ? 1 : 0, c);
+  } else {
+    for (int c = 0; c < lo.NC; ++c) add(WK_DEC3, SX_D3, SG_REC, H, 2, c);
+    add(WK_DEC0_C, SG_D1, SX_HC, H, 1, -1);
+    add(WK_DEC0_Z, SG_D1, SX_Z, lo.Lp16, 0, -1);
+    add(WK_HEADS_E, SX_E4, SG_ML, lo.NH, 2, -1);
+    add(WK_HEADS_C, SX_HC, SG_ML, lo.NH, 0, -1);
+    if (enc2_in_role2) add(WK_ENC2, SG_E3, SX_E2, H, 1, -1);
+  }
+  return n;
+}
+// relative cost of a role's ops per tile (for the division of the SMs between the roles)
 __host__ __device__ inline int wgrad_role_cols(const Layout& lo, int role) {
   WOp ops[WG_MAX_OPS];
+  if (chain_long(lo)) {
+    const int n = wgrad_program_long(lo, role, ops);
+    int total = 0;
+    for (int o = 0; o < n; ++o) total += ops[o].FB + (ops[o].bias == 1 ? 16 : (ops[o].bias == 2 ? ops[o].FB / 4 : 0));
+    return total;
+  }
   const int n = wgrad_program(lo, role, ops);
   const WOp& w = ops[n - 1];   // columns are handed out in op order
   return w.bias == 0 ? w.d_col + w.FB : (w.bias == 1 ? w.d_col_b + 16 : w.d_col_b + w.FB);
@@ -1181,6 +1439,8 @@ struct WgradArgs {
   WOp ops[WG_ROLES][WG_MAX_OPS];   // the per-tile program of every role (wgrad_program, built on the host)
   int n_ops[WG_ROLES];
   const int* ready;         // when set: per-tile epilogue counters of the chain CTAs running beside this kernel's
+  int nc;                   // long trajectories: their 128-feature chunks (wgrad_program_long; a CTA adds every op of
+                            // every tile it walks to ONE slab of its own); 0: trajectories of up to 64 floats
   long long* trace;         // development aid: %globaltimer stamps of the CTAs of tile 0 (null in production)
 };
 struct WgradKArgs {
@@ -1192,12 +1452,14 @@ struct WgradKArgs {
 __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-// number of the chain epilogue (c_epi) that completes a stash image
-__device__ inline int slot_epilogue(int slot) {
-  if (slot == SX_START || slot == SX_X) return 0;   // staged before the tile's first epilogue
-  for (int e = 0; e < CH_EPIS; ++e)
-    if (c_epi[e][2] == slot) return e;
-  return CH_EPIS - 1;
+// number of the chain epilogue that completes a stash image; nc: chunks of a long trajectory (epi_at), else 1
+__device__ inline int slot_epilogue(int slot, int nc) {
+  if (slot == SX_START) return 0;                   // staged before the tile's first epilogue
+  if (slot == SX_X) return nc - 1;                  // ... the last chunk of x_rel by the last staging epilogue
+  if (slot == SG_REC) return 2 * nc + 8;            // the last chunk of the loss writes the last gradients
+  for (int r = 0; r < CH_EPIS; ++r)
+    if (c_epi[r][2] == slot) return r < 10 ? r + nc - 1 : r + 3 * (nc - 1);
+  return CH_EPIS + 3 * (nc - 1) - 1;
 }
 // spin (one lane) until the chain has completed epilogue `epi` of a tile, then order the bulk copies behind it
 // The chain CTAs come first in the grid and never wait, so the counter always moves; should it not (a fault in the chain
@@ -1283,7 +1545,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   const int n_ops = a.n_ops[role];
   // Next to a running chain (one tile per unit) every op is written out as soon as its own products are complete,
   // while the CTA waits for the chain to finish the images of its next op; otherwise once per unit.
-  const bool per_op = a.ready != nullptr && ut == 1;
+  const int nck = a.nc > 0 ? a.nc : 1;
+  // Long trajectories: every op of every tile is added to the CTA's one slab as soon as it is complete (the
+  // accumulators of all chunks do not fit tensor memory).  Else next to a running chain with one tile per unit: ...
+  const bool per_op = ut == 1 && (a.ready != nullptr || a.nc > 0);
   // Several tiles per unit next to a running chain: op by op over the unit's tiles (the early images of ALL its tiles
   // before the late images of the first), so that only the last ops are left when the chain ends.  After a chain
   // kernel: tile by tile (the next tile's images are being prefetched meanwhile).
@@ -1302,10 +1567,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           const float* ts = a.stash + (size_t)tile * lo.tile_stash;
           const WOp op = ops[o];
           const float* srcA = ts + lo.slot_off[op.slotA];
-          const float* srcB = ts + lo.slot_off[op.slotB];
-          const int FBm = lo.slot_w[op.slotB];  // width of the B image in memory
+          const float* srcB = ts + lo.slot_off[op.slotB] + (op.chunk > 0 ? (size_t)op.chunk * (128 * 128) : 0);
+          const int FBm = op.chunk >= 0 ? 128 : lo.slot_w[op.slotB];  // width of the B image in memory
           const uint32_t bytesA = WG_ROWS * H * 4, bytesB = (uint32_t)(WG_ROWS * FBm * 4);
-          if (a.ready != nullptr) wait_tile_ready(a.ready + tile, max(slot_epilogue(op.slotA), slot_epilogue(op.slotB)));
+          if (a.ready != nullptr) wait_tile_ready(a.ready + tile, max(slot_epilogue(op.slotA, nck), slot_epilogue(op.slotB, nck)));
           if (a.trace != nullptr && tile == 0) a.trace[180 + role * 16 + 1 + o] = global_ns();
           if (a.ready == nullptr) {
             // After a chain kernel the stash of a large batch streams from HBM, and six 16-row stages in flight do
@@ -1320,7 +1585,8 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             if (tn < a.n_tiles) {
               const float* tsn = a.stash + (size_t)tn * lo.tile_stash;
               l2_prefetch(tsn + lo.slot_off[ops[on].slotA], CH_M * H * 4);
-              l2_prefetch(tsn + lo.slot_off[ops[on].slotB], (uint32_t)(CH_M * lo.slot_w[ops[on].slotB] * 4));
+              if (ops[on].chunk >= 0) l2_prefetch(tsn + lo.slot_off[ops[on].slotB] + (size_t)ops[on].chunk * (128 * 128), CH_M * 128 * 4);
+              else l2_prefetch(tsn + lo.slot_off[ops[on].slotB], (uint32_t)(CH_M * lo.slot_w[ops[on].slotB] * 4));
             }
           }
           for (int c = 0; c < chunks; ++c) {
@@ -1353,7 +1619,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
         const uint32_t idesc = umma_idesc_tf32(128, op.FB, UMMA_A_MN | UMMA_B_MN);
         const uint32_t idesc_b1 = umma_idesc_tf32(128, 16, UMMA_A_MN | UMMA_B_MN);
         // MN-major images: LBO = feature-atom stride (512 bytes), SBO = 4-row-atom stride (width * 16 bytes)
-        const uint32_t FBm = (uint32_t)lo.slot_w[op.slotB];
+        const uint32_t FBm = op.chunk >= 0 ? 128u : (uint32_t)lo.slot_w[op.slotB];
         const uint64_t a_bits = umma_desc(0u, 512u, H * 16u, 1u), b_bits = umma_desc(0u, 512u, FBm * 16u, 1u);
         const uint64_t ones_a_desc = umma_desc(smem_u32(ones_a), 512u, 2048u, 1u);
         const uint64_t ones_b_desc = umma_desc(smem_u32(ones_b), 512u, 512u, 1u);
@@ -1411,8 +1677,12 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     const int q = warp & 3, hh = warp >> 2;
     const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float* slab = a.slabs + (size_t)(a.unit_begin[role] + unit) * a.slab_stride;
+    // long trajectories: one slab per CTA, the first unit writes it, the others add to it
+    const bool add_to = a.nc > 0 && unit != my_index;
+    float* slab = a.slabs + (size_t)(a.unit_begin[role] + (a.nc > 0 ? my_index : unit)) * a.slab_stride;
     float* stg = wo_stage + warp * (32 * 20);   // this warp's staging tile of the write-out
+    const int f0 = ops[o].chunk > 0 ? ops[o].chunk * 128 : 0;   // first feature of the op's chunk of the trajectory
+    auto put = [&](float* dst, float val) { *dst = add_to ? *dst + val : val; };
     const int L = lo.L, I = lo.I;
     {
       const WOp op = ops[o];
@@ -1427,7 +1697,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
         int rstride = H, ncols = 16;
         switch (op.kind) {
           case WK_COND1: row0 = slab + lo.p_w[L_COND1] + c * 16; break;
-          case WK_ENC0: row0 = slab + lo.p_w[L_ENC0] + c * 16; rstride = I; ncols = min(16, I - c * 16); break;
+          case WK_ENC0: row0 = slab + lo.p_w[L_ENC0] + f0 + c * 16; rstride = I; ncols = min(16, I - f0 - c * 16); break;
           case WK_ENC1: row0 = slab + lo.p_w[L_ENC1] + c * 16; break;
           case WK_ENC2: row0 = slab + lo.p_w[L_ENC2] + c * 16; break;
           case WK_ENC3: row0 = slab + lo.p_w[L_ENC3] + c * 16; break;
@@ -1455,12 +1725,17 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             const float4 val = *reinterpret_cast<const float4*>(stg + r * 20 + c4 * 4);
             float* dst = row0 + (size_t)(q * 32 + r) * rstride + c4 * 4;
             if (vec) {
-              *reinterpret_cast<float4*>(dst) = val;
+              float4 out = val;
+              if (add_to) {
+                const float4 old = *reinterpret_cast<const float4*>(dst);
+                out = make_float4(old.x + val.x, old.y + val.y, old.z + val.z, old.w + val.w);
+              }
+              *reinterpret_cast<float4*>(dst) = out;
             } else {
-              if (c4 * 4 + 0 < ncols) dst[0] = val.x;
-              if (c4 * 4 + 1 < ncols) dst[1] = val.y;
-              if (c4 * 4 + 2 < ncols) dst[2] = val.z;
-              if (c4 * 4 + 3 < ncols) dst[3] = val.w;
+              if (c4 * 4 + 0 < ncols) dst[0] = add_to ? dst[0] + val.x : val.x;
+              if (c4 * 4 + 1 < ncols) dst[1] = add_to ? dst[1] + val.y : val.y;
+              if (c4 * 4 + 2 < ncols) dst[2] = add_to ? dst[2] + val.z : val.z;
+              if (c4 * 4 + 3 < ncols) dst[3] = add_to ? dst[3] + val.w : val.w;
             }
           }
           __syncwarp();   // the tile is rewritten by the next chunk
@@ -1472,18 +1747,18 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           const float val = __uint_as_float(v[j]);
           switch (op.kind) {
             case WK_COND0:
-              if (col < 2) slab[lo.p_w[L_COND0] + ln * 2 + col] = val;
-              else if (col == 2) slab[lo.p_b[L_COND0] + ln] = val;
+              if (col < 2) put(slab + lo.p_w[L_COND0] + ln * 2 + col, val);
+              else if (col == 2) put(slab + lo.p_b[L_COND0] + ln, val);
               break;
             case WK_HEADS_E:
             case WK_HEADS_C: {  // transposed: for one column the warp writes 32 consecutive floats
               const int koff = op.kind == WK_HEADS_C ? H : 0;
-              if (col < L) slab[lo.p_w[L_HEADS] + col * (2 * H) + koff + ln] = val;
-              else if (col < 2 * L) slab[lo.p_wlv + (col - L) * (2 * H) + koff + ln] = val;
+              if (col < L) put(slab + lo.p_w[L_HEADS] + col * (2 * H) + koff + ln, val);
+              else if (col < 2 * L) put(slab + lo.p_wlv + (col - L) * (2 * H) + koff + ln, val);
               break;
             }
             default:  // WK_DEC3, transposed
-              if (col < I) slab[lo.p_w[L_DEC3] + col * H + ln] = val;
+              if (f0 + col < I) put(slab + lo.p_w[L_DEC3] + (size_t)(f0 + col) * H + ln, val);
               break;
           }
         }
@@ -1504,7 +1779,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           case WK_DEC1: l = L_DEC1; break;
           default: l = L_DEC2; break;
         }
-        slab[lo.p_b[l] + ln] = val;
+        put(slab + lo.p_b[l] + ln, val);
       } else if (op.bias == 2 && q == 0) {
         for (int c = hh; c < op.FB / 16; c += 2) {
           uint32_t v[16];
@@ -1516,10 +1791,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
               const int col = c * 16 + j;
               const float val = __uint_as_float(v[j]);
               if (op.kind == WK_HEADS_E) {
-                if (col < L) slab[lo.p_b[L_HEADS] + col] = val;
-                else if (col < 2 * L) slab[lo.p_blv + (col - L)] = val;
-              } else if (col < I) {
-                slab[lo.p_b[L_DEC3] + col] = val;
+                if (col < L) put(slab + lo.p_b[L_HEADS] + col, val);
+                else if (col < 2 * L) put(slab + lo.p_blv + (col - L), val);
+              } else if (f0 + col < I) {
+                put(slab + lo.p_b[L_DEC3] + f0 + col, val);
               }
             }
           }
@@ -1533,7 +1808,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     for (int it = 0; it < nt * n_ops; ++it) {
       {
         const int o = op_major ? it / nt : it % n_ops;
-        const int nB4 = WG_ROWS * lo.slot_w[ops[o].slotB] / 4;  // float4 of the B part
+        const int nB4 = WG_ROWS * (ops[o].chunk >= 0 ? 128 : lo.slot_w[ops[o].slotB]) / 4;  // float4 of the B part
         for (int c = 0; c < chunks; ++c, rs.advance()) {
           // the two halves of the work warps take alternate stages (the ring depth is even, so a stage always has the
           // same half): two stages are being split at any time, which hides the shared-memory round trip, the proxy
@@ -1565,6 +1840,9 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           if (pending >= 0) {
             wait_done();
             write_op(pending, unit);
+            // long trajectories: op o + 1 writes the columns this op has just been read from, and its first stage is
+            // handed over by HALF of the work warps - all of them must be done reading first
+            if (a.nc > 0) asm volatile("bar.sync 1, %0;" ::"n"(WG_WORK_THREADS) : "memory");
           }
           pending = o;
         }
@@ -1830,7 +2108,9 @@ __global__ void reduce_tc_kernel(const __grid_constant__ Layout lo, const float*
 // =========================================================================================
 // the extra A columns (64) hold the widest small operand (NH = 2 * latent_dim padded) and, in their last 8, the ones
 // column, which is rewritten at the start of every tile
-bool train_tc_supported(const Layout& lo) { return lo.NC == 1 && lo.Ip <= 64 && lo.NH <= 64; }
+// latent_dim <= 32 (the widest small operand, NH = 2 * latent_dim padded, is 64 columns); any trajectory length: up
+// to 64 floats in one piece (chain_program), longer ones in chunks of 128 features (chain_program_long)
+bool train_tc_supported(const Layout& lo) { return lo.NH <= 64 && lo.Lp16 <= 32; }
 
 static long long* g_chain_trace = nullptr;
 static int g_chain_trace_tile = 0;
@@ -1880,8 +2160,9 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
       const double cost = (double)((units + n - 1) / n) * (u + 0.4);
       if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && u > best_u)) { best_cost = cost; best_u = u; }
     }
+    if (chain_long(lo)) best_u = 1;   // long trajectories: every op of every tile goes straight to the slab of its CTA
     p.unit_tiles[r] = best_u;
-    p.unit_count[r] = (int)((p.n_tiles + p.unit_tiles[r] - 1) / p.unit_tiles[r]);
+    p.unit_count[r] = chain_long(lo) ? (int)n : (int)((p.n_tiles + p.unit_tiles[r] - 1) / p.unit_tiles[r]);
     p.unit_begin[r] = slabs;
     slabs += p.unit_count[r];
   }
@@ -1908,7 +2189,9 @@ static ChainArgs chain_args(const Layout& lo, const TrainTcPlan& plan, const Tra
   a.trace_tile = g_chain_trace_tile;
   a.ready = nullptr;
   for (int o = 0; o < CH_MAX_OPS; ++o) a.ops[o] = COp{};
-  a.n_ops = chain_program(lo, a.ops);
+  a.n_chunks = chain_long(lo) ? lo.NC : 0;
+  a.n_ops = chain_long(lo) ? chain_program_long(lo, a.ops) : chain_program(lo, a.ops);
+  a.n_epis = CH_EPIS + 3 * (a.n_chunks > 0 ? a.n_chunks - 1 : 0);
   return a;
 }
 static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const float* stash, float* slabs) {
@@ -1919,8 +2202,9 @@ static WgradArgs wgrad_args(const Layout& lo, const TrainTcPlan& plan, const flo
     a.unit_tiles[r] = plan.unit_tiles[r];
     a.unit_begin[r] = plan.unit_begin[r];
     for (int o = 0; o < WG_MAX_OPS; ++o) a.ops[r][o] = WOp{};
-    a.n_ops[r] = wgrad_program(lo, r, a.ops[r]);
+    a.n_ops[r] = chain_long(lo) ? wgrad_program_long(lo, r, a.ops[r]) : wgrad_program(lo, r, a.ops[r]);
   }
+  a.nc = chain_long(lo) ? lo.NC : 0;
   a.ready = nullptr;
   a.trace = g_chain_trace;
   return a;

@@ -106,6 +106,9 @@ def per_tensor_err(grads, grads_ref):
     (50, 8, 200, O.SCRIPT_WEIGHTS),     # BASELINE configs[4] lower end of the length sweep
     (100, 16, 150, O.DEFAULT_WEIGHTS),  # three chunks, ragged last chunk (300 = 2*128 + 44)
     (400, 64, 40, O.SCRIPT_WEIGHTS),    # top of the envelope: ten chunks, latent 64
+    (400, 16, 300, O.SCRIPT_WEIGHTS),   # ten chunks on the tensor cores (latent <= 32), several tiles, ragged
+    (200, 32, 5000, O.DEFAULT_WEIGHTS), # five chunks, widest heads layer, 40 tiles: chain CTAs with followers
+    (64, 8, 20000, O.SCRIPT_WEIGHTS),   # 192 features: two chunks, the second half empty; more tiles than SMs
 ])
 def test_fused_fwd_bwd_vs_oracle(T, L, B, weights, impl):
     from dmvae.train import FusedTrainer
