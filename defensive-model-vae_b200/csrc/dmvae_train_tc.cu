@@ -298,6 +298,9 @@ template <> struct TmemVec<8> {
 };
 
 // cta / ncta: index of this CTA among the chain CTAs and their number (the whole grid for chain_kernel)
+// LNG: trajectories of more than 64 floats (chain_program_long); a compile-time switch, so that the short-trajectory
+// instantiation carries none of the chunk walks (as a run-time flag they cost the batch-4096 step 5.6 us)
+template <bool LNG>
 __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a, const int cta, const int ncta,
                                            unsigned char* smem_dyn) {
   const int L = lo.L, I = lo.I, T = lo.T, Ip = lo.Ip, NH = lo.NH, Lp16 = lo.Lp16;
@@ -332,8 +335,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* __restrict__ pk = a.packed;
   const long long n_tiles = (a.B + CH_M - 1) / CH_M;
-  const bool lng = a.n_chunks > 0;          // trajectories of more than 64 floats, walked in chunks of 128 features
-  const int NCK = lng ? a.n_chunks : 1;
+  constexpr bool lng = LNG;                 // trajectories of more than 64 floats, walked in chunks of 128 features
+  const int NCK = LNG ? a.n_chunks : 1;
 
   if (tid == 0) {
     if (a.trace != nullptr && cta == 0) a.trace[176] = global_ns();
@@ -1306,9 +1309,10 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
   if (a.trace != nullptr && cta == 0 && tid == 0) a.trace[177] = global_ns();
 }
 
+template <bool LNG>
 __global__ void __launch_bounds__(CH_THREADS, 1) chain_kernel(const __grid_constant__ ChainKArgs k) {
   extern __shared__ unsigned char smem_dyn[];
-  chain_body(k.lo, k.c, (int)blockIdx.x, (int)gridDim.x, smem_dyn);
+  chain_body<LNG>(k.lo, k.c, (int)blockIdx.x, (int)gridDim.x, smem_dyn);
 }
 
 // =========================================================================================
@@ -1487,6 +1491,7 @@ constexpr size_t WG_SMEM_BYTES = (size_t)WG_STAGES * WG_STAGE_FLOATS * 4 + 4096 
 static_assert(WG_SMEM_BYTES <= 232448, "weight-gradient kernel: shared memory");
 
 // cta: index of this CTA among the weight-gradient CTAs
+template <bool LNG>
 __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a, const int cta, unsigned char* smem_dyn) {
   float *ring, *ones_a, *ones_b, *wo_stage;
   uint64_t *raw_full, *split_full, *empty, *d_done, *d_free;
@@ -1545,10 +1550,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   const int n_ops = a.n_ops[role];
   // Next to a running chain (one tile per unit) every op is written out as soon as its own products are complete,
   // while the CTA waits for the chain to finish the images of its next op; otherwise once per unit.
-  const int nck = a.nc > 0 ? a.nc : 1;
+  const int nck = LNG ? a.nc : 1;
   // Long trajectories: every op of every tile is added to the CTA's one slab as soon as it is complete (the
   // accumulators of all chunks do not fit tensor memory).  Else next to a running chain with one tile per unit: ...
-  const bool per_op = ut == 1 && (a.ready != nullptr || a.nc > 0);
+  const bool per_op = ut == 1 && (a.ready != nullptr || LNG);
   // Several tiles per unit next to a running chain: op by op over the unit's tiles (the early images of ALL its tiles
   // before the late images of the first), so that only the last ops are left when the chain ends.  After a chain
   // kernel: tile by tile (the next tile's images are being prefetched meanwhile).
@@ -1567,8 +1572,8 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           const float* ts = a.stash + (size_t)tile * lo.tile_stash;
           const WOp op = ops[o];
           const float* srcA = ts + lo.slot_off[op.slotA];
-          const float* srcB = ts + lo.slot_off[op.slotB] + (op.chunk > 0 ? (size_t)op.chunk * (128 * 128) : 0);
-          const int FBm = op.chunk >= 0 ? 128 : lo.slot_w[op.slotB];  // width of the B image in memory
+          const float* srcB = ts + lo.slot_off[op.slotB] + (LNG && op.chunk > 0 ? (size_t)op.chunk * (128 * 128) : 0);
+          const int FBm = LNG && op.chunk >= 0 ? 128 : lo.slot_w[op.slotB];  // width of the B image in memory
           const uint32_t bytesA = WG_ROWS * H * 4, bytesB = (uint32_t)(WG_ROWS * FBm * 4);
           if (a.ready != nullptr) wait_tile_ready(a.ready + tile, max(slot_epilogue(op.slotA, nck), slot_epilogue(op.slotB, nck)));
           if (a.trace != nullptr && tile == 0) a.trace[180 + role * 16 + 1 + o] = global_ns();
@@ -1585,7 +1590,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             if (tn < a.n_tiles) {
               const float* tsn = a.stash + (size_t)tn * lo.tile_stash;
               l2_prefetch(tsn + lo.slot_off[ops[on].slotA], CH_M * H * 4);
-              if (ops[on].chunk >= 0) l2_prefetch(tsn + lo.slot_off[ops[on].slotB] + (size_t)ops[on].chunk * (128 * 128), CH_M * 128 * 4);
+              if (LNG && ops[on].chunk >= 0) l2_prefetch(tsn + lo.slot_off[ops[on].slotB] + (size_t)ops[on].chunk * (128 * 128), CH_M * 128 * 4);
               else l2_prefetch(tsn + lo.slot_off[ops[on].slotB], (uint32_t)(CH_M * lo.slot_w[ops[on].slotB] * 4));
             }
           }
@@ -1619,7 +1624,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
         const uint32_t idesc = umma_idesc_tf32(128, op.FB, UMMA_A_MN | UMMA_B_MN);
         const uint32_t idesc_b1 = umma_idesc_tf32(128, 16, UMMA_A_MN | UMMA_B_MN);
         // MN-major images: LBO = feature-atom stride (512 bytes), SBO = 4-row-atom stride (width * 16 bytes)
-        const uint32_t FBm = op.chunk >= 0 ? 128u : (uint32_t)lo.slot_w[op.slotB];
+        const uint32_t FBm = LNG && op.chunk >= 0 ? 128u : (uint32_t)lo.slot_w[op.slotB];
         const uint64_t a_bits = umma_desc(0u, 512u, H * 16u, 1u), b_bits = umma_desc(0u, 512u, FBm * 16u, 1u);
         const uint64_t ones_a_desc = umma_desc(smem_u32(ones_a), 512u, 2048u, 1u);
         const uint64_t ones_b_desc = umma_desc(smem_u32(ones_b), 512u, 512u, 1u);
@@ -1678,10 +1683,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     const int ln = q * 32 + lane;  // tensor-memory lane = feature index of the A side
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     // long trajectories: one slab per CTA, the first unit writes it, the others add to it
-    const bool add_to = a.nc > 0 && unit != my_index;
-    float* slab = a.slabs + (size_t)(a.unit_begin[role] + (a.nc > 0 ? my_index : unit)) * a.slab_stride;
+    const bool add_to = LNG && unit != my_index;
+    float* slab = a.slabs + (size_t)(a.unit_begin[role] + (LNG ? my_index : unit)) * a.slab_stride;
     float* stg = wo_stage + warp * (32 * 20);   // this warp's staging tile of the write-out
-    const int f0 = ops[o].chunk > 0 ? ops[o].chunk * 128 : 0;   // first feature of the op's chunk of the trajectory
+    const int f0 = LNG && ops[o].chunk > 0 ? ops[o].chunk * 128 : 0;   // first feature of the op's chunk of the trajectory
     auto put = [&](float* dst, float val) { *dst = add_to ? *dst + val : val; };
     const int L = lo.L, I = lo.I;
     {
@@ -1808,7 +1813,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     for (int it = 0; it < nt * n_ops; ++it) {
       {
         const int o = op_major ? it / nt : it % n_ops;
-        const int nB4 = WG_ROWS * (ops[o].chunk >= 0 ? 128 : lo.slot_w[ops[o].slotB]) / 4;  // float4 of the B part
+        const int nB4 = WG_ROWS * (LNG && ops[o].chunk >= 0 ? 128 : lo.slot_w[ops[o].slotB]) / 4;  // float4 of the B part
         for (int c = 0; c < chunks; ++c, rs.advance()) {
           // the two halves of the work warps take alternate stages (the ring depth is even, so a stage always has the
           // same half): two stages are being split at any time, which hides the shared-memory round trip, the proxy
@@ -1842,7 +1847,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             write_op(pending, unit);
             // long trajectories: op o + 1 writes the columns this op has just been read from, and its first stage is
             // handed over by HALF of the work warps - all of them must be done reading first
-            if (a.nc > 0) asm volatile("bar.sync 1, %0;" ::"n"(WG_WORK_THREADS) : "memory");
+            if (LNG) asm volatile("bar.sync 1, %0;" ::"n"(WG_WORK_THREADS) : "memory");
           }
           pending = o;
         }
@@ -1873,9 +1878,10 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   if (warp == WG_PRODUCER_WARP) tmem_dealloc(tmem, 512);
 }
 
+template <bool LNG>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_constant__ WgradKArgs k) {
   extern __shared__ unsigned char smem_dyn[];
-  wgrad_body(k.lo, k.w, (int)blockIdx.x, smem_dyn);
+  wgrad_body<LNG>(k.lo, k.w, (int)blockIdx.x, smem_dyn);
 }
 
 // Small batches leave most SMs without a chain tile: one launch runs the chain CTAs (the first chain_grid blocks)
@@ -1889,10 +1895,11 @@ struct FusedTcArgs {
   int chain_grid;
 };
 static_assert(CH_THREADS == WG_THREADS, "the fused launch runs both bodies with one block size");
+template <bool LNG>
 __global__ void __launch_bounds__(CH_THREADS, 1) train_tc_fused_kernel(const __grid_constant__ FusedTcArgs k) {
   extern __shared__ unsigned char smem_dyn[];
-  if ((int)blockIdx.x < k.chain_grid) chain_body(k.lo, k.c, (int)blockIdx.x, k.chain_grid, smem_dyn);
-  else wgrad_body(k.lo, k.w, (int)blockIdx.x - k.chain_grid, smem_dyn);
+  if ((int)blockIdx.x < k.chain_grid) chain_body<LNG>(k.lo, k.c, (int)blockIdx.x, k.chain_grid, smem_dyn);
+  else wgrad_body<LNG>(k.lo, k.w, (int)blockIdx.x - k.chain_grid, smem_dyn);
 }
 
 // =========================================================================================
@@ -2221,9 +2228,10 @@ cudaError_t launch_chain(const Layout& lo, const TrainTcPlan& plan, const TrainI
   ChainKArgs k;
   k.lo = lo;
   k.c = chain_args(lo, plan, io, stash, loss_part);
-  const cudaError_t e = set_smem_limit(chain_kernel, plan.chain_smem);
+  auto kernel = k.c.n_chunks > 0 ? chain_kernel<true> : chain_kernel<false>;
+  const cudaError_t e = set_smem_limit(kernel, plan.chain_smem);
   if (e != cudaSuccess) return e;
-  chain_kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(k);
+  kernel<<<plan.chain_grid, CH_THREADS, plan.chain_smem, stream>>>(k);
   return cudaGetLastError();
 }
 
@@ -2231,9 +2239,10 @@ cudaError_t launch_wgrad(const Layout& lo, const TrainTcPlan& plan, const float*
   WgradKArgs k;
   k.lo = lo;
   k.w = wgrad_args(lo, plan, stash, slabs);
-  const cudaError_t e = set_smem_limit(wgrad_kernel, WG_SMEM_BYTES);
+  auto kernel = k.w.nc > 0 ? wgrad_kernel<true> : wgrad_kernel<false>;
+  const cudaError_t e = set_smem_limit(kernel, WG_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  wgrad_kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(k);
+  kernel<<<plan.wgrad_grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(k);
   return cudaGetLastError();
 }
 
@@ -2248,9 +2257,10 @@ cudaError_t launch_chain_wgrad_fused(const Layout& lo, const TrainTcPlan& plan, 
   k.w.ready = flags;
   k.chain_grid = plan.chain_grid;
   const size_t smem = plan.chain_smem > WG_SMEM_BYTES ? plan.chain_smem : WG_SMEM_BYTES;
-  cudaError_t e = set_smem_limit(train_tc_fused_kernel, smem);
+  auto kernel = k.c.n_chunks > 0 ? train_tc_fused_kernel<true> : train_tc_fused_kernel<false>;
+  cudaError_t e = set_smem_limit(kernel, smem);
   if (e != cudaSuccess) return e;
-  train_tc_fused_kernel<<<plan.chain_grid + plan.wgrad_grid, CH_THREADS, smem, stream>>>(k);
+  kernel<<<plan.chain_grid + plan.wgrad_grid, CH_THREADS, smem, stream>>>(k);
   return cudaGetLastError();
 }
 
