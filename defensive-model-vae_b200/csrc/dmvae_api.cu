@@ -634,6 +634,73 @@ int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, i
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "trajectories_per_cell");
 }
 
+// ---------------------------------------------------------------------------- batched MPC path tracker
+static int check_mpc(const DmvaeMpcCfg* c, const char* what) {
+  if (!c) return fail(DMVAE_ERR_ARG, "%s: null cfg", what);
+  if (c->n_way < 4 || c->n_way > DMVAE_MPC_MAX_WAY)
+    return fail(DMVAE_ERR_SHAPE, "%s: n_way %d outside 4..%d (the quadratic / linear interpolants of fewer than four waypoints are not built)",
+                what, c->n_way, DMVAE_MPC_MAX_WAY);
+  if (c->horizon < 1 || c->horizon > DMVAE_MPC_MAX_HORIZON || c->blocks < 1 || c->blocks > c->horizon)
+    return fail(DMVAE_ERR_ARG, "%s: need 1 <= blocks <= horizon <= %d (the reference raises when the control horizon exceeds the prediction horizon)",
+                what, DMVAE_MPC_MAX_HORIZON);
+  if (!(c->wheelbase > 0.0) || !(c->max_steer > 0.0) || !(c->max_steer < 1.5) || !(c->max_accel > 0.0) || !(c->q_theta >= 0.0) ||
+      !(c->q_v >= 0.0) || !(c->r_accel > 0.0) || !(c->r_steer > 0.0) || c->max_iter < 1 || !(c->tol >= 0.0))
+    return fail(DMVAE_ERR_ARG, "%s: wheelbase, limits and increment weights must be positive (max_steer < 1.5 rad), max_iter >= 1", what);
+  return DMVAE_OK;
+}
+
+int64_t dmvae_mpc_workspace_bytes(const DmvaeMpcCfg* cfg, int64_t n) {
+  if (check_mpc(cfg, "mpc_workspace_bytes") != DMVAE_OK || n < 1) return -1;
+  return (int64_t)dmvae::mpc_workspace_bytes(*cfg, n);
+}
+
+int dmvae_mpc_prepare(const DmvaeMpcCfg* cfg, const void* waypoints, const double* initial_state, int64_t n, void* workspace,
+                      double* state, int32_t* status, double* profile, void* stream) {
+  int rc = check_mpc(cfg, "mpc_prepare");
+  if (rc != DMVAE_OK) return rc;
+  if (!waypoints || !initial_state || !workspace || !state || !status || n < 1)
+    return fail(DMVAE_ERR_ARG, "mpc_prepare: null pointer or n < 1");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_MPC_PREPARE, st,
+                             dmvae::launch_mpc_prepare(*cfg, waypoints, initial_state, static_cast<double*>(workspace), n, state, status, profile, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "mpc_prepare");
+}
+
+int dmvae_mpc_track(const DmvaeMpcCfg* cfg, void* workspace, int64_t n, double dt, const int32_t* n_steps, const int32_t* status,
+                    int32_t step_begin, int32_t step_count, double* state, double* states_out, double* controls_out,
+                    int64_t out_rows, int32_t* iters_out, void* stream) {
+  int rc = check_mpc(cfg, "mpc_track");
+  if (rc != DMVAE_OK) return rc;
+  if (!workspace || !n_steps || !state || n < 1 || !(dt > 0.0) || step_begin < 0 || step_count < 0)
+    return fail(DMVAE_ERR_ARG, "mpc_track: null pointer, n < 1, dt <= 0 or a negative step range");
+  if ((states_out || controls_out) && out_rows < (int64_t)step_begin + step_count + 1)
+    return fail(DMVAE_ERR_ARG, "mpc_track: out_rows %lld cannot hold the states up to step %d", (long long)out_rows, step_begin + step_count);
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_MPC_TRACK, st,
+                             dmvae::launch_mpc_track(*cfg, static_cast<double*>(workspace), n, dt, n_steps, status, step_begin, step_count, state,
+                                                     states_out, controls_out, out_rows, iters_out, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "mpc_track");
+}
+
+int dmvae_mpc_windows(const DmvaeMpcCfg* cfg, const void* workspace, int64_t n, double dt, const double* times, int32_t n_times,
+                      const int32_t* status, double* out, void* stream) {
+  int rc = check_mpc(cfg, "mpc_windows");
+  if (rc != DMVAE_OK) return rc;
+  if (!workspace || !times || !out || n < 1 || n_times < 1 || n_times > 64 || !(dt > 0.0))
+    return fail(DMVAE_ERR_ARG, "mpc_windows: null pointer, n < 1, dt <= 0 or n_times outside 1..64");
+  if ((rc = require_device(nullptr)) != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* times_dev = nullptr;
+  cudaError_t e = cudaMallocAsync(&times_dev, sizeof(double) * n_times, st);
+  if (e != cudaSuccess) return cuda_fail(e, "mpc_windows");
+  e = cudaMemcpyAsync(times_dev, times, sizeof(double) * n_times, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = dmvae::launch_mpc_windows(*cfg, static_cast<const double*>(workspace), n, dt, times_dev, n_times, status, out, st);
+  cudaFreeAsync(times_dev, st);
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "mpc_windows");
+}
+
 int dmvae_tf32_probe(int64_t iters, int mode, float* sink, double* flop_out, void* stream) {
   if (!sink || iters < 1 || mode < 0 || mode > 3) return fail(DMVAE_ERR_ARG, "tf32_probe: null sink, iters < 1 or mode not 0..3");
   int sms = 0;

@@ -116,4 +116,17 @@ cudaError_t launch_histogram(const float* values, long long m, const double* edg
 cudaError_t launch_cells(const float* traj, long long n, int T, int layout, double x0, double xstep, int nx, double y0, double ystep,
                          int ny, unsigned long long* counts, int sm_count, cudaStream_t stream);
 
+
+// batched MPC path tracker (dmvae_mpc.cu)
+using MpcCfg = DmvaeMpcCfg;
+constexpr int MPC_MAX_WAY = DMVAE_MPC_MAX_WAY, MPC_MAX_HOR = DMVAE_MPC_MAX_HORIZON, MPC_MAX_BLK = DMVAE_MPC_MAX_HORIZON;
+size_t mpc_workspace_bytes(const MpcCfg& c, long long n);
+cudaError_t launch_mpc_prepare(const MpcCfg& c, const void* way, const double* init, double* ws, long long n, double* state, int* status,
+                               double* profile, cudaStream_t stream);
+cudaError_t launch_mpc_track(const MpcCfg& c, double* ws, long long n, double dt, const int* n_steps, const int* status, int step_begin,
+                             int step_count, double* state, double* states_out, double* controls_out, long long out_rows, int* iters_out,
+                             cudaStream_t stream);
+cudaError_t launch_mpc_windows(const MpcCfg& c, const double* ws, long long n, double dt, const double* times, int n_times, const int* status,
+                               double* out, cudaStream_t stream);
+
 }  // namespace dmvae

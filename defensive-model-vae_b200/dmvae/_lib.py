@@ -40,6 +40,13 @@ class DmvaeDpPeers(ctypes.Structure):
                 ("inbox", c_void_p * MAX_PEERS)]
 
 
+class DmvaeMpcCfg(ctypes.Structure):
+    _fields_ = [("n_way", c_int32), ("way_f32", c_int32), ("horizon", c_int32), ("blocks", c_int32), ("max_iter", c_int32),
+                ("reserved", c_int32), ("wheelbase", ctypes.c_double), ("max_steer", ctypes.c_double), ("max_accel", ctypes.c_double),
+                ("q_theta", ctypes.c_double), ("q_v", ctypes.c_double), ("r_accel", ctypes.c_double), ("r_steer", ctypes.c_double),
+                ("tol", ctypes.c_double)]
+
+
 # name -> (restype, argtypes); mirrors include/dmvae.h one to one
 _P = c_void_p
 _CFG = POINTER(DmvaeCfg)
@@ -84,6 +91,10 @@ SIGNATURES = {
     "dmvae_histogram": (c_int, [_P, c_int64, POINTER(ctypes.c_double), c_int32, _P, _P]),
     "dmvae_trajectories_per_cell": (c_int, [_P, c_int64, c_int32, c_int32, ctypes.c_double, ctypes.c_double, c_int32,
                                             ctypes.c_double, ctypes.c_double, c_int32, _P, _P]),
+    "dmvae_mpc_workspace_bytes": (c_int64, [POINTER(DmvaeMpcCfg), c_int64]),
+    "dmvae_mpc_prepare": (c_int, [POINTER(DmvaeMpcCfg), _P, _P, c_int64, _P, _P, _P, _P, _P]),
+    "dmvae_mpc_track": (c_int, [POINTER(DmvaeMpcCfg), _P, c_int64, ctypes.c_double, _P, _P, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P]),
+    "dmvae_mpc_windows": (c_int, [POINTER(DmvaeMpcCfg), _P, c_int64, ctypes.c_double, POINTER(ctypes.c_double), c_int32, _P, _P, _P]),
     "dmvae_kernel_name": (c_char_p, [c_int]),
     "dmvae_launch_count": (c_int64, [c_int]),
     "dmvae_profile_begin": (c_int, []),
@@ -91,8 +102,8 @@ SIGNATURES = {
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
     "dmvae_tf32_probe": (c_int, [c_int64, c_int, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 19
-ABI_VERSION = 2
+KERNEL_COUNT = 21
+ABI_VERSION = 3
 # include/dmvae_debug.h (development aids, outside the drop-in boundary)
 DEBUG_SIGNATURES = {
     "dmvae_debug_decode_trace": (c_int, [_P]),

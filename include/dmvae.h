@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DMVAE_ABI_VERSION 2
+#define DMVAE_ABI_VERSION 3
 
 #define DMVAE_OK 0
 #define DMVAE_ERR_SHAPE (-1)   /* configuration outside the supported envelope */
@@ -294,6 +294,55 @@ int dmvae_histogram(const float* values, int64_t m, const double* edges, int32_t
 int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, int32_t layout, double x0, double x_step,
                                 int32_t nx_edges, double y0, double y_step, int32_t ny_edges, uint64_t* counts, void* stream);
 
+/* ---- batched MPC path tracker ------------------------------------------------
+ * The reference turns each generated waypoint set into a driven trajectory with PathTracker (MPC/MPC_Tracking.py:418-523,
+ * called from Distribution.py:91-105): PathInterpolator (:89-277) -> per time step a reference window (:464-478), one
+ * solve of the controller's optimal control problem (MPCController.solve_mpc, :311-415) and one Euler step of the bicycle
+ * model with the first control (:484-486).  These entry points do the same for n independent trajectories, one GPU thread
+ * each, in float64.  The optimisation problem is the reference's (weights Q = diag(20, 5) on heading and speed over
+ * horizon + 1 rows, R = diag(1, 50) on the control increments over `blocks` rows, the last row held for the rest of the
+ * horizon, the effective bounds of :390-398 with the inequality constraint of :376-387); it is solved to convergence by a
+ * control-limited DDP / Newton method where the reference runs SLSQP to ftol = 1e-6, so results agree with the
+ * reference's to its early-stopping noise, not bit for bit (statistical parity).
+ *
+ *   waypoints      (n, n_way, 3) [x, y, t], float32 (way_f32 = 1: the VAE's output; the knot arithmetic that the reference
+ *                  does in float32 is done in float32) or float64; 4 <= n_way <= 64 (cubic interpolants only)
+ *   initial_state  (n, 5) float64 [x, y, theta, vx, vy] (Distribution.py:80)
+ *   workspace      dmvae_mpc_workspace_bytes(cfg, n) bytes: interpolants, previous control and previous solution of every
+ *                  trajectory; written by dmvae_mpc_prepare, carried from one dmvae_mpc_track call to the next
+ *   state          (n, 4) float64 [x, y, theta, v]: written by prepare (PathTracker.__init__, :435-441), advanced by track
+ *   status         (n) int32, written by prepare: 0 ok, 1 waypoint times do not increase strictly (the reference raises
+ *                  ValueError, :118-119); such trajectories are skipped by track
+ *   profile        optional (n, 5) float64 [start_theta, end_vx, end_vy, end_theta, t_end] (:194-221), or NULL
+ * dmvae_mpc_track runs steps [step_begin, step_begin + step_count) of every trajectory j that has them (s < n_steps[j],
+ * n_steps = int(total_time / dt) per trajectory, :505).  states_out (n, out_rows, 4) float64 or NULL: row s + 1 = state
+ * after step s, row 0 = the initial state (written when step_begin = 0); controls_out (n, out_rows - 1, 2) or NULL: the
+ * applied (a, delta) of step s; rows of steps a trajectory does not have are left untouched.  iters_out (n) int32 or NULL:
+ * solver iterations summed over the trajectory's steps.
+ * dmvae_mpc_windows: the reference windows [theta_ref, v_ref] that step() would build at the given current times (host
+ * array of n_times doubles): out (n, n_times, horizon + 1, 2) float64. */
+#define DMVAE_MPC_MAX_WAY 64
+#define DMVAE_MPC_MAX_HORIZON 40
+typedef struct DmvaeMpcCfg {
+  int32_t n_way;
+  int32_t way_f32;
+  int32_t horizon;   /* prediction_horizon (Distribution.py:98: 30), <= DMVAE_MPC_MAX_HORIZON */
+  int32_t blocks;    /* control_horizon (:99: 20), <= horizon */
+  int32_t max_iter;  /* solver iterations per controller call at most (50) */
+  int32_t reserved;
+  double wheelbase, max_steer, max_accel;     /* 2.8, 0.5, 7.0 (MPC_Tracking.py:26) */
+  double q_theta, q_v, r_accel, r_steer;      /* 20, 5, 1, 50 (:304-306) */
+  double tol;                                 /* stop when no control changed by more than this (1e-11) */
+} DmvaeMpcCfg;
+int64_t dmvae_mpc_workspace_bytes(const DmvaeMpcCfg* cfg, int64_t n);
+int dmvae_mpc_prepare(const DmvaeMpcCfg* cfg, const void* waypoints, const double* initial_state, int64_t n, void* workspace,
+                      double* state, int32_t* status, double* profile, void* stream);
+int dmvae_mpc_track(const DmvaeMpcCfg* cfg, void* workspace, int64_t n, double dt, const int32_t* n_steps, const int32_t* status,
+                    int32_t step_begin, int32_t step_count, double* state, double* states_out, double* controls_out,
+                    int64_t out_rows, int32_t* iters_out, void* stream);
+int dmvae_mpc_windows(const DmvaeMpcCfg* cfg, const void* workspace, int64_t n, double dt, const double* times, int32_t n_times,
+                      const int32_t* status, double* out, void* stream);
+
 /* ---- instrumentation -------------------------------------------------------
  * Nothing in the reference corresponds to these: they let bench.py report what the
  * library launched and how long the dominant kernel ran inside the timed region.
@@ -301,8 +350,9 @@ int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, i
  * (backward), 5 reduce, 6 reduce+Adam, 7 Adam, 8 loss, 9 loss backward, 10 FFMA probe,
  * 11 decode (tensor cores), 12 train chain (tensor cores), 13 weight gradients (tensor
  * cores), 14 partial-slab reduction (+ Adam), 15 chain + weight gradients in one launch
- * (small batches), 16 waypoint speeds, 17 histogram, 18 trajectories per grid cell. */
-#define DMVAE_KERNEL_COUNT 19
+ * (small batches), 16 waypoint speeds, 17 histogram, 18 trajectories per grid cell, 19 MPC tracker
+ * set-up, 20 MPC tracker steps. */
+#define DMVAE_KERNEL_COUNT 21
 const char* dmvae_kernel_name(int kernel);
 /* Kernels launched by this process since the library was loaded (kernel < 0: all). */
 int64_t dmvae_launch_count(int kernel);

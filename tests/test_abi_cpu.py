@@ -57,6 +57,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.DmvaeLossWeights) == 16
     assert ctypes.sizeof(_lib.DmvaeAdam) == 40
     assert _lib.MAX_PEERS == 8 and ctypes.sizeof(_lib.DmvaeDpPeers) == 16 + 8 * 8
+    assert ctypes.sizeof(_lib.DmvaeMpcCfg) == 6 * 4 + 8 * 8
     text = open(HEADER).read()
     assert "#define DMVAE_MAX_PEERS 8" in text
     assert f"#define DMVAE_KERNEL_COUNT {_lib.KERNEL_COUNT}" in text
@@ -64,7 +65,7 @@ def test_struct_layouts_match_the_header():
 
 def test_host_side_queries(lib):
     from dmvae import _lib
-    assert lib.dmvae_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.dmvae_abi_version() == _lib.ABI_VERSION == 3
     assert f"#define DMVAE_ABI_VERSION {_lib.ABI_VERSION}" in open(HEADER).read()
     cfg = _lib.cfg(10, 8)
     assert lib.dmvae_param_count(ctypes.byref(cfg)) == 128942          # T = 10, L = 8
@@ -75,7 +76,13 @@ def test_host_side_queries(lib):
     assert lib.dmvae_grad_count(ctypes.byref(cfg400)) == 465589        # T = 400, L = 64 (+ 5 loss terms)
     bad = _lib.cfg(401, 8)
     assert lib.dmvae_param_count(ctypes.byref(bad)) < 0 and b"seq_len" in lib.dmvae_last_error()
+    mpc = _lib.DmvaeMpcCfg(n_way=10, way_f32=1, horizon=30, blocks=20, max_iter=50, reserved=0, wheelbase=2.8, max_steer=0.5,
+                           max_accel=7.0, q_theta=20.0, q_v=5.0, r_accel=1.0, r_steer=50.0, tol=1e-11)
+    assert lib.dmvae_mpc_workspace_bytes(ctypes.byref(mpc), 1000) == (10 + 8 * 9 + 8 + 40) * 1000 * 8
+    mpc.n_way = 3
+    assert lib.dmvae_mpc_workspace_bytes(ctypes.byref(mpc), 1000) < 0 and b"n_way" in lib.dmvae_last_error()
     names = {lib.dmvae_kernel_name(i).decode() for i in range(_lib.KERNEL_COUNT)}
+    assert {"mpc_prepare_kernel", "mpc_track_kernel"} <= names
     assert {"decode_tc_kernel", "chain_kernel", "wgrad_kernel", "reduce_tc_kernel", "train_tc_fused_kernel"} <= names
 
 
