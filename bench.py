@@ -255,6 +255,35 @@ def cpu_decode_rate(rows: int, budget_s: float):
     return n * rows / dt, n, dt
 
 
+def tracker_jobs(n: int, seed: int, device):
+    """Inputs of the MPC tracker from the synthetic trajectories: [x, y, t] float32 waypoints as
+    Distribution.py:74-78 hands them over and initial states [x, y, theta, vx, vy] along the first segment."""
+    traj = synth_trajectories(n, seed, device)                  # (n, T, 3) [t, x, y], t0 = 0
+    way = traj[:, :, [1, 2, 0]].contiguous()
+    d = (way[:, 1] - way[:, 0]).double()
+    vx, vy = d[:, 0] / d[:, 2], d[:, 1] / d[:, 2]
+    init = torch.stack([way[:, 0, 0].double(), way[:, 0, 1].double(), torch.atan2(vy, vx), vx, vy], 1).contiguous()
+    return way, init
+
+
+def cpu_tracker_rate(budget_s: float) -> dict:
+    """Controller calls per second of the reference's tracker on ONE host core (SLSQP is sequential; the port
+    oracle/mpc_oracle.py of MPC/MPC_Tracking.py, scenario time step 0.02 s, horizons 30 / 20 as Distribution.py:94-101)."""
+    from oracle import mpc_oracle as MO
+    way, init = tracker_jobs(4, 11, "cpu")
+    w, s0 = way[0].numpy(), init[0].numpy()
+    MO.track(w, s0, 0.02, max_steps=1)
+    steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        MO.track(w, s0, 0.02, max_steps=4)
+        steps += 4
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": "controller calls/s", "cores": 1, "kind": "port",
+            "sample": f"{steps} controller calls (SLSQP, 40 variables, finite-difference gradients) of one synthetic trajectory in {dt:.1f} s; "
+                      "the reference's own class needs ~1 s per call on the same problem (NumPy objective)"}
+
+
 def reference_config_legs(gpu: bool) -> dict:
     """BASELINE configs[0] (the reference's own configuration): training on the shipped
     StaticBlindTown05 set with batch 38 = the whole set (Training_VAE.py:275-280: one step per epoch), and the
@@ -388,6 +417,7 @@ def run_reference(args):
         "decode": {"metric": "decoded_trajectories_per_sec", "value": dec_rate, "unit": "trajectories/s",
                    "sample": f"{dec_n} x {1 << 18} rows, shared start, host randn + cond-encoder + decoder + offset add"},
         "reference_config": reference_config_legs(gpu=False),
+        "mpc_tracker": cpu_tracker_rate(8.0),
         "gpu_launches": 0,
     }
     emit(line)
@@ -869,6 +899,55 @@ def run_cuda(args):
         metrics["check"] = {"histogram_total": int(h_m.sum()), "expected": R * T, "cells_max": int(H_m.max()),
                             "cells_equal_wrapper": bool((cells_d.cpu().numpy().reshape(H_m.shape) == H_m).all())}
 
+    # batched MPC tracker: controller calls per second over synthetic waypoint sets, one thread per
+    # trajectory; e2e = host waypoints in, full state histories out (the tracked_trajectory_* content)
+    mpc = None
+    if rank == 0:
+        from dmvae.tracker import BatchTracker
+        n_mpc, k_mpc = args.mpc_rows, 40
+        way_m, init_m = tracker_jobs(n_mpc, 11, dev)
+        bt = BatchTracker(way_m, init_m, 0.02, 30, 20)
+        bt.advance(10)                                          # the first calls start without a previous solution
+        torch.cuda.synchronize()
+        it0 = bt.iters.clone()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        bt.advance(k_mpc)
+        m1.record()
+        torch.cuda.synchronize()
+        mpc_ms = m0.elapsed_time(m1)
+        running = int((bt.n_steps >= bt.step).sum())
+        # end to end through dmvae.tracker: pinned host inputs -> device, set-up, the first k_mpc steps with their state
+        # and control histories, histories back to pinned host memory
+        way_h, init_h = way_m.cpu().pin_memory(), init_m.cpu().pin_memory()
+        st_h = torch.empty(n_mpc, k_mpc + 1, 4, dtype=torch.float64).pin_memory()
+        ct_h = torch.empty(n_mpc, k_mpc, 2, dtype=torch.float64).pin_memory()
+        st_d = torch.empty(n_mpc, k_mpc + 1, 4, dtype=torch.float64, device=dev)
+        ct_d = torch.empty(n_mpc, k_mpc, 2, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bt2 = BatchTracker(way_h.to(dev, non_blocking=True), init_h.to(dev, non_blocking=True), 0.02, 30, 20)
+        bt2.advance(k_mpc, st_d, ct_d)
+        st_h.copy_(st_d, non_blocking=True)
+        ct_h.copy_(ct_d, non_blocking=True)
+        torch.cuda.synchronize()
+        mpc_e2e_dt = time.perf_counter() - t0
+        mpc = {"metric": "mpc_controller_calls_per_sec", "value": n_mpc * k_mpc / (mpc_ms * 1e-3), "unit": "controller calls/s",
+               "config": {"workload": f"{n_mpc} synthetic waypoint sets (10 waypoints, float32), time step 0.02 s, prediction / control "
+                                      "horizon 30 / 20 (Distribution.py:94-101), steps 10..50 of every trajectory",
+                          "steps_per_trajectory_mean": float(bt.n_steps.mean()), "trajectories_still_running": running},
+               "ms": mpc_ms, "solver_iterations_per_call": float((bt.iters - it0).double().mean()) / k_mpc,
+               "complete_trajectories_per_sec_implied": n_mpc * k_mpc / (mpc_ms * 1e-3) / float(bt.n_steps.mean()),
+               "e2e": {"value": n_mpc * k_mpc / mpc_e2e_dt, "unit": "controller calls/s",
+                       "h2d_bytes_per_step": int(way_h.numel() * 4 + init_h.numel() * 8),
+                       "d2h_bytes_per_step": int(st_h.numel() * 8 + ct_h.numel() * 8),
+                       "note": "set-up (interpolants, heading scan) + the first 40 steps from a cold solver + histories to the host"},
+               "roofline": {"bound": "fp64 issue / local-memory latency (one thread per trajectory; see profiles/*_prof_mpc_track_kernel.txt)",
+                            "traffic": (traffic_from_profile("mpc_track_kernel") or {}).get("bytes_per_launch"),
+                            "traffic_source": (traffic_from_profile("mpc_track_kernel") or {}).get("source")},
+               "cpu_baseline": None if args.no_cpu else cpu_tracker_rate(8.0)}
+        del bt, bt2, st_d, ct_d
+
     # the reference shuffles its data set every epoch (Training_VAE.py:327): the same resident step with the rows of
     # every epoch picked through the keyed permutation (dmvae_train_step_resident, shuffle = 1)
     shuffled = None
@@ -972,6 +1051,7 @@ def run_cuda(args):
         "large_batch": big,
         "shuffled_resident_set": shuffled,
         "validation_metrics": metrics,
+        "mpc_tracker": mpc,
         "reference_config": ref_cfg,
         "cpu_baseline": cpu_obj,
         "e2e": e2e_obj,
@@ -1021,6 +1101,7 @@ def main():
                     help="rows per GPU of the resident set: 2^23 = 1.0 GB per GPU, 64 M rows on eight GPUs (BASELINE configs[3])")
     ap.add_argument("--big-batch", type=int, default=1 << 16, help="rows per GPU of the large-batch throughput leg")
     ap.add_argument("--decode-rows", type=int, default=1 << 20)
+    ap.add_argument("--mpc-rows", type=int, default=1 << 16, help="trajectories of the MPC tracker leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="host-driven steps instead of the CUDA-graph step")
     ap.add_argument("--exchange", choices=("auto", "peer", "nccl"), default="auto",

@@ -21,7 +21,8 @@
 // make it a small optimal control problem in the state (theta, v, previous a, previous delta): it is solved by
 // differential dynamic programming with exact second derivatives (a Newton method on the control sequence, one 2 x 2
 // box-constrained quadratic problem per stage, Tassa et al.'s control-limited DDP), warm-started from the previous
-// step's shifted solution and iterated to a control change below 1e-11.  SLSQP in the reference stops at ftol = 1e-6,
+// step's shifted solution and iterated until no control moves by more than cfg.tol (1e-6; the method converges
+// quadratically, so the controls are then good to ~1e-11).  SLSQP in the reference stops at ftol = 1e-6,
 // i.e. within ~1e-3 of the same minimiser in the controls; the parity tests hold this kernel to 1e-7 against that
 // minimiser (oracle/mpc_oracle.py solve_exact) and to the early-stopping noise against the reference's own runs.
 //
@@ -223,18 +224,23 @@ __device__ void mpc_window(const MpcCfg& c, const Knots& K, const double t_end, 
   for (int i = 0; i <= c.horizon; ++i) {
     const double t = current_time + i * dt;
     double vx, vy;
+    // heading of (vx, vy).  Where the end velocity stands in, get_reference_heading recomputes atan2(evy, evx) and wraps
+    // it: that is end_theta, which the wrap leaves alone
+    double heading = end_theta;
     if (t <= t_end) {   // get_reference (:235-243)
       K.eval(t, cur, vx, vy);
-      if (fabs(atan2(vy, vx) - start_theta) > 90 * M_PI / 180) {
+      heading = atan2(vy, vx);
+      if (fabs(heading - start_theta) > 90 * M_PI / 180) {
         vx = evx;
         vy = evy;
+        heading = end_theta;
       }
     } else {            // beyond the last waypoint: straight on with the end velocity (:246-250)
       vx = evx;
       vy = evy;
     }
     const double v = sqrt(vx * vx + vy * vy);
-    if (v >= 0.1) held = t > t_end ? wrap_heading(end_theta) : wrap_heading(atan2(vy, vx));   // :264-273
+    if (v >= 0.1) held = wrap_heading(heading);   // :264-273 (beyond the end: the wrapped end heading, wrapped again)
     thr[i] = held;
     vr[i] = v;
   }
@@ -273,59 +279,64 @@ __device__ void box_qp2(double q00, double q01, double q11, double g0, double g1
   fr[1] = d[1] > lo[1] && d[1] < hi[1];
 }
 
+// Per-thread working set of the solver (local memory).  It is what bounds the kernel: the first build kept 7 KB per
+// thread (rollouts, gains and controls for the largest horizons in float64), 460 MB for the resident threads of a B200,
+// and streamed it through HBM (110 GB of DRAM traffic for 20 steps of 65 536 trajectories).  Now: sized by the
+// instantiation (HOR, BLK), no stored rollouts (the forward sweep recomputes the nominal states with the arithmetic
+// that produced them, the backward sweep walks them back), feedback gains in float32 (they shape the Newton step, not
+// the fixed point it converges to): 2.4 KB per thread at (30, 20).
+template <int HOR, int BLK>
 struct MpcLocal {
-  double th[MPC_MAX_HOR + 1], v[MPC_MAX_HOR + 1], thr[MPC_MAX_HOR + 1], vr[MPC_MAX_HOR + 1];
-  double a[MPC_MAX_BLK], dl[MPC_MAX_BLK], an[MPC_MAX_BLK], dn[MPC_MAX_BLK], tau[MPC_MAX_BLK];
-  double kff[MPC_MAX_BLK][2], kfb[MPC_MAX_BLK][2][4];
+  double thr[HOR + 1], vr[HOR + 1];
+  double a[BLK], dl[BLK], tau[BLK], an[BLK], dn[BLK], taun[BLK];
+  double kff[BLK][2];
+  float kfb[BLK][2][4];
 };
 
 __device__ __forceinline__ double mpc_alim(const MpcCfg& c, int k) { return 2 * k < c.blocks ? c.max_accel : c.max_steer; }
 
-// rollout of controls (ua, ud) from (th0, v0): fills th, v (and tau = tan of the steering of every control row) and
-// returns the cost of solve_mpc's objective (:344-371)
-__device__ double mpc_rollout(const MpcCfg& c, const double cdt, const double dt, const double th0, const double v0, const double* ua,
-                              const double* ud, const double* thr, const double* vr, const bool have_last, const double la,
-                              const double ld, double* th, double* v, double* tau) {
-  const int N = c.horizon, M = c.blocks;
-  th[0] = th0;
-  v[0] = v0;
-  double cost = 0.0;
-  for (int i = 0; i < N; ++i) {
-    const int k = i < M ? i : M - 1;
-    if (i < M) tau[i] = tan(ud[i]);
-    const double eth = th[i] - thr[i], ev = v[i] - vr[i];
-    cost += c.q_theta * eth * eth + c.q_v * ev * ev;
-    th[i + 1] = th[i] + cdt * v[i] * tau[k];
-    v[i + 1] = v[i] + dt * ua[k];
-  }
-  {
-    const double eth = th[N] - thr[N], ev = v[N] - vr[N];
-    cost += c.q_theta * eth * eth + c.q_v * ev * ev;
-  }
-  for (int k = 0; k < M; ++k) {
-    if (k == 0 && !have_last) continue;
-    const double da = ua[k] - (k == 0 ? la : ua[k - 1]), dd = ud[k] - (k == 0 ? ld : ud[k - 1]);
-    cost += c.r_accel * da * da + c.r_steer * dd * dd;
-  }
-  return cost;
-}
-
-// One controller call: minimise the objective over the control rows S.a / S.dl (in: warm start, out: solution).
-// Returns the iterations used.
+// One controller call: minimise the objective of solve_mpc (:329-373) over the control rows S.a / S.dl (in: warm
+// start, out: solution).  Returns the iterations used.
+template <int HOR, int BLK>
 __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, const double v0, const bool have_last, const double la,
-                         const double ld, MpcLocal& S) {
+                         const double ld, MpcLocal<HOR, BLK>& S) {
   const int N = c.horizon, M = c.blocks;
   const double cdt = dt / c.wheelbase;
   const double qth2 = 2.0 * c.q_theta, qv2 = 2.0 * c.q_v;
-  double cost = mpc_rollout(c, cdt, dt, th0, v0, S.a, S.dl, S.thr, S.vr, have_last, la, ld, S.th, S.v, S.tau);
+  // nominal rollout of the warm start: its cost and its last state (thN, vN); tau = tan of every row's steering
+  double cost = 0.0, thN = th0, vN = v0;
+  for (int i = 0; i < N; ++i) {
+    const int k = i < M ? i : M - 1;
+    if (i < M) {
+      S.tau[i] = tan(S.dl[i]);
+      if (i > 0 || have_last) {
+        const double da = S.a[i] - (i == 0 ? la : S.a[i - 1]), dd = S.dl[i] - (i == 0 ? ld : S.dl[i - 1]);
+        cost += c.r_accel * da * da + c.r_steer * dd * dd;
+      }
+    }
+    const double eth = thN - S.thr[i], ev = vN - S.vr[i];
+    cost += c.q_theta * eth * eth + c.q_v * ev * ev;
+    thN = thN + cdt * vN * S.tau[k];
+    vN = vN + dt * S.a[k];
+  }
+  {
+    const double eth = thN - S.thr[N], ev = vN - S.vr[N];
+    cost += c.q_theta * eth * eth + c.q_v * ev * ev;
+  }
   int it = 0;
   for (; it < c.max_iter; ++it) {
-    // ---- backward sweep: gradient g and Hessian H of the cost-to-go in x = (theta, v, previous a, previous delta)
-    double g[4] = {qth2 * (S.th[N] - S.thr[N]), qv2 * (S.v[N] - S.vr[N]), 0.0, 0.0};
+    // ---- backward sweep: gradient g and Hessian H of the cost-to-go in x = (theta, v, previous a, previous delta).
+    // The nominal states are walked back from the last one (v_i = v_{i+1} - dt a, theta_i = theta_{i+1} - cdt v_i tau):
+    // equal to the forward values to rounding, which moves the fixed point by ~1e-15.
+    double th = thN, v = vN;
+    double maxd = 0.0;   // largest feed-forward change of this sweep
+    double g[4] = {qth2 * (th - S.thr[N]), qv2 * (v - S.vr[N]), 0.0, 0.0};
     double H[4][4] = {{qth2, 0, 0, 0}, {0, qv2, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
     for (int i = N - 1; i >= M; --i) {   // rows beyond the control horizon: the last control row is held (:337-339)
       const double tau = S.tau[M - 1], sig = 1.0 + tau * tau;
-      const double a01 = cdt * tau, a03 = cdt * S.v[i] * sig, a12 = dt;
+      v = v - dt * S.a[M - 1];
+      th = th - cdt * v * tau;
+      const double a01 = cdt * tau, a03 = cdt * v * sig, a12 = dt;
       // A = [[1, a01, 0, a03], [0, 1, a12, 0], [0, 0, 1, 0], [0, 0, 0, 1]];  HA = H A,  H' = A^T HA
       double HA[4][4];
 #pragma unroll
@@ -346,12 +357,12 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
       // second derivatives of theta' = theta + cdt v tan(q): d2/dv dq = cdt sig, d2/dq2 = 2 cdt v sig tau
       H[1][3] += g0 * cdt * sig;
       H[3][1] += g0 * cdt * sig;
-      H[3][3] += g0 * 2.0 * cdt * S.v[i] * sig * tau;
+      H[3][3] += g0 * 2.0 * cdt * v * sig * tau;
       H[0][0] += qth2;
       H[1][1] += qv2;
       const double n0 = g[0], n1 = a01 * g[0] + g[1], n2 = a12 * g[1] + g[2], n3 = a03 * g[0] + g[3];
-      g[0] = n0 + qth2 * (S.th[i] - S.thr[i]);
-      g[1] = n1 + qv2 * (S.v[i] - S.vr[i]);
+      g[0] = n0 + qth2 * (th - S.thr[i]);
+      g[1] = n1 + qv2 * (v - S.vr[i]);
       g[2] = n2;
       g[3] = n3;
     }
@@ -360,8 +371,10 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
       const double ra2 = 2.0 * w * c.r_accel, rs2 = 2.0 * w * c.r_steer;
       const double pa = i == 0 ? la : S.a[i - 1], pd = i == 0 ? ld : S.dl[i - 1];
       const double tau = S.tau[i], sig = 1.0 + tau * tau;
-      const double ct = cdt * tau, b = cdt * S.v[i] * sig;
-      const double lth = qth2 * (S.th[i] - S.thr[i]), lv = qv2 * (S.v[i] - S.vr[i]);
+      v = v - dt * S.a[i];
+      th = th - cdt * v * tau;
+      const double ct = cdt * tau, b = cdt * v * sig;
+      const double lth = qth2 * (th - S.thr[i]), lv = qv2 * (v - S.vr[i]);
       const double lua = ra2 * (S.a[i] - pa), lud = rs2 * (S.dl[i] - pd);
       // columns of d x' / d u: a -> (0, dt, 1, 0), delta -> (b, 0, 0, 1)
       double Ha[4], Hd[4];
@@ -373,7 +386,7 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
       const double Qu[2] = {lua + dt * g[1] + g[2], lud + b * g[0] + g[3]};
       double q00 = ra2 + dt * Ha[1] + Ha[2];
       const double q01 = b * Ha[0] + Ha[3];
-      double q11 = rs2 + b * Hd[0] + Hd[3] + g[0] * 2.0 * cdt * S.v[i] * sig * tau;
+      double q11 = rs2 + b * Hd[0] + Hd[3] + g[0] * 2.0 * cdt * v * sig * tau;
       double Qux[2][4] = {{Ha[0], ct * Ha[0] + Ha[1], -ra2, 0.0}, {Hd[0], ct * Hd[0] + Hd[1] + g[0] * cdt * sig, 0.0, -rs2}};
       const double Qx[4] = {lth + g[0], lv + ct * g[0] + g[1], -lua, -lud};
       double Qxx[4][4] = {{qth2 + H[0][0], ct * H[0][0] + H[0][1], 0, 0},
@@ -408,10 +421,14 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
       }
       S.kff[i][0] = d[0];
       S.kff[i][1] = d[1];
+      maxd = fmax(maxd, fmax(fabs(d[0]), fabs(d[1])));
+      // the gains are kept (and, for consistency, used below) in float32
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        S.kfb[i][0][q] = K[0][q];
-        S.kfb[i][1][q] = K[1][q];
+        S.kfb[i][0][q] = (float)K[0][q];
+        S.kfb[i][1][q] = (float)K[1][q];
+        K[0][q] = (double)S.kfb[i][0][q];
+        K[1][q] = (double)S.kfb[i][1][q];
       }
       // cost-to-go: g = Qx + K^T (Quu d + Qu) + Qux^T d,  H = Qxx + K^T Quu K + K^T Qux + Qux^T K
       const double t0 = q00 * d[0] + q01 * d[1] + Qu[0], t1 = q01 * d[0] + q11 * d[1] + Qu[1];
@@ -426,19 +443,31 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
                     Qux[1][r] * K[1][q];
       }
     }
-    // ---- forward sweep with a halving step
-    double alpha = 1.0, maxdu = 0.0;
+    // a Newton step three orders below the tolerance: nothing left to do (and no step of that size could be told
+    // from rounding in the cost; without this test a converged lane would walk through every halving below while the
+    // rest of its warp waits - measured: 6 of 32 lanes active in the forward sweep)
+    if (maxd < 1e-3 * c.tol) {
+      ++it;
+      break;
+    }
+    // ---- forward sweep with a halving step: the new controls, their rollout and its cost; the nominal rollout is
+    // recomputed alongside (the same arithmetic that produced it: the same values)
+    double alpha = 1.0, maxdu = 0.0, cost_n = 0.0, thn = th0, vn = v0;
     bool accepted = false;
-    for (int ls = 0; ls < 12; ++ls, alpha *= 0.5) {
+    for (int ls = 0; ls < 8; ++ls, alpha *= 0.5) {
       double dth = 0.0, dv = 0.0, dpa = 0.0, dpd = 0.0;   // deviation of the new rollout from the nominal one
-      double thn = th0, vn = v0;
-      double cost_n = 0.0;
+      double thm = th0, vm = v0;                          // nominal
+      thn = th0;
+      vn = v0;
+      cost_n = 0.0;
       maxdu = 0.0;
       for (int i = 0; i < N; ++i) {
         const int k = i < M ? i : M - 1;
         if (i < M) {
-          double ua = S.a[i] + alpha * S.kff[i][0] + S.kfb[i][0][0] * dth + S.kfb[i][0][1] * dv + S.kfb[i][0][2] * dpa + S.kfb[i][0][3] * dpd;
-          double ud = S.dl[i] + alpha * S.kff[i][1] + S.kfb[i][1][0] * dth + S.kfb[i][1][1] * dv + S.kfb[i][1][2] * dpa + S.kfb[i][1][3] * dpd;
+          double ua = S.a[i] + alpha * S.kff[i][0] + (double)S.kfb[i][0][0] * dth + (double)S.kfb[i][0][1] * dv +
+                      (double)S.kfb[i][0][2] * dpa + (double)S.kfb[i][0][3] * dpd;
+          double ud = S.dl[i] + alpha * S.kff[i][1] + (double)S.kfb[i][1][0] * dth + (double)S.kfb[i][1][1] * dv +
+                      (double)S.kfb[i][1][2] * dpa + (double)S.kfb[i][1][3] * dpd;
           const double alim = mpc_alim(c, i);
           ua = fmin(fmax(ua, -alim), alim);
           ud = fmin(fmax(ud, -c.max_steer), c.max_steer);
@@ -448,25 +477,25 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
           }
           S.an[i] = ua;
           S.dn[i] = ud;
-          dpa = ua - S.a[i];
+          S.taun[i] = tan(ud);
+          dpa = ua - S.a[i];     // the next stage sees this row as its previous control
           dpd = ud - S.dl[i];
           maxdu = fmax(maxdu, fmax(fabs(dpa), fabs(dpd)));
         }
         const double eth = thn - S.thr[i], ev = vn - S.vr[i];
         cost_n += c.q_theta * eth * eth + c.q_v * ev * ev;
-        const double tn = tan(S.dn[k]);
-        const double th_next = thn + cdt * vn * tn;
+        thn = thn + cdt * vn * S.taun[k];
         vn = vn + dt * S.an[k];
-        thn = th_next;
-        dth = thn - S.th[i + 1];
-        dv = vn - S.v[i + 1];
-        // (dpa, dpd) already hold the change of the control row that the next stage sees as its previous control
+        thm = thm + cdt * vm * S.tau[k];
+        vm = vm + dt * S.a[k];
+        dth = thn - thm;
+        dv = vn - vm;
       }
       {
         const double eth = thn - S.thr[N], ev = vn - S.vr[N];
         cost_n += c.q_theta * eth * eth + c.q_v * ev * ev;
       }
-      if (cost_n <= cost) {
+      if (cost_n <= cost + 1e-13 * fabs(cost)) {   // the two costs are summed in different orders: rounding is no rejection
         accepted = true;
         break;
       }
@@ -475,8 +504,11 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
     for (int k = 0; k < M; ++k) {
       S.a[k] = S.an[k];
       S.dl[k] = S.dn[k];
+      S.tau[k] = S.taun[k];
     }
-    cost = mpc_rollout(c, cdt, dt, th0, v0, S.a, S.dl, S.thr, S.vr, have_last, la, ld, S.th, S.v, S.tau);
+    thN = thn;
+    vN = vn;
+    cost = cost_n;
     if (maxdu < c.tol) {
       ++it;
       break;
@@ -485,6 +517,7 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
   return it;
 }
 
+template <int HOR, int BLK>
 __global__ void __launch_bounds__(64) mpc_track_kernel(const MpcCfg c, double* __restrict__ ws, const long long n, const double dt,
                                                        const int* __restrict__ n_steps, const int* __restrict__ status, const int step_begin,
                                                        const int step_count, double* __restrict__ state, double* __restrict__ states_out,
@@ -495,7 +528,7 @@ __global__ void __launch_bounds__(64) mpc_track_kernel(const MpcCfg c, double* _
   if (status != nullptr && status[j] != 0) return;
   const int last_step = min(step_begin + step_count, n_steps[j]);
   if (step_begin >= last_step && !(step_begin == 0 && states_out != nullptr)) return;
-  MpcLocal S;
+  MpcLocal<HOR, BLK> S;
   const Knots K{ws, n, j, c.n_way, mpc_f_cx(c), mpc_f_cy(c)};
   double* scal = ws + (size_t)mpc_f_scal(c) * n + j;
   const double t_end = scal[(size_t)MS_T_END * n], start_theta = scal[(size_t)MS_START_THETA * n];
@@ -583,8 +616,10 @@ cudaError_t launch_mpc_prepare(const MpcCfg& c, const void* way, const double* i
 cudaError_t launch_mpc_track(const MpcCfg& c, double* ws, long long n, double dt, const int* n_steps, const int* status, int step_begin,
                              int step_count, double* state, double* states_out, double* controls_out, long long out_rows, int* iters_out,
                              cudaStream_t stream) {
-  mpc_track_kernel<<<(unsigned int)((n + 63) / 64), 64, 0, stream>>>(c, ws, n, dt, n_steps, status, step_begin, step_count, state, states_out,
-                                                                   controls_out, out_rows, iters_out);
+  // the reference's own horizons (Distribution.py:98-99) have their own, smaller instantiation
+  auto kernel = c.horizon <= 30 && c.blocks <= 20 ? mpc_track_kernel<30, 20> : mpc_track_kernel<MPC_MAX_HOR, MPC_MAX_BLK>;
+  kernel<<<(unsigned int)((n + 63) / 64), 64, 0, stream>>>(c, ws, n, dt, n_steps, status, step_begin, step_count, state, states_out, controls_out,
+                                                          out_rows, iters_out);
   return cudaGetLastError();
 }
 

@@ -33,7 +33,7 @@ from ._lib import DmvaeMpcCfg, check, ptr, stream_ptr
 
 
 def mpc_config(n_way: int, way_f32: bool, prediction_horizon: int = 10, control_horizon: int = 5, wheelbase: float = 2.8,
-               max_steer: float = 0.5, max_accel: float = 7.0, max_iter: int = 50, tol: float = 1e-11) -> DmvaeMpcCfg:
+               max_steer: float = 0.5, max_accel: float = 7.0, max_iter: int = 50, tol: float = 1e-6) -> DmvaeMpcCfg:
     """``VehicleModel`` limits (``MPC_Tracking.py:26``) and ``MPCController`` weights (``:304-306``); the horizons default
     to the class defaults (``:283-284``) - ``Distribution.py:98-99`` passes 30 and 20."""
     if control_horizon > prediction_horizon:
@@ -70,7 +70,7 @@ class BatchTracker:
     solution of every trajectory live in the workspace between the calls."""
 
     def __init__(self, waypoints, initial_states, dt: float, prediction_horizon: int = 10, control_horizon: int = 5,
-                 wheelbase: float = 2.8, total_time=None, max_iter: int = 50, tol: float = 1e-11):
+                 wheelbase: float = 2.8, total_time=None, max_iter: int = 50, tol: float = 1e-6):
         if not torch.cuda.is_available():
             raise _lib.DmvaeError("no CUDA device is visible and dmvae has no CPU path")
         dev = torch.device("cuda", torch.cuda.current_device())

@@ -332,7 +332,7 @@ typedef struct DmvaeMpcCfg {
   int32_t reserved;
   double wheelbase, max_steer, max_accel;     /* 2.8, 0.5, 7.0 (MPC_Tracking.py:26) */
   double q_theta, q_v, r_accel, r_steer;      /* 20, 5, 1, 50 (:304-306) */
-  double tol;                                 /* stop when no control changed by more than this (1e-11) */
+  double tol;                                 /* stop when no control changed by more than this in the last iteration (1e-6; quadratic convergence: the controls are then good to ~1e-11) */
 } DmvaeMpcCfg;
 int64_t dmvae_mpc_workspace_bytes(const DmvaeMpcCfg* cfg, int64_t n);
 int dmvae_mpc_prepare(const DmvaeMpcCfg* cfg, const void* waypoints, const double* initial_state, int64_t n, void* workspace,

@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE.  Run once in the build container (where ``/root/reference`` is mounted); takes a few minutes
 (the reference needs about a second per controller call):
 
-    python -m oracle.make_golden_mpc
+    python -m oracle.make_golden_mpc            # tests/golden/mpc_track.npz
+    python -m oracle.make_golden_mpc --full     # tests/golden/mpc_track_full.npz (two complete runs, ~10 minutes)
 
 tests/golden/mpc_track.npz, per case ``c``: the waypoints ``[x, y, t]`` (float32 as the VAE hands them over, one
 case float64), the initial state ``[x, y, theta, vx, vy]``, the time step, what ``PathInterpolator`` derived
@@ -147,5 +148,27 @@ def main():
     print("wrote", os.path.join(GOLD, "mpc_track.npz"))
 
 
+def main_full():
+    """tests/golden/mpc_track_full.npz: two COMPLETE reference runs (run_simulation(waypoints[-1, -1]) as
+    Distribution.py:104-105 calls it, 401 and 222 controller calls), for the end-to-end gap between the reference's
+    early-stopped SLSQP and a converged solver over a whole trajectory.  About ten minutes."""
+    M = load_tracker_module()
+    gold = {}
+    for c in cases()[:2]:
+        name, way, dt = c["name"], c["way"], c["dt"]
+        init = np.array(c["init"], dtype=np.float64)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = M.PathTracker(way.copy(), init.copy(), 2.8, 30, 20, dt)
+            times, states, controls = tr.run_simulation(total_time=way[-1, -1])
+        gold[f"{name}_way"], gold[f"{name}_init"], gold[f"{name}_dt"] = way, init, np.float64(dt)
+        gold[f"{name}_times"], gold[f"{name}_states"], gold[f"{name}_controls"] = times, states, controls
+        print(name, states.shape, states[-1], flush=True)
+    np.savez_compressed(os.path.join(GOLD, "mpc_track_full.npz"), **gold)
+    print("wrote", os.path.join(GOLD, "mpc_track_full.npz"))
+
+
 if __name__ == "__main__":
-    main()
+    if "--full" in sys.argv:
+        main_full()
+    else:
+        main()

@@ -78,6 +78,22 @@ def test_closed_loop_against_reference_runs_and_converged_oracle(gold, name):
         assert np.abs(ct - gold[f"{name}_seg{s}_controls"]).max() < 5e-3
 
 
+@pytest.mark.parametrize("name", ["sce1_brake", "sce2_west"])
+def test_complete_runs_stay_with_the_reference(golden_dir, name):
+    """Two COMPLETE reference runs (run_simulation(waypoints[-1, -1]) as Distribution.py:104-105 calls it: 401 and 222
+    controller calls, tests/golden/mpc_track_full.npz).  The feedback loop keeps the early-stopping noise from adding up:
+    measured (converged CPU solver vs the reference) <= 9e-5 m, 1e-5 rad, 6e-5 m/s, 1e-3 m/s^2 over the whole run."""
+    from dmvae.tracker import track_batch
+    full = np.load(os.path.join(golden_dir, "mpc_track_full.npz"))
+    way, init, dt = full[f"{name}_way"], full[f"{name}_init"], float(full[f"{name}_dt"])
+    res = track_batch(way[None], init[None], dt)
+    times, st, ct = res.trajectory(0)
+    assert st.shape == full[f"{name}_states"].shape and ct.shape == full[f"{name}_controls"].shape
+    np.testing.assert_array_equal(times, full[f"{name}_times"])
+    assert np.abs(st - full[f"{name}_states"]).max() < 5e-4
+    assert np.abs(ct - full[f"{name}_controls"]).max() < 5e-3
+
+
 def test_reference_class_surface(gold):
     """dmvae.tracker.PathTracker used the way Distribution.process_single_trajectory uses the reference's class."""
     from dmvae.tracker import PathTracker
