@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v)
 SRCS=(dmvae_api.cu dmvae_pack.cu dmvae_decode.cu dmvae_decode_tc.cu)
-for extra in dmvae_train.cu dmvae_train_tc.cu dmvae_adam.cu dmvae_loss.cu dmvae_prof.cu dmvae_probe_tc.cu dmvae_metrics.cu dmvae_mpc.cu; do [ -f "$extra" ] && SRCS+=("$extra"); done
+for extra in dmvae_train.cu dmvae_train_tc.cu dmvae_adam.cu dmvae_loss.cu dmvae_prof.cu dmvae_probe_tc.cu dmvae_metrics.cu dmvae_mpc.cu dmvae_dense.cu; do [ -f "$extra" ] && SRCS+=("$extra"); done
 mkdir -p build
 objs=()
 for s in "${SRCS[@]}"; do

@@ -634,6 +634,18 @@ int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, i
   return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "trajectories_per_cell");
 }
 
+// ---------------------------------------------------------------------------- sub-modules called on their own
+int dmvae_dense(const float* weight, const float* bias, const float* x, float* y, int64_t B, int32_t in_features, int32_t out_features,
+                int32_t relu, void* stream) {
+  if (!weight || !x || !y || B < 1 || in_features < 1 || out_features < 1 || in_features > 4096 || out_features > 4096)
+    return fail(DMVAE_ERR_ARG, "dense: null pointer, B < 1 or a feature count outside 1..4096");
+  const int rc = require_device(nullptr);
+  if (rc != DMVAE_OK) return rc;
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const cudaError_t e = PROF(dmvae::K_DENSE, st, dmvae::launch_dense(weight, bias, x, y, B, in_features, out_features, relu != 0, st));
+  return e == cudaSuccess ? DMVAE_OK : cuda_fail(e, "dense");
+}
+
 // ---------------------------------------------------------------------------- batched MPC path tracker
 static int check_mpc(const DmvaeMpcCfg* c, const char* what) {
   if (!c) return fail(DMVAE_ERR_ARG, "%s: null cfg", what);

@@ -117,6 +117,10 @@ cudaError_t launch_cells(const float* traj, long long n, int T, int layout, doub
                          int ny, unsigned long long* counts, int sm_count, cudaStream_t stream);
 
 
+// one Linear (+ ReLU) layer from the state_dict arena (dmvae_dense.cu): W (out, in) row-major, x (B, in), y (B, out)
+cudaError_t launch_dense(const float* W, const float* b, const float* x, float* y, long long B, int in, int out, int relu,
+                         cudaStream_t stream);
+
 // batched MPC path tracker (dmvae_mpc.cu)
 using MpcCfg = DmvaeMpcCfg;
 constexpr int MPC_MAX_WAY = DMVAE_MPC_MAX_WAY, MPC_MAX_HOR = DMVAE_MPC_MAX_HORIZON, MPC_MAX_BLK = DMVAE_MPC_MAX_HORIZON;

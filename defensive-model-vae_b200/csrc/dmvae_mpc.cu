@@ -518,7 +518,7 @@ __device__ int mpc_solve(const MpcCfg& c, const double dt, const double th0, con
 }
 
 template <int HOR, int BLK>
-__global__ void __launch_bounds__(64) mpc_track_kernel(const MpcCfg c, double* __restrict__ ws, const long long n, const double dt,
+__global__ void __launch_bounds__(64, 8) mpc_track_kernel(const MpcCfg c, double* __restrict__ ws, const long long n, const double dt,
                                                        const int* __restrict__ n_steps, const int* __restrict__ status, const int step_begin,
                                                        const int step_count, double* __restrict__ state, double* __restrict__ states_out,
                                                        double* __restrict__ controls_out, const long long out_rows,

@@ -32,7 +32,7 @@ const char* kernel_name(int id) {
                                        "loss_kernel", "loss_grad_kernel", "ffma_probe_kernel", "decode_tc_kernel",
                                        "chain_kernel", "wgrad_kernel", "reduce_tc_kernel", "train_tc_fused_kernel",
                                        "speeds_kernel", "histogram_kernel", "cells_kernel", "mpc_prepare_kernel",
-                                       "mpc_track_kernel"};
+                                       "mpc_track_kernel", "dense_kernel"};
   return id >= 0 && id < K_COUNT ? names[id] : "?";
 }
 

@@ -6,7 +6,7 @@ namespace dmvae {
 
 enum KernelId {
   K_PACK = 0, K_DECODE, K_TRAIN_FUSED, K_TRAIN_FWD, K_TRAIN_BWD, K_REDUCE, K_REDUCE_ADAM, K_ADAM, K_LOSS, K_LOSS_GRAD,
-  K_FFMA_PROBE, K_DECODE_TC, K_CHAIN, K_WGRAD, K_REDUCE_TC, K_TRAIN_TC_FUSED, K_SPEEDS, K_HISTOGRAM, K_CELLS, K_MPC_PREPARE, K_MPC_TRACK, K_COUNT
+  K_FFMA_PROBE, K_DECODE_TC, K_CHAIN, K_WGRAD, K_REDUCE_TC, K_TRAIN_TC_FUSED, K_SPEEDS, K_HISTOGRAM, K_CELLS, K_MPC_PREPARE, K_MPC_TRACK, K_DENSE, K_COUNT
 };
 
 // Brackets one kernel launch: counts it and, when profiling is on, records an event pair

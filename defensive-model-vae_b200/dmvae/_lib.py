@@ -91,6 +91,7 @@ SIGNATURES = {
     "dmvae_histogram": (c_int, [_P, c_int64, POINTER(ctypes.c_double), c_int32, _P, _P]),
     "dmvae_trajectories_per_cell": (c_int, [_P, c_int64, c_int32, c_int32, ctypes.c_double, ctypes.c_double, c_int32,
                                             ctypes.c_double, ctypes.c_double, c_int32, _P, _P]),
+    "dmvae_dense": (c_int, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32, _P]),
     "dmvae_mpc_workspace_bytes": (c_int64, [POINTER(DmvaeMpcCfg), c_int64]),
     "dmvae_mpc_prepare": (c_int, [POINTER(DmvaeMpcCfg), _P, _P, c_int64, _P, _P, _P, _P, _P]),
     "dmvae_mpc_track": (c_int, [POINTER(DmvaeMpcCfg), _P, c_int64, ctypes.c_double, _P, _P, c_int32, c_int32, _P, _P, _P, c_int64, _P, _P]),
@@ -102,7 +103,7 @@ SIGNATURES = {
     "dmvae_ffma_probe": (c_int, [c_int64, _P, POINTER(ctypes.c_double), _P]),
     "dmvae_tf32_probe": (c_int, [c_int64, c_int, _P, POINTER(ctypes.c_double), _P]),
 }
-KERNEL_COUNT = 21
+KERNEL_COUNT = 22
 ABI_VERSION = 3
 # include/dmvae_debug.h (development aids, outside the drop-in boundary)
 DEBUG_SIGNATURES = {

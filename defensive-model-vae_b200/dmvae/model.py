@@ -46,30 +46,63 @@ def _envelope(seq_len: int, dim: int, latent_dim: int, hidden_dim: int) -> None:
         raise NotImplementedError(f"seq_len={seq_len}: supported range is 2..{MAX_SEQ}")
 
 
+def _dense(owner, linear: nn.Linear, x: torch.Tensor, relu: bool) -> torch.Tensor:
+    """One ``nn.Linear`` (+ ReLU) of a sub-module called on its own: ``dmvae_dense`` on the layer's views of the
+    parameter arena.  Forward only."""
+    owner.flat_parameters()                      # parameters on the device, contiguous views of the arena
+    w, b = linear.weight.data, (linear.bias.data if linear.bias is not None else None)
+    xx = x.detach().to(device=w.device, dtype=torch.float32).contiguous()
+    if xx.dim() != 2 or xx.shape[1] != linear.in_features:
+        raise ValueError(f"expected (B, {linear.in_features}), got {tuple(x.shape)}")
+    y = torch.empty(xx.shape[0], linear.out_features, dtype=torch.float32, device=w.device)
+    if xx.shape[0] > 0:
+        with torch.cuda.device(w.device):
+            check(_lib.lib().dmvae_dense(ptr(w), ptr(b), ptr(xx), ptr(y), xx.shape[0], linear.in_features, linear.out_features,
+                                         int(relu), stream_ptr()), "dmvae_dense")
+    return y
+
+
 class _KernelBackedSequential(nn.Sequential):
-    """Keeps the reference's sub-module tree (for state_dict keys and init order)
-    but refuses to run torch ops: the owning model's fused entry points are the
-    only compute path."""
+    """Keeps the reference's sub-module tree (state_dict keys, initialisation order).  Called on its own
+    (``model.encoder(x)``, ``model.decoder(zc)`` - Training_VAE.py:141-151, :158-167; no caller in the reference does)
+    it walks its layers through ``dmvae_dense``, one launch per Linear with the ReLU that follows it fused; forward
+    only, no autograd graph.  ``model.encode`` / ``decode`` / ``forward`` never come here: they run in the fused kernels."""
 
-    _what = "this sub-module"
-
-    def forward(self, *args, **kwargs):  # pragma: no cover - guard
-        raise NotImplementedError(
-            f"{self._what} is evaluated inside the fused kernels; call model.encode()/decode()/forward() "
-            "(dmvae has no op-by-op PyTorch path)")
+    def forward(self, x):  # type: ignore[override]
+        owner = self._owner()
+        src = x.device
+        layers = list(self.children())
+        h = x
+        i = 0
+        while i < len(layers):
+            layer = layers[i]
+            if isinstance(layer, nn.Flatten):
+                h = h.reshape(h.shape[0], -1)
+            elif isinstance(layer, nn.Unflatten):
+                h = h.reshape(h.shape[0], *layer.unflattened_size)
+            elif isinstance(layer, nn.Linear):
+                relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
+                h = _dense(owner, layer, h, relu)
+                i += int(relu)
+            elif isinstance(layer, nn.ReLU):
+                h = torch.clamp_min(h, 0.0)
+            i += 1
+        return h.to(src)
 
 
 class _ConditionEncoder(_KernelBackedSequential):
     """``model.condition_encoder(c)`` is called directly by the reference's
-    generate helpers (Tools.py:55, :898), so this one is callable."""
+    generate helpers (Tools.py:55, :898): the fused condition-encoder kernel."""
 
     def forward(self, condition: torch.Tensor) -> torch.Tensor:  # type: ignore[override]
         return self._owner()._cond_encode(condition)
 
 
 class _KernelBackedLinear(nn.Linear):
-    def forward(self, *args, **kwargs):  # pragma: no cover - guard
-        raise NotImplementedError("fc_mu / fc_logvar are evaluated inside the fused kernels; call model.encode()")
+    """``model.fc_mu(h)`` / ``model.fc_logvar(h)`` on their own (Training_VAE.py:154-155): ``dmvae_dense``."""
+
+    def forward(self, x):  # type: ignore[override]
+        return _dense(self._owner(), self, x, False).to(x.device)
 
 
 class ConditionalTrajectoryVAE(nn.Module):
@@ -96,10 +129,10 @@ class ConditionalTrajectoryVAE(nn.Module):
             nn.Linear(latent_dim + hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim), nn.ReLU(),
             nn.Linear(hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, seq_len * dim),
             nn.Unflatten(1, (seq_len, dim)))
-        self.encoder._what, self.decoder._what = "model.encoder", "model.decoder"
         import weakref
         ref = weakref.ref(self)
-        object.__setattr__(self.condition_encoder, "_owner", ref)
+        for sub in (self.condition_encoder, self.encoder, self.fc_mu, self.fc_logvar, self.decoder):
+            object.__setattr__(sub, "_owner", ref)
 
         self._cfg = _lib.cfg(seq_len, latent_dim, dim, hidden_dim)
         self._arena: Optional[torch.Tensor] = None       # flat parameters, state_dict order

@@ -294,6 +294,15 @@ int dmvae_histogram(const float* values, int64_t m, const double* edges, int32_t
 int dmvae_trajectories_per_cell(const float* traj, int64_t n, int32_t seq_len, int32_t layout, double x0, double x_step,
                                 int32_t nx_edges, double y0, double y_step, int32_t ny_edges, uint64_t* counts, void* stream);
 
+/* ---- sub-modules called on their own -------------------------------------------
+ * The reference's sub-modules are plain nn.Sequential / nn.Linear objects (Training_VAE.py:141-167), so
+ * model.encoder(x), model.decoder(zc), model.fc_mu(h), model.fc_logvar(h) are callable.  No reference caller does that
+ * (encode / decode / forward run in the fused kernels); for completeness of the module surface one layer at a time:
+ * y (B, out) = act(x (B, in) * weight^T + bias), weight (out, in) row-major as nn.Linear stores it (a view into the
+ * parameter arena), relu != 0 applies max(., 0).  FP32 FFMA.  Forward only. */
+int dmvae_dense(const float* weight, const float* bias, const float* x, float* y, int64_t B, int32_t in_features,
+                int32_t out_features, int32_t relu, void* stream);
+
 /* ---- batched MPC path tracker ------------------------------------------------
  * The reference turns each generated waypoint set into a driven trajectory with PathTracker (MPC/MPC_Tracking.py:418-523,
  * called from Distribution.py:91-105): PathInterpolator (:89-277) -> per time step a reference window (:464-478), one
@@ -351,8 +360,8 @@ int dmvae_mpc_windows(const DmvaeMpcCfg* cfg, const void* workspace, int64_t n, 
  * 11 decode (tensor cores), 12 train chain (tensor cores), 13 weight gradients (tensor
  * cores), 14 partial-slab reduction (+ Adam), 15 chain + weight gradients in one launch
  * (small batches), 16 waypoint speeds, 17 histogram, 18 trajectories per grid cell, 19 MPC tracker
- * set-up, 20 MPC tracker steps. */
-#define DMVAE_KERNEL_COUNT 21
+ * set-up, 20 MPC tracker steps, 21 one Linear layer on its own. */
+#define DMVAE_KERNEL_COUNT 22
 const char* dmvae_kernel_name(int kernel);
 /* Kernels launched by this process since the library was loaded (kernel < 0: all). */
 int64_t dmvae_launch_count(int kernel);

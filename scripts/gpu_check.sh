@@ -12,13 +12,15 @@ python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; e
 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench_driver_flags.json 2> gpurun_out/${tag}_bench_driver_flags.err; echo "bench (driver flags) rc=$?"
 tail -c 1500 gpurun_out/${tag}_bench.json
 python scripts/trace_chain.py 4096 > gpurun_out/${tag}_fused_trace.txt 2>&1
-SMALL="python bench.py --steps 6 --warmup 3 --no-cpu --dataset-rows 131072 --big-batch 65536 --decode-rows 1048576"
+SMALL="python bench.py --steps 6 --warmup 3 --no-cpu --dataset-rows 131072 --big-batch 65536 --decode-rows 1048576 --mpc-rows 65536"
 $SMALL > gpurun_out/${tag}_small.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu1.log 2>&1
 echo "ncu list rc=$?"
-for k in train_tc_fused_kernel:5 chain_kernel:2 wgrad_kernel:2 decode_tc_kernel:4 reduce_tc_kernel:5 train_kernel:2; do
+for k in train_tc_fused_kernel:5 chain_kernel:2 wgrad_kernel:2 decode_tc_kernel:4 reduce_tc_kernel:5 train_kernel:2 mpc_track_kernel:1; do
   name=${k%%:*}; skip=${k##*:}
   ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -f -o gpurun_out/${tag}_prof_${name} $SMALL > gpurun_out/${tag}_ncu_${name}.log 2>&1
   echo "ncu full $name rc=$?"
 done
+timeout 900 python scripts/sweep.py --out gpurun_out/${tag}_sweep.jsonl > gpurun_out/${tag}_sweep.txt 2>&1; echo "sweep rc=$?"
+python scripts/quick_mpc_bench.py 1048576 20 > gpurun_out/${tag}_mpc_1m.txt 2>&1
 ls -la gpurun_out | tail -20

@@ -67,6 +67,37 @@ def test_condition_encoder_and_decode_submodule_api(golden_dir):
     assert rel_err(rel.numpy(), kat["sce1_rel"]) < TOL
 
 
+@pytest.mark.parametrize("T,L,B", [(10, 8, 33), (50, 24, 200), (400, 64, 5)])
+def test_submodules_called_on_their_own(T, L, B):
+    """model.encoder(x), model.fc_mu(h), model.fc_logvar(h), model.decoder(zc) as plain callables (the reference's
+    sub-modules are nn.Sequential / nn.Linear, Training_VAE.py:141-167), against torch's own Linear / ReLU on the same
+    weights; 2e-6 relative (fp32, another summation order)."""
+    p = O.init_params(T, L, seed=7)
+    m = model_from_params(p, T, L)
+    g = torch.Generator().manual_seed(T + B)
+    x = torch.randn(B, T, 3, generator=g)
+    F = torch.nn.functional
+    h = x.reshape(B, -1)
+    for i in (1, 3, 5, 7):
+        h = F.relu(F.linear(h, p[f"encoder.{i}.weight"], p[f"encoder.{i}.bias"]))
+    got_h = m.encoder(x)
+    assert got_h.shape == (B, 128) and got_h.device.type == "cpu"
+    assert rel_err(got_h.numpy(), h.numpy()) < 2e-6
+    hh = torch.cat([h, torch.randn(B, 128, generator=g)], 1)
+    for name in ("fc_mu", "fc_logvar"):
+        want = F.linear(hh, p[f"{name}.weight"], p[f"{name}.bias"])
+        got = getattr(m, name)(hh)
+        assert got.shape == (B, L) and rel_err(got.numpy(), want.numpy()) < 2e-6
+    zc = torch.randn(B, L + 128, generator=g)
+    d = zc
+    for i in (0, 2, 4):
+        d = F.relu(F.linear(d, p[f"decoder.{i}.weight"], p[f"decoder.{i}.bias"]))
+    d = F.linear(d, p["decoder.6.weight"], p["decoder.6.bias"]).reshape(B, T, 3)
+    got_d = m.decoder(zc.cuda())
+    assert got_d.shape == (B, T, 3) and got_d.is_cuda
+    assert rel_err(got_d.cpu().numpy(), d.numpy()) < 2e-6
+
+
 @pytest.mark.parametrize("T,L,B", [(10, 8, 1), (10, 8, 127), (10, 8, 128), (10, 8, 129), (10, 8, 5000),
                                    (12, 8, 300), (2, 1, 77), (21, 16, 513), (32, 32, 260), (42, 64, 1000),
                                    (10, 5, 333), (7, 3, 64),

@@ -95,8 +95,9 @@ def test_complete_runs_stay_with_the_reference(golden_dir, name):
 
 
 def test_reference_class_surface(gold):
-    """dmvae.tracker.PathTracker used the way Distribution.process_single_trajectory uses the reference's class."""
-    from dmvae.tracker import PathTracker
+    """The drop-in module (repo root MPC/MPC_Tracking.py) imported the way Distribution.py:9 imports the reference's, its
+    PathTracker used the way Distribution.process_single_trajectory (:91-105) uses it."""
+    from MPC.MPC_Tracking import PathTracker
     name = "sce2_west"
     way, init, dt = gold[f"{name}_way"], gold[f"{name}_init"].copy(), float(gold[f"{name}_dt"])
     tr = PathTracker(waypoints=way, initial_state=init, wheelbase=2.8, prediction_horizon=30, control_horizon=20, dt=dt)
