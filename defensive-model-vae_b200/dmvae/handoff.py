@@ -4,14 +4,14 @@ tracker of the reference's batch driver, with the VAE part done ONCE for all log
 Reference flow, per CSV (``Distribution.py:51-111`` called from ``:114-166``): start conditions from the log
 (``Tools.get_start_conditions_from_csv``) -> one generated trajectory (``Tools.load_model_and_generate_trajectory``,
 a checkpoint load + one B = 1 decode) -> columns reordered ``[t, x, y] -> [x, y, t]`` and ``t0 := 0``
-(``:77-78``) -> ``PathTracker`` (SLSQP MPC, out of scope here, stays on the CPU) -> ``np.save`` under
+(``:77-78``) -> ``PathTracker`` (SLSQP MPC; its batched GPU counterpart is ``dmvae/tracker.py``) -> ``np.save`` under
 ``results/GeneratedData/tracked_trajectory_{sce}_exp{n}_{k}.npy`` (``:157``).
 
 Here: the start conditions of all CSVs are read first, ONE batched decode with a per-row start point produces
 every waypoint set (``dmvae_decode``), and each result carries what the tracker call needs (initial state,
 scenario time step, output name) plus the check the tracker would fail on (``MPC/MPC_Tracking.py:117-119``
-raises unless the waypoint times increase strictly).  Nothing here runs the MPC or writes the
-``tracked_trajectory_*`` files: their format is the tracker's.
+raises unless the waypoint times increase strictly).  The tracking itself and the ``tracked_trajectory_*`` files are
+``dmvae.tracker.run_tracker_jobs(jobs)``.
 """
 from __future__ import annotations
 

@@ -165,6 +165,33 @@ def test_saturated_controls_follow_the_effective_bounds():
     assert np.abs(st - so).max() < 1e-7 and np.abs(ct - co).max() < 1e-6
 
 
+def test_tracker_jobs_are_tracked_and_saved_like_the_reference_driver(gold, tmp_path):
+    """run_tracker_jobs = the tracking half of Distribution.batch_process_trajectories (:114-166): every trackable job
+    tracked (one launch per time step value), its (S + 1, 4) states saved under the reference's file name, untrackable
+    jobs skipped; the three return values of the reference."""
+    from dmvae.handoff import TrackerJob
+    from dmvae.tracker import run_tracker_jobs
+    jobs = []
+    for k, name in enumerate(["sce1_brake", "sce2_west", "sce4_south"]):
+        way, dt = gold[f"{name}_way"], float(gold[f"{name}_dt"])
+        jobs.append(TrackerJob(csv_path=f"log_{k}.csv", save_name=f"tracked_trajectory_sce{k}_exp1_{k}.npy", waypoints=way,
+                               initial_state=gold[f"{name}_init"].copy(), time_step=dt, total_time=float(way[-1, -1]), trackable=True))
+    bad = gold["sce1_brake_way"].copy()
+    bad[5, 2] = bad[4, 2]
+    jobs.append(TrackerJob("log_bad.csv", "tracked_trajectory_bad.npy", bad, gold["sce1_brake_init"].copy(), 0.02, 1.0, False))
+    trajs, times, saved = run_tracker_jobs(jobs, str(tmp_path))
+    assert len(trajs) == len(times) == len(saved) == 3
+    assert sorted(os.path.basename(f) for f in saved) == sorted(j.save_name for j in jobs[:3])
+    full = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpc_track_full.npz"))
+    by_name = {os.path.basename(f): np.load(f) for f in saved}
+    for k, name in enumerate(["sce1_brake", "sce2_west"]):          # the two complete reference runs
+        got = by_name[f"tracked_trajectory_sce{k}_exp1_{k}.npy"]
+        assert got.shape == full[f"{name}_states"].shape and got.dtype == np.float64
+        assert np.abs(got - full[f"{name}_states"]).max() < 5e-4
+    assert by_name["tracked_trajectory_sce2_exp1_2.npy"].shape == (int(gold["sce4_south_steps_total"]) + 1, 4)
+    assert not os.path.exists(tmp_path / "tracked_trajectory_bad.npy")
+
+
 def test_argument_errors_are_loud():
     from dmvae import DmvaeError
     from dmvae.tracker import BatchTracker
