@@ -945,7 +945,7 @@ def run_cuda(args):
                "roofline": {"bound": "fp64 issue / local-memory latency (one thread per trajectory; see profiles/*_prof_mpc_track_kernel.txt)",
                             "traffic": (traffic_from_profile("mpc_track_kernel") or {}).get("bytes_per_launch"),
                             "traffic_source": (traffic_from_profile("mpc_track_kernel") or {}).get("source")},
-               "cpu_baseline": None if args.no_cpu else cpu_tracker_rate(8.0)}
+               "cpu_baseline": cpu_tracker_rate(8.0) if (world == 1 and not args.no_cpu) else None}
         del bt, bt2, st_d, ct_d
 
     # the reference shuffles its data set every epoch (Training_VAE.py:327): the same resident step with the rows of

@@ -255,6 +255,21 @@ def generate_shard(model, start_points, n: int, seed: int, rank: int, world: int
     return lo, hi, (outs[0] if len(outs) == 1 else torch.cat(outs, 0))
 
 
+def track_shard(waypoints, initial_states, dt: float, rank: int, world: int, **kw):
+    """The MPC tracker (``dmvae.tracker.track_batch``) on this rank's rows [lo, hi) of a global batch of waypoint sets:
+    trajectories are independent, so tracking shards like generation - contiguous row ranges, no collective, and every
+    row's result is what a single GPU computes for it.  Returns (lo, hi, TrackResult or None for an empty shard)."""
+    from .tracker import track_batch
+    n = int(waypoints.shape[0])
+    lo, hi = shard_range(n, rank, world)
+    if hi == lo:
+        return lo, hi, None
+    total = kw.pop("total_time", None)
+    if total is not None and np.ndim(total) > 0:
+        total = np.asarray(total)[lo:hi]
+    return lo, hi, track_batch(waypoints[lo:hi], initial_states[lo:hi], dt, total_time=total, **kw)
+
+
 def write_sharded_npy(path: str, rows: np.ndarray, lo: int, n: int, rank: int, world: int) -> None:
     """All ranks write their slab [lo, lo+len(rows)) of one ``(n, T, 3)`` float32 ``.npy``:
     rank 0 creates the pre-sized file, a barrier, then every rank writes through a memmap."""

@@ -151,6 +151,28 @@ def test_batch_rows_are_independent_and_chunks_compose(gold):
     assert np.abs(res.states[150, :7].cpu().numpy() - so).max() < 1e-7
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_tracking_shards_like_generation(gold, world):
+    """Rank r tracks rows [r n / G, (r + 1) n / G): the rows of every sharding are bit-identical to the single launch."""
+    from dmvae.parallel import track_shard
+    from dmvae.tracker import track_batch
+    rng = np.random.default_rng(world)
+    n, K = 37, 8
+    way = np.repeat(gold["sce4_south_way"][None], n, 0).copy()
+    way[:, 1:, :2] += rng.normal(0, 0.3, (n, 9, 2)).astype(np.float32)
+    init = np.repeat(gold["sce4_south_init"][None], n, 0)
+    whole = track_batch(way, init, 0.02, max_steps=K)
+    seen = 0
+    for r in range(world):
+        lo, hi, part = track_shard(way, init, 0.02, r, world, max_steps=K)
+        if part is None:
+            assert lo == hi
+            continue
+        assert torch.equal(part.states, whole.states[lo:hi]) and torch.equal(part.controls, whole.controls[lo:hi])
+        seen += hi - lo
+    assert seen == n
+
+
 def test_saturated_controls_follow_the_effective_bounds():
     """Speed far above the reference: the first rows brake hard, rows 10..19 are held at the -0.5 that the reference's
     bounds list gives them (MPC_Tracking.py:390-398); the applied control equals the converged CPU solve."""
