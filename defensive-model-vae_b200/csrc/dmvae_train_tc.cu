@@ -1554,10 +1554,14 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
   // Long trajectories: every op of every tile is added to the CTA's one slab as soon as it is complete (the
   // accumulators of all chunks do not fit tensor memory).  Else next to a running chain with one tile per unit: ...
   const bool per_op = ut == 1 && (a.ready != nullptr || LNG);
+  // Long trajectories after a chain kernel, several tiles per unit: op by op over the unit's tiles, an op's accumulator
+  // kept in tensor memory over those tiles and added to the slab once per unit instead of once per tile (the
+  // read-add-write of every op of every tile was 16 % of the sampled stalls of the work warps at T = 100)
+  const bool lng_units = LNG && ut > 1;
   // Several tiles per unit next to a running chain: op by op over the unit's tiles (the early images of ALL its tiles
   // before the late images of the first), so that only the last ops are left when the chain ends.  After a chain
   // kernel: tile by tile (the next tile's images are being prefetched meanwhile).
-  const bool op_major = a.ready != nullptr && !per_op;
+  const bool op_major = (a.ready != nullptr && !per_op) || lng_units;
   constexpr int chunks = CH_M / WG_ROWS;  // 8 ring stages per (tile, op)
 
   if (warp == WG_PRODUCER_WARP) {
@@ -1583,7 +1587,18 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             // of this CTA) are pulled into L2 while this op's stages go through the ring.
             int on = o + 1;
             long long tn = tile;
-            if (on == n_ops) {
+            if (op_major) {   // next in the walk: the same op of the unit's next tile, else the next op of its first tile
+              on = o;
+              tn = tile + 1;
+              if (tn == t0 + nt) {
+                on = o + 1;
+                tn = t0;
+                if (on == n_ops) {
+                  on = 0;
+                  tn = (unit + role_ctas) * ut;
+                }
+              }
+            } else if (on == n_ops) {
               on = 0;
               tn = tile + 1 < t0 + nt ? tile + 1 : (unit + role_ctas) * ut;
             }
@@ -1656,13 +1671,15 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           __syncwarp();
           rs.advance();
         }
-        if (per_op) {   // this op's accumulator is final (one tile per unit): the work warps write it out while the
-          if (elect_one()) umma_commit(&d_done[n_commit & 1u]);   // next op's products run
+        // this op's accumulator is final (one tile per unit, or the unit's last tile of the op): the work warps write
+        // it out while the next op's products run
+        if (per_op || (lng_units && it % nt == nt - 1)) {
+          if (elect_one()) umma_commit(&d_done[n_commit & 1u]);
           __syncwarp();
           ++n_commit;
         }
       }
-      if (!per_op) {
+      if (!per_op && !lng_units) {
         if (elect_one()) umma_commit(&d_done[n_commit & 1u]);
         __syncwarp();
         ++n_commit;
@@ -1838,7 +1855,7 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&split_full[rs.stage]);
         }
-        if (per_op) {
+        if (per_op || (lng_units && it % nt == 0)) {   // (several tiles per unit: after the op's FIRST tile)
           // the stages of op o are split and on their way through the tensor cores: meanwhile the accumulator of the
           // op before it (complete by now, or soon) goes to the slab - a write-out costs almost as much as the
           // products of an op, and the accumulators of a role do not share columns
@@ -1853,14 +1870,14 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
         }
       }
     }
-    if (per_op && pending >= 0) {
+    if ((per_op || lng_units) && pending >= 0) {
       wait_done();
       if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
       write_op(pending, unit);
     }
 
     // ---- write-out: accumulators -> the unit's partial slab (torch layout of each tensor) ----------
-    if (!per_op) {
+    if (!per_op && !lng_units) {
       wait_done();
       if (a.trace != nullptr && unit == 0 && tid == 0) a.trace[180 + role * 16 + 8] = global_ns();
       for (int o = 0; o < n_ops; ++o) write_op(o, unit);
@@ -2167,7 +2184,11 @@ TrainTcPlan plan_train_tc(const Layout& lo, long long B, int sm_count, int overl
       const double cost = (double)((units + n - 1) / n) * (u + 0.4);
       if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && u > best_u)) { best_cost = cost; best_u = u; }
     }
-    if (chain_long(lo)) best_u = 1;   // long trajectories: every op of every tile goes straight to the slab of its CTA
+    // long trajectories: an op's accumulator goes straight to the slab of its CTA - next to a running chain after every
+    // tile, after a chain kernel once per unit of tiles (the same op of up to 4 tiles accumulated in tensor memory)
+    if (chain_long(lo) && p.overlap) best_u = 1;
+    // ... and every CTA of the role must walk at least one unit: its slab is summed whether it wrote it or not
+    while (chain_long(lo) && best_u > 1 && (p.n_tiles + best_u - 1) / best_u < n) --best_u;
     p.unit_tiles[r] = best_u;
     p.unit_count[r] = chain_long(lo) ? (int)n : (int)((p.n_tiles + p.unit_tiles[r] - 1) / p.unit_tiles[r]);
     p.unit_begin[r] = slabs;

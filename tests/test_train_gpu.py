@@ -109,6 +109,7 @@ def per_tensor_err(grads, grads_ref):
     (400, 16, 300, O.SCRIPT_WEIGHTS),   # ten chunks on the tensor cores (latent <= 32), several tiles, ragged
     (200, 32, 5000, O.DEFAULT_WEIGHTS), # five chunks, widest heads layer, 40 tiles: chain CTAs with followers
     (64, 8, 20000, O.SCRIPT_WEIGHTS),   # 192 features: two chunks, the second half empty; more tiles than SMs
+    (100, 16, 40000, O.SCRIPT_WEIGHTS), # three chunks, 313 tiles: weight-gradient units of four tiles (ragged last unit)
 ])
 def test_fused_fwd_bwd_vs_oracle(T, L, B, weights, impl):
     from dmvae.train import FusedTrainer
