@@ -400,7 +400,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
     for (long long tile = cta; tile < n_tiles; tile += ncta)
       for (int o = 0; o < n_ops; ++o) {
         const COp op = ops[o];
-        const bool tr = a.trace != nullptr && !lng && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
+        const bool tr = a.trace != nullptr && (!lng || NCK <= 2) && cta == 0 && tile == cta + (long long)a.trace_tile * ncta && lane == 0;
         if (op.wait_a && !op.pipe) {
           for (int k = 0; k < 4; ++k) mbar_wait(&a_ready[k], a_phase);
         }
@@ -618,6 +618,47 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       const float sx = x_at(1), sy = x_at(2);
       const int width = lng ? 128 : Ip, n0 = chunk * 128;
       float* img = ts + lo.slot_off[SX_X] + (size_t)chunk * (128 * 128);
+      if (lng) {
+        // A thread reads its own row from global memory (__ldg is a volatile asm: loads stay in program order, and the
+        // first USE of one stalls the thread for a full memory latency).  One tile of the trace: 36 k cycles per chunk
+        // with the loads of a group issued right before their use - so the 16 loads of four groups are issued
+        // together, then used.
+#pragma unroll 1
+        for (int c16 = 0; c16 < 128 / (16 * CH_CP) * CH_CP; c16 += CH_CP) {   // batches of four groups of this thread
+          float xv[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c4 = (c16 * 4) + cp + q * CH_CP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + c4 * 4 + i;
+              xv[q * 4 + i] = n < I ? x_at(n) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c4 = (c16 * 4) + cp + q * CH_CP;
+            uint32_t hi[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = n0 + c4 * 4 + i;
+              float val = xv[q * 4 + i];
+              if (n < I) {
+                const int d = n % 3;
+                if (d == 1) val = val - sx;
+                else if (d == 2) val = val - sy;
+              }
+              xv[q * 4 + i] = val;
+              split_tf32(val, hi[i], lw[i]);
+            }
+            tmem_st4(lane_base + CT_AHI + c4 * 4, hi[0], hi[1], hi[2], hi[3]);
+            tmem_st4(lane_base + CT_ALO + c4 * 4, lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<float4*>(img + mn_image_index(4 * c4, m, 128, width * 4)) =
+                make_float4(xv[q * 4], xv[q * 4 + 1], xv[q * 4 + 2], xv[q * 4 + 3]);
+          }
+        }
+        return;
+      }
 #pragma unroll 2
       for (int c4 = cp; c4 < width / 4; c4 += CH_CP) {
         float xv[4];
@@ -758,7 +799,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       const long long row = tile * CH_M + m;
       const bool row_ok = row < a.B;
       float* ts = a.stash + (size_t)tile * lo.tile_stash;
-      tr_tile = a.trace != nullptr && !lng && cta == 0 && tile == cta + (long long)a.trace_tile * ncta;
+      tr_tile = a.trace != nullptr && (!lng || NCK <= 2) && cta == 0 && tile == cta + (long long)a.trace_tile * ncta;
       epi_no = 0;
       float lw_prev[16], lw_sum[4], lw_rt;   // state of the chunked loss walk (epi_loss_chunk)
       int lw_pos;
@@ -1189,6 +1230,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll 1
           for (int grp = 0; grp < 8; ++grp) {
             const int nb = c * 128 + grp * 16;
+            // all loads of the group first (see stage_xrel: 114 k cycles per chunk with a load right before its use),
+            // the accumulator columns under them
+            float xg[16], bg[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool inside = nb + j < I;
+              xg[j] = inside ? x_at(nb + j) : 0.f;
+              bg[j] = inside ? __ldg(bias + nb + j) : 0.f;
+            }
             uint32_t v[16];
             tmem_ld16(lane_base + dcol + grp * 16, v);
             tmem_ld_wait();
@@ -1201,8 +1251,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               d = d >= 3 ? d - 3 : d;                       // n % 3: 0 time, 1 x, 2 y
               const bool inside = n < I;
               const bool on = inside && row_ok;
-              const float r = __uint_as_float(v[j]) + (inside ? __ldg(bias + n) : 0.f);
-              const float xv = inside ? x_at(n) : 0.f;
+              const float r = __uint_as_float(v[j]) + bg[j];
+              const float xv = xg[j];
               const float target = d == 0 ? xv : (d == 1 ? xv - sx : xv - sy);
               const float diff = r - target;
               float gn = c_rec * diff;
