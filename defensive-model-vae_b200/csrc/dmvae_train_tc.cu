@@ -586,6 +586,23 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       }
     };
     auto x_at = [&](int n) -> float { return lng ? (xrow != nullptr ? __ldg(xrow + n) : 0.f) : xbuf[m * I + n]; };
+    // long trajectories: features [n, n + 4) of this thread's row (n a multiple of 4), zero beyond I or the batch end; one
+    // 128-bit or two 64-bit loads where the row's address allows (a warp-wide scalar load of 32 rows occupies the load
+    // unit as long as a 128-bit one: a quarter of the instructions)
+    auto x4_at = [&](int n) -> float4 {
+      if (xrow == nullptr || n >= I) return make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* p = xrow + n;
+      if (n + 4 <= I) {
+        const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+        if ((ad & 15u) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+        if ((ad & 7u) == 0) {
+          const float2 u = __ldg(reinterpret_cast<const float2*>(p)), w = __ldg(reinterpret_cast<const float2*>(p) + 1);
+          return make_float4(u.x, u.y, w.x, w.y);
+        }
+        return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+      }
+      return make_float4(__ldg(p), n + 1 < I ? __ldg(p + 1) : 0.f, n + 2 < I ? __ldg(p + 2) : 0.f, 0.f);
+    };
     // start point of the tile's row: the 16-wide stash image ([x0, y0, 1, 0...]; the same columns become the A operand
     // of cond0 in the epilogue that precedes it, stage_start_cols)
     auto stage_start = [&](long long tile) {
@@ -629,11 +646,8 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int c4 = (c16 * 4) + cp + q * CH_CP;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = n0 + c4 * 4 + i;
-              xv[q * 4 + i] = n < I ? x_at(n) : 0.f;
-            }
+            const float4 g = x4_at(n0 + c4 * 4);
+            xv[q * 4] = g.x; xv[q * 4 + 1] = g.y; xv[q * 4 + 2] = g.z; xv[q * 4 + 3] = g.w;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1234,11 +1248,12 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             // the accumulator columns under them
             float xg[16], bg[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const bool inside = nb + j < I;
-              xg[j] = inside ? x_at(nb + j) : 0.f;
-              bg[j] = inside ? __ldg(bias + nb + j) : 0.f;
+            for (int q = 0; q < 4; ++q) {
+              const float4 g = x4_at(nb + 4 * q);
+              xg[4 * q] = g.x; xg[4 * q + 1] = g.y; xg[4 * q + 2] = g.z; xg[4 * q + 3] = g.w;
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) bg[j] = nb + j < I ? __ldg(bias + nb + j) : 0.f;
             uint32_t v[16];
             tmem_ld16(lane_base + dcol + grp * 16, v);
             tmem_ld_wait();
