@@ -1769,7 +1769,15 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
     float* slab = a.slabs + (size_t)(a.unit_begin[role] + (LNG ? my_index : unit)) * a.slab_stride;
     float* stg = wo_stage + warp * (32 * 20);   // this warp's staging tile of the write-out
     const int f0 = LNG && ops[o].chunk > 0 ? ops[o].chunk * 128 : 0;   // first feature of the op's chunk of the trajectory
-    auto put = [&](float* dst, float val) { *dst = add_to ? *dst + val : val; };
+    // Adding to the slab: a reduction at the L2 (red.global.add.f32, nothing comes back), not load - add - store: the
+    // slabs of a large batch are evicted by the stash that streams past them, and a thread that waits for the old value
+    // of every element pays an HBM round trip per element (28 % of this kernel's stall samples at T = 100).  An element
+    // is only ever touched by one thread, unit after unit: same-address accesses of one thread keep their order, so the
+    // sum is the same bits as before.
+    auto put = [&](float* dst, float val) {
+      if (add_to) atomicAdd(dst, val);
+      else *dst = val;
+    };
     const int L = lo.L, I = lo.I;
     {
       const WOp op = ops[o];
@@ -1811,18 +1819,13 @@ __device__ __forceinline__ void wgrad_body(const Layout& lo, const WgradArgs& a,
             const int r = (lane >> 2) + 8 * i;
             const float4 val = *reinterpret_cast<const float4*>(stg + r * 20 + c4 * 4);
             float* dst = row0 + (size_t)(q * 32 + r) * rstride + c4 * 4;
-            if (vec) {
-              float4 out = val;
-              if (add_to) {
-                const float4 old = *reinterpret_cast<const float4*>(dst);
-                out = make_float4(old.x + val.x, old.y + val.y, old.z + val.z, old.w + val.w);
-              }
-              *reinterpret_cast<float4*>(dst) = out;
+            if (vec && !add_to) {
+              *reinterpret_cast<float4*>(dst) = val;
             } else {
-              if (c4 * 4 + 0 < ncols) dst[0] = add_to ? dst[0] + val.x : val.x;
-              if (c4 * 4 + 1 < ncols) dst[1] = add_to ? dst[1] + val.y : val.y;
-              if (c4 * 4 + 2 < ncols) dst[2] = add_to ? dst[2] + val.z : val.z;
-              if (c4 * 4 + 3 < ncols) dst[3] = add_to ? dst[3] + val.w : val.w;
+              if (c4 * 4 + 0 < ncols) put(dst, val.x);
+              if (c4 * 4 + 1 < ncols) put(dst + 1, val.y);
+              if (c4 * 4 + 2 < ncols) put(dst + 2, val.z);
+              if (c4 * 4 + 3 < ncols) put(dst + 3, val.w);
             }
           }
           __syncwarp();   // the tile is rewritten by the next chunk
