@@ -271,9 +271,9 @@ static int train_common(const DmvaeCfg* cfg, const float* packed, const float* x
   const float wv[4] = {w->recon, w->kld, w->start, w->time};
   cudaError_t e;
   if (step_dev != nullptr && !dmvae::train_tc_supported(lo))
-    return fail(DMVAE_ERR_SHAPE, "%s: the device-side step counter needs the tensor-core path (3*seq_len <= 64, latent_dim <= 32)", what);
+    return fail(DMVAE_ERR_SHAPE, "%s: the device-side step counter needs the tensor-core path (latent_dim <= 32)", what);
   if (dp != nullptr && !dmvae::train_tc_supported(lo))
-    return fail(DMVAE_ERR_SHAPE, "%s: the peer-memory exchange needs the tensor-core path (3*seq_len <= 64, latent_dim <= 32)", what);
+    return fail(DMVAE_ERR_SHAPE, "%s: the peer-memory exchange needs the tensor-core path (latent_dim <= 32)", what);
   const bool want_tc = g_train_impl >= 2 || (g_train_impl == 0 && B >= TRAIN_TC_MIN_ROWS);
   if ((want_tc || step_dev != nullptr || dp != nullptr) && dmvae::train_tc_supported(lo)) {
     // tensor cores: forward/loss/backward chain -> weight gradients -> partial-slab reduction (+ Adam)

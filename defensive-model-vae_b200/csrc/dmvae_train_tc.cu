@@ -24,8 +24,9 @@
 //   reduce_tc_kernel  fixed-order sum of the partial slabs (+ the loss partials), optionally with
 //                  the Adam update (torch optim/adam.py::_single_tensor_adam) in the same thread.
 //
-// Envelope of this path: 3*seq_len <= 64 and latent_dim <= 32 (the reference uses 10/12 and 8);
-// anything else inside the ABI envelope runs the FFMA kernel of dmvae_train.cu.
+// Envelope of this path: latent_dim <= 32 at any seq_len (the reference uses 8 and 10/12).  Up to 3*seq_len = 64 the
+// trajectory is one operand; beyond that the <true> instantiations of the chain and weight-gradient bodies walk the
+// first encoder / last decoder layer in chunks of 128 features.  latent_dim 33..64 runs the FFMA kernel of dmvae_train.cu.
 #include "dmvae_common.cuh"
 #include "dmvae_launch.h"
 #include "dmvae_pack.cuh"

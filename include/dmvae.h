@@ -22,8 +22,9 @@
  *
  * Shape envelope: dim == 3, hidden_dim == 128,
  * 1 <= latent_dim <= 64, 2 <= seq_len <= 400.  Inside it the tensor-core kernels cover all of
- * generation (latent_dim <= 56 with a per-row start point) and 3*seq_len <= 64, latent_dim <= 32 for
- * training; the rest runs on the FP32 FFMA kernels behind the same entry points.
+ * generation (latent_dim <= 56 with a per-row start point) and every seq_len with latent_dim <= 32 for
+ * training (beyond 3*seq_len = 64 the first encoder / last decoder layer walk the trajectory in chunks of 128
+ * features); the rest runs on the FP32 FFMA kernels behind the same entry points.
  */
 #ifndef DMVAE_H_
 #define DMVAE_H_
