@@ -947,6 +947,19 @@ def run_cuda(args):
                             "traffic_source": (traffic_from_profile("mpc_track_kernel") or {}).get("source")},
                "cpu_baseline": cpu_tracker_rate(8.0) if (world == 1 and not args.no_cpu) else None}
         del bt, bt2, st_d, ct_d
+        # complete runs through the public call (set-up, every step of every trajectory, histories in device memory):
+        # the trajectories have 150 .. 990 steps, track_batch orders them so that the lanes of a warp finish together
+        from dmvae.tracker import track_batch
+        n_full = min(n_mpc, 16384)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        full_res = track_batch(way_m[:n_full], init_m[:n_full], 0.02)
+        torch.cuda.synchronize()
+        full_dt = time.perf_counter() - t0
+        mpc["complete_runs"] = {"trajectories": n_full, "controller_calls": int(full_res.n_steps.sum()), "seconds": full_dt,
+                                "trajectories_per_sec": n_full / full_dt, "controller_calls_per_sec": float(full_res.n_steps.sum()) / full_dt,
+                                "solver_iterations_per_call": float(full_res.iterations.sum()) / float(full_res.n_steps.sum())}
+        del full_res
 
     # the reference shuffles its data set every epoch (Training_VAE.py:327): the same resident step with the rows of
     # every epoch picked through the keyed permutation (dmvae_train_step_resident, shuffle = 1)

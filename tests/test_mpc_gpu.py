@@ -173,6 +173,26 @@ def test_tracking_shards_like_generation(gold, world):
     assert seen == n
 
 
+def test_rows_of_different_lengths_come_back_in_the_callers_order(gold):
+    """track_batch tracks the rows in the order of their step counts (so that the lanes of a warp finish together) and
+    undoes that on the way out: every row equals the same trajectory tracked on its own, bit for bit, tails included."""
+    from dmvae.tracker import track_batch
+    base = gold["sce2_west_way"]
+    scales = [0.30, 1.0, 0.12, 0.55, 0.12, 0.80]
+    way = np.stack([base * np.array([1.0, 1.0, k], dtype=np.float32) for k in scales])
+    way[:, :, :2] = base[None, :, :2] * np.array(scales, dtype=np.float32)[:, None, None]     # same speeds, shorter paths
+    init = np.repeat(gold["sce2_west_init"][None], len(scales), 0)
+    res = track_batch(way, init, 0.025)
+    assert len(set(res.n_steps.tolist())) >= 4 and res.n_steps[1] == res.n_steps.max()
+    for j in range(len(scales)):
+        one = track_batch(way[j:j + 1], init[j:j + 1], 0.025)
+        s = int(res.n_steps[j])
+        assert s == int(one.n_steps[0])
+        assert torch.equal(one.states[0], res.states[j, :s + 1]) and torch.equal(one.controls[0], res.controls[j, :s])
+        assert torch.equal(res.states[j, s:], res.states[j, s:s + 1].expand(res.states.shape[1] - s, 4))   # tail = last state
+        assert res.iterations[j] == one.iterations[0]
+
+
 def test_saturated_controls_follow_the_effective_bounds():
     """Speed far above the reference: the first rows brake hard, rows 10..19 are held at the -0.5 that the reference's
     bounds list gives them (MPC_Tracking.py:390-398); the applied control equals the converged CPU solve."""
