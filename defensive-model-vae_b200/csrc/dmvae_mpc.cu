@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(const MpcCfg c, const 
   vx[0] = vx0;
   vy[0] = vy0;
   ok = ok && t[1] > 0.0;   // the knot times themselves must increase for the interpolant
+  ok = ok && t_last < 1e6 && t_first > -1e6;   // finite (an infinite last time would make the 1 ms heading scan endless)
   status[j] = ok ? 0 : 1;  // 1: waypoint times do not increase strictly (the reference raises, :118-119)
   // initial state (:435-441): heading wrapped, speed = |(vx, vy)|
   {

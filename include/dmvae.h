@@ -322,7 +322,7 @@ int dmvae_dense(const float* weight, const float* bias, const float* x, float* y
  *                  trajectory; written by dmvae_mpc_prepare, carried from one dmvae_mpc_track call to the next
  *   state          (n, 4) float64 [x, y, theta, v]: written by prepare (PathTracker.__init__, :435-441), advanced by track
  *   status         (n) int32, written by prepare: 0 ok, 1 waypoint times do not increase strictly (the reference raises
- *                  ValueError, :118-119); such trajectories are skipped by track
+ *                  ValueError, :118-119) or are not finite / beyond 1e6 s; such trajectories are skipped by track
  *   profile        optional (n, 5) float64 [start_theta, end_vx, end_vy, end_theta, t_end] (:194-221), or NULL
  * dmvae_mpc_track runs steps [step_begin, step_begin + step_count) of every trajectory j that has them (s < n_steps[j],
  * n_steps = int(total_time / dt) per trajectory, :505).  states_out (n, out_rows, 4) float64 or NULL: row s + 1 = state
