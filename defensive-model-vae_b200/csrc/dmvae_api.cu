@@ -649,8 +649,8 @@ int dmvae_dense(const float* weight, const float* bias, const float* x, float* y
 // ---------------------------------------------------------------------------- batched MPC path tracker
 static int check_mpc(const DmvaeMpcCfg* c, const char* what) {
   if (!c) return fail(DMVAE_ERR_ARG, "%s: null cfg", what);
-  if (c->n_way < 4 || c->n_way > DMVAE_MPC_MAX_WAY)
-    return fail(DMVAE_ERR_SHAPE, "%s: n_way %d outside 4..%d (the quadratic / linear interpolants of fewer than four waypoints are not built)",
+  if (c->n_way < 2 || c->n_way > DMVAE_MPC_MAX_WAY)
+    return fail(DMVAE_ERR_SHAPE, "%s: n_way %d outside 2..%d (the reference needs at least two waypoints, MPC_Tracking.py:114-115)",
                 what, c->n_way, DMVAE_MPC_MAX_WAY);
   if (c->horizon < 1 || c->horizon > DMVAE_MPC_MAX_HORIZON || c->blocks < 1 || c->blocks > c->horizon)
     return fail(DMVAE_ERR_ARG, "%s: need 1 <= blocks <= horizon <= %d (the reference raises when the control horizon exceeds the prediction horizon)",

@@ -67,14 +67,35 @@ struct Knots {
   }
 };
 
-// Not-a-knot cubic interpolant of (t_i, y_i), i < nw (nw >= 4) as one cubic per interval:
+// Not-a-knot cubic interpolant of (t_i, y_i), i < nw (nw >= 4; a parabola / a line for 3 / 2 points) as one cubic per interval:
 // c0 + c1 s + c2 s^2 + c3 s^3, s = t - t_i, written to out[(4 i + k) * n].  m: scratch of MPC_MAX_WAY doubles x 3.
 __device__ void notaknot(const double* t, const double* y, int nw, double* out, long long n, double* m, double* cp, double* dp) {
+  auto h = [&](int i) { return t[i + 1] - t[i]; };
+  auto d = [&](int i) { return (y[i + 1] - y[i]) / h(i); };
+  // fewer than four points: the reference falls back to interp1d(kind='quadratic') for three (one parabola through
+  // them) and kind='linear' for two (MPC_Tracking.py:126-137, :173-178)
+  if (nw == 2) {
+    out[0] = y[0];
+    out[(size_t)n] = d(0);
+    out[(size_t)2 * n] = 0.0;
+    out[(size_t)3 * n] = 0.0;
+    return;
+  }
+  if (nw == 3) {
+    const double dd = (d(1) - d(0)) / (t[2] - t[0]);   // second divided difference
+    out[0] = y[0];
+    out[(size_t)n] = d(0) - dd * h(0);
+    out[(size_t)2 * n] = dd;
+    out[(size_t)3 * n] = 0.0;
+    out[(size_t)4 * n] = y[1];
+    out[(size_t)5 * n] = d(0) + dd * h(0);
+    out[(size_t)6 * n] = dd;
+    out[(size_t)7 * n] = 0.0;
+    return;
+  }
   // second derivatives m_1 .. m_{nw-2} from the tridiagonal system with m_0 and m_{nw-1} eliminated through the
   // not-a-knot conditions (third derivative continuous across t_1 and t_{nw-2})
   const int N = nw - 2;   // unknowns
-  auto h = [&](int i) { return t[i + 1] - t[i]; };
-  auto d = [&](int i) { return (y[i + 1] - y[i]) / h(i); };
   for (int k = 0; k < N; ++k) {   // row of m_{k+1}
     const int i = k + 1;
     double lo = h(i - 1), di = 2.0 * (h(i - 1) + h(i)), up = h(i);
@@ -136,8 +157,15 @@ __global__ void __launch_bounds__(128) mpc_prepare_kernel(const MpcCfg c, const 
       ok = ok && dtf > 0.f;
       if (dtf == 0.f) dtf = 1e-6f;
       t[i + 1] = (double)__fadd_rn(w[i * 3 + 2], __fmul_rn(dtf, 0.5f));
-      vx[i + 1] = ((double)w[(i + 1) * 3] - (double)w[i * 3]) / (double)dtf;
-      vy[i + 1] = ((double)w[(i + 1) * 3 + 1] - (double)w[i * 3 + 1]) / (double)dtf;
+      if (nw == 2) {
+        // two waypoints: the reference's position interpolant is interp1d(kind='linear'), which stays in the waypoints'
+        // float32 (the spline kinds evaluate in float64): position difference and quotient are float32 operations
+        vx[i + 1] = (double)__fdiv_rn(__fsub_rn(w[(i + 1) * 3], w[i * 3]), dtf);
+        vy[i + 1] = (double)__fdiv_rn(__fsub_rn(w[(i + 1) * 3 + 1], w[i * 3 + 1]), dtf);
+      } else {
+        vx[i + 1] = ((double)w[(i + 1) * 3] - (double)w[i * 3]) / (double)dtf;
+        vy[i + 1] = ((double)w[(i + 1) * 3 + 1] - (double)w[i * 3 + 1]) / (double)dtf;
+      }
     }
     t_first = (double)w[2];
     t_last = (double)w[(nw - 1) * 3 + 2];

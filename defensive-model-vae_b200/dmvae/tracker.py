@@ -15,8 +15,8 @@ of SLSQP's early stop at ftol = 1e-6: trajectories agree with the reference's to
 * ``run_tracker_jobs`` the second half of ``Distribution.batch_process_trajectories`` for the jobs of
   ``handoff.generate_tracker_jobs``: tracks them in one batch and writes ``tracked_trajectory_*.npy``.
 
-No CPU path: raises without a CUDA device.  Fewer than four waypoints (the reference's quadratic / linear interpolants)
-are not supported.
+No CPU path: raises without a CUDA device.  Two to 64 waypoints per trajectory (cubic interpolants from four on, the
+reference's quadratic / linear fall-backs for three / two).
 """
 from __future__ import annotations
 

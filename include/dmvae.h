@@ -316,7 +316,8 @@ int dmvae_dense(const float* weight, const float* bias, const float* x, float* y
  * reference's to its early-stopping noise, not bit for bit (statistical parity).
  *
  *   waypoints      (n, n_way, 3) [x, y, t], float32 (way_f32 = 1: the VAE's output; the knot arithmetic that the reference
- *                  does in float32 is done in float32) or float64; 4 <= n_way <= 64 (cubic interpolants only)
+ *                  does in float32 is done in float32) or float64; 2 <= n_way <= 64 (cubic interpolants from four waypoints on,
+ *                  one parabola for three, a line for two: MPC_Tracking.py:126-137)
  *   initial_state  (n, 5) float64 [x, y, theta, vx, vy] (Distribution.py:80)
  *   workspace      dmvae_mpc_workspace_bytes(cfg, n) bytes: interpolants, previous control and previous solution of every
  *                  trajectory; written by dmvae_mpc_prepare, carried from one dmvae_mpc_track call to the next

@@ -5,6 +5,7 @@ TEST INFRASTRUCTURE.  Run once in the build container (where ``/root/reference``
 
     python -m oracle.make_golden_mpc            # tests/golden/mpc_track.npz
     python -m oracle.make_golden_mpc --full     # tests/golden/mpc_track_full.npz (two complete runs, ~10 minutes)
+    python -m oracle.make_golden_mpc --small    # tests/golden/mpc_track_small.npz (three / two waypoints)
 
 tests/golden/mpc_track.npz, per case ``c``: the waypoints ``[x, y, t]`` (float32 as the VAE hands them over, one
 case float64), the initial state ``[x, y, theta, vx, vy]``, the time step, what ``PathInterpolator`` derived
@@ -167,8 +168,50 @@ def main_full():
     print("wrote", os.path.join(GOLD, "mpc_track_full.npz"))
 
 
+def main_small():
+    """tests/golden/mpc_track_small.npz: three and two waypoints - the reference's quadratic / linear interpolants
+    (MPC_Tracking.py:126-137, :173-178): what PathInterpolator derives, windows, four controller calls."""
+    M = load_tracker_module()
+    rng = np.random.default_rng(7)
+    gold = {}
+    for name, n, dtype in (("three", 3, np.float32), ("two", 2, np.float32), ("three_f64", 3, np.float64)):
+        way = waypoints_along(rng, n, (3.0, -2.0), 0.6, 9.0, 6.0, 0.8, 1.3, 0.2, dtype)
+        init = np.array([3.0, -2.0, 0.6, 7.4, 5.1])
+        dt = 0.02
+        quiet = io.StringIO()
+        with contextlib.redirect_stdout(quiet):
+            tr = M.PathTracker(way.copy(), init.copy(), 2.8, 30, 20, dt)
+            pi = tr.path_interp
+            t_end = float(way[-1, 2])
+            win_times = np.array([0.0, 0.4 * t_end, t_end - 10 * dt, t_end + 3 * dt])
+            wins = np.zeros((len(win_times), 31, 2))
+            for k, ct in enumerate(win_times):
+                held = 0.0
+                for i in range(31):
+                    t_ref = float(ct) + i * dt
+                    _, _, vx, vy = pi.get_reference(t_ref)
+                    v_ref = np.sqrt(vx ** 2 + vy ** 2)
+                    if v_ref >= 0.1:
+                        held = pi.get_reference_heading(t_ref)
+                    wins[k, i] = [held, v_ref]
+            states, controls = [tr.current_state.copy()], []
+            for j in range(4):
+                st, u = tr.step(j * dt)
+                states.append(st.copy())
+                controls.append(u.copy())
+        gold[f"{name}_way"], gold[f"{name}_init"], gold[f"{name}_dt"] = way, init, np.float64(dt)
+        gold[f"{name}_profile"] = np.array([pi.start_theta, pi.end_vx, pi.end_vy, pi.end_theta, pi.t_end])
+        gold[f"{name}_win_times"], gold[f"{name}_windows"] = win_times, wins
+        gold[f"{name}_states"], gold[f"{name}_controls"] = np.array(states), np.array(controls)
+        print(name, np.array(states)[-1], flush=True)
+    np.savez_compressed(os.path.join(GOLD, "mpc_track_small.npz"), **gold)
+    print("wrote", os.path.join(GOLD, "mpc_track_small.npz"))
+
+
 if __name__ == "__main__":
-    if "--full" in sys.argv:
+    if "--small" in sys.argv:
+        main_small()
+    elif "--full" in sys.argv:
         main_full()
     else:
         main()

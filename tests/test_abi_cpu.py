@@ -79,7 +79,7 @@ def test_host_side_queries(lib):
     mpc = _lib.DmvaeMpcCfg(n_way=10, way_f32=1, horizon=30, blocks=20, max_iter=50, reserved=0, wheelbase=2.8, max_steer=0.5,
                            max_accel=7.0, q_theta=20.0, q_v=5.0, r_accel=1.0, r_steer=50.0, tol=1e-11)
     assert lib.dmvae_mpc_workspace_bytes(ctypes.byref(mpc), 1000) == (10 + 8 * 9 + 8 + 40) * 1000 * 8
-    mpc.n_way = 3
+    mpc.n_way = 1
     assert lib.dmvae_mpc_workspace_bytes(ctypes.byref(mpc), 1000) < 0 and b"n_way" in lib.dmvae_last_error()
     names = {lib.dmvae_kernel_name(i).decode() for i in range(_lib.KERNEL_COUNT)}
     assert {"mpc_prepare_kernel", "mpc_track_kernel"} <= names

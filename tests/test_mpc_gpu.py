@@ -94,6 +94,22 @@ def test_complete_runs_stay_with_the_reference(golden_dir, name):
     assert np.abs(ct - full[f"{name}_controls"]).max() < 5e-3
 
 
+@pytest.mark.parametrize("name", ["three", "two", "three_f64"])
+def test_three_and_two_waypoints(golden_dir, name):
+    """The reference's quadratic / linear interpolants for fewer than four waypoints (tests/golden/mpc_track_small.npz)."""
+    from dmvae.tracker import BatchTracker, track_batch
+    g = np.load(os.path.join(golden_dir, "mpc_track_small.npz"))
+    way, init, dt = g[f"{name}_way"], g[f"{name}_init"], float(g[f"{name}_dt"])
+    bt = BatchTracker(way[None], init[None], dt, 30, 20)
+    assert int(bt.status[0]) == 0
+    assert np.abs(bt.profile[0].cpu().numpy() - g[f"{name}_profile"]).max() < 1e-9
+    assert np.abs(bt.windows(g[f"{name}_win_times"])[0].cpu().numpy() - g[f"{name}_windows"]).max() < 1e-9
+    _, st, ct = track_batch(way[None], init[None], dt, max_steps=4).trajectory(0)
+    assert np.abs(st - g[f"{name}_states"]).max() < 5e-4 and np.abs(ct - g[f"{name}_controls"]).max() < 5e-3
+    _, so, co = O.track(way, init, dt, max_steps=4, solver="exact")
+    assert np.abs(st - so).max() < 1e-7 and np.abs(ct - co).max() < 1e-6
+
+
 def test_reference_class_surface(gold):
     """The drop-in module (repo root MPC/MPC_Tracking.py) imported the way Distribution.py:9 imports the reference's, its
     PathTracker used the way Distribution.process_single_trajectory (:91-105) uses it."""
@@ -237,9 +253,8 @@ def test_tracker_jobs_are_tracked_and_saved_like_the_reference_driver(gold, tmp_
 def test_argument_errors_are_loud():
     from dmvae import DmvaeError
     from dmvae.tracker import BatchTracker
-    way = np.zeros((1, 3, 3), dtype=np.float32)
-    way[0, :, 2] = [0, 1, 2]
+    way = np.zeros((1, 1, 3), dtype=np.float32)
     with pytest.raises(DmvaeError):
-        BatchTracker(way, np.zeros((1, 5)), 0.02, 30, 20)         # three waypoints: quadratic interpolants are not built
+        BatchTracker(way, np.zeros((1, 5)), 0.02, 30, 20)         # one waypoint: the reference raises too (MPC_Tracking.py:114-115)
     with pytest.raises(ValueError):
         BatchTracker(np.zeros((1, 10, 3), dtype=np.float32), np.zeros((1, 5)), 0.02, 5, 10)

@@ -66,6 +66,20 @@ def test_a_complete_run_of_the_converged_solver_stays_with_the_reference(golden_
     assert np.abs(controls - full["sce2_west_controls"]).max() < 5e-3
 
 
+@pytest.mark.parametrize("name", ["three", "two", "three_f64"])
+def test_three_and_two_waypoints_use_the_quadratic_and_linear_interpolants(golden_dir, name):
+    """tests/golden/mpc_track_small.npz (the reference run on 3 / 2 waypoints: interp1d kind 'quadratic' / 'linear',
+    MPC_Tracking.py:126-137, :173-178)."""
+    g = np.load(os.path.join(golden_dir, "mpc_track_small.npz"))
+    way, init, dt = g[f"{name}_way"], g[f"{name}_init"], float(g[f"{name}_dt"])
+    p = O.SpeedProfile(way, init)
+    np.testing.assert_array_equal(np.array([p.start_theta, p.end_vx, p.end_vy, p.end_theta, p.t_end]), g[f"{name}_profile"])
+    for k, ct in enumerate(g[f"{name}_win_times"]):
+        np.testing.assert_array_equal(p.window(float(ct), dt, 30), g[f"{name}_windows"][k])
+    _, states, controls = O.track(way, init, dt, max_steps=4)
+    assert np.abs(states - g[f"{name}_states"]).max() < 1e-4 and np.abs(controls - g[f"{name}_controls"]).max() < 2e-3
+
+
 def test_analytic_gradient_matches_differences():
     rng = np.random.default_rng(3)
     ref = np.stack([1.5 + 0.01 * rng.standard_normal(31), 8 + rng.standard_normal(31)], 1)
