@@ -1220,8 +1220,15 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
       // backwards gets c_mono added three features later, possibly from the next group or chunk, so a group is written
       // to the stash only when the next one has been walked.
       auto epi_loss_chunk = [&](int c, uint32_t dcol) {
+        static_assert(CH_CP == 2, "the loss walk of a chunk is shared by the two threads of a row");
         wait_d();
-        if (cp == 0) {
+        {
+          // The two threads of a row take one half of the chunk each (groups [4 cp, 4 cp + 4) of 16 features): the walk is
+          // bound by the instruction stream of ONE warp per scheduler (30 k cycles per chunk with half of the epilogue
+          // warps idle).  The monotonicity term couples a time feature with the one three features earlier; across
+          // the two seams (feature 64 of the chunk, and the chunk's end) every thread evaluates what it needs from the
+          // accumulator columns next to its range - r = accumulator + bias, the same two operands and the same
+          // addition on either side of a seam, so both threads see the same number.
           const float c_rec = a.w_recon * 2.f * a.inv_batch / (float)I;
           const float c_start = a.w_start * a.inv_batch;
           const float c_t0 = a.w_time * 2.f * a.inv_batch;
@@ -1237,13 +1244,50 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
               *reinterpret_cast<float4*>(img + mn_image_index(4 * (c4 + q4), m, 128, 512)) =
                   make_float4(g[4 * q4], g[4 * q4 + 1], g[4 * q4 + 2], g[4 * q4 + 3]);
           };
+          // r of feature n0 + k (k < 4) of this chunk: columns [col0, col0 + 4) of the accumulator + bias
+          auto r4_at = [&](int col0, float (&r)[4]) {
+            uint32_t v4[4];
+            tmem_ld4(lane_base + dcol + col0, v4);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int n = c * 128 + col0 + k;
+              r[k] = __uint_as_float(v4[k]) + (n < I ? __ldg(bias + n) : 0.f);
+            }
+          };
+          // (static indices only: a run-time index would move the arrays to local memory)
+          auto pick3 = [](const float (&r)[4], int i) { return i == 0 ? r[0] : (i == 1 ? r[1] : (i == 2 ? r[2] : r[3])); };
+          auto bump = [&](int o, float x) {   // lw_prev[13 + o] += x
+            if (o == 0) lw_prev[13] += x;
+            else if (o == 1) lw_prev[14] += x;
+            else lw_prev[15] += x;
+          };
+          const int g0 = 4 * cp;                       // this thread's groups [g0, g0 + 4)
           if (c == 0) {
             lw_sum[0] = lw_sum[1] = lw_sum[2] = lw_sum[3] = 0.f;
-            lw_rt = 0.f;
+            if (cp == 0) lw_rt = 0.f;
             lw_pos = -1;
           }
+          if (cp == 1) {
+            if (c > 0) {
+              // the last group of the previous chunk is still pending: a time step of THIS chunk that runs backwards
+              // adds c_mono to its predecessor there (feature n_f - 3, position 13 + (n_f - 128 c) of that group)
+              const int o = (3 - (c * 128) % 3) % 3, n_f = c * 128 + o;
+              float r[4];
+              r4_at(0, r);
+              const float dt = pick3(r, o) - lw_rt;    // lw_rt: the last time feature of the previous chunk (this thread's)
+              if (n_f < I && row_ok && dt < 0.f) bump(o, c_mono);
+              write_group(lw_pos, lw_prev);
+              lw_pos = -1;
+            }
+            // the time feature before feature 64 of the chunk (the other thread's last one)
+            const int o = (c * 128 + 64) % 3, k = o == 0 ? 3 : o;      // n_p = 128 c + 64 - k, column 64 - k
+            float r[4];
+            r4_at(60, r);
+            lw_rt = pick3(r, 4 - k);
+          }
 #pragma unroll 1
-          for (int grp = 0; grp < 8; ++grp) {
+          for (int grp = g0; grp < g0 + 4; ++grp) {
             const int nb = c * 128 + grp * 16;
             // all loads of the group first (see stage_xrel: 114 k cycles per chunk with a load right before its use),
             // the accumulator columns under them
@@ -1260,6 +1304,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             tmem_ld_wait();
             float gcur[16];
             const int ph = nb % 3;
+            const bool seam = grp == g0;   // the predecessor of this group's first time feature belongs to the other thread
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = nb + j;
@@ -1283,7 +1328,7 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
                     lw_sum[3] -= dt;
                     gn -= c_mono;
                     if (j >= 3) gcur[j >= 3 ? j - 3 : 0] += c_mono;
-                    else lw_prev[13 + j] += c_mono;
+                    else if (!seam) lw_prev[13 + j] += c_mono;   // (across a seam the owner of that feature adds it)
                   }
                 }
                 lw_rt = r;
@@ -1298,18 +1343,35 @@ __device__ __forceinline__ void chain_body(const Layout& lo, const ChainArgs& a,
             for (int j = 0; j < 16; ++j) lw_prev[j] = gcur[j];
             lw_pos = c * 8 + grp;
           }
-          if (c == NCK - 1) {
+          if (cp == 0) {
+            // the first time feature of the other half (feature 128 c + 64 + o): running backwards, it adds c_mono to this
+            // half's last time feature, position 13 + o of the group that is still pending here
+            const int o = (3 - (c * 128 + 64) % 3) % 3, n_a = c * 128 + 64 + o;
+            float r[4];
+            r4_at(64, r);
+            const float dt = pick3(r, o) - lw_rt;
+            if (n_a < I && row_ok && dt < 0.f) bump(o, c_mono);
             write_group(lw_pos, lw_prev);
-            if (row_ok) {
-              loss_acc[0] += lw_sum[0] * (a.inv_batch / (float)I);
-              loss_acc[2] += lw_sum[1] * (a.inv_batch * 0.5f);
-              loss_acc[3] += lw_sum[2] * a.inv_batch + (T > 1 ? lw_sum[3] * (a.inv_batch / (float)(T - 1)) : 0.f);
+            lw_pos = -1;
+            // ... and the last time feature of the chunk, which this thread's first one of the NEXT chunk is compared with
+            // (its accumulator will be gone by then)
+            if (c < NCK - 1) {
+              const int k = (c * 128 + 128) % 3 == 0 ? 3 : (c * 128 + 128) % 3;   // feature 128 c + 128 - k, column 128 - k
+              r4_at(124, r);
+              lw_rt = pick3(r, 4 - k);
             }
+          } else if (c == NCK - 1) {
+            write_group(lw_pos, lw_prev);   // nothing follows the last chunk
+          }
+          if (c == NCK - 1 && row_ok) {
+            loss_acc[0] += lw_sum[0] * (a.inv_batch / (float)I);
+            loss_acc[2] += lw_sum[1] * (a.inv_batch * 0.5f);
+            loss_acc[3] += lw_sum[2] * a.inv_batch + (T > 1 ? lw_sum[3] * (a.inv_batch / (float)(T - 1)) : 0.f);
           }
         }
         if (c == NCK - 1) {
           // every product of the last decoder layer is complete: its input d3 may go.  The first chunk of the gradient
-          // comes back from the stash (the other half of the row was written by this lane quarter's first warp)
+          // comes back from the stash (both threads of a row have written their halves of it)
           asm volatile("bar.sync 1, %0;" ::"n"(CH_EPI_THREADS) : "memory");
           stage_g(0);
         }
