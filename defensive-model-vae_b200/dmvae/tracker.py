@@ -246,22 +246,22 @@ class PathTracker:
         return self.current_state.copy(), control
 
     def run_simulation(self, total_time: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """All ``int(total_time / dt)`` steps in one launch (``:495-523``)."""
+        """All ``int(total_time / dt)`` steps in one launch (``:495-523``).  Like the reference's loop, the run starts at
+        time 0 (``current_time = i * dt`` for ``i`` from 0) from the CURRENT state and previous control, whatever was
+        tracked before, and appends to the recorded lists."""
         num_steps = int(total_time / self.dt)
         bt = self._bt
         bt.state[0].copy_(torch.from_numpy(np.asarray(self.current_state, dtype=np.float64)))
-        first = len(self.controls)
-        bt.step = first
-        rows = first + num_steps + 1
-        states = torch.empty(1, rows, 4, dtype=torch.float64, device=bt.state.device)
-        controls = torch.empty(1, rows - 1, 2, dtype=torch.float64, device=bt.state.device)
+        bt.step = 0
+        states = torch.empty(1, num_steps + 1, 4, dtype=torch.float64, device=bt.state.device)
+        controls = torch.empty(1, num_steps, 2, dtype=torch.float64, device=bt.state.device)
         bt.advance(num_steps, states, controls)
-        st = states[0, first + 1:].cpu().numpy()
-        ct = controls[0, first:].cpu().numpy()
+        st = states[0, 1:].cpu().numpy()
+        ct = controls[0].cpu().numpy()
         for i in range(num_steps):
             self.trajectory.append(st[i].copy())
             self.controls.append(ct[i].copy())
-            self.times.append((first + i) * self.dt + self.dt)
+            self.times.append(i * self.dt + self.dt)
         if num_steps:
             self.current_state = st[-1].copy()
         return np.array(self.times), np.array(self.trajectory), np.array(self.controls)
