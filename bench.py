@@ -98,6 +98,8 @@ def traffic_from_profile(kernel: str):
     import re
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_prof_*.txt")), reverse=True):
+        if path.endswith("_long.txt"):      # captures of the long-trajectory instantiations (T = 100): another workload
+            continue
         try:
             text = open(path).read()
         except OSError:
